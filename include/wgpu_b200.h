@@ -1,0 +1,308 @@
+/*
+ * wgpu_b200.h -- C ABI of the B200-native render-pass backend.
+ *
+ * This is the drop-in boundary for wgpu-cpu's render-pass draw path: every entry point below
+ * is what one method of wgpu-cpu's `impl wgpu::custom::*Interface for ...` blocks would bind
+ * (the Rust host crate becomes a thin caller), and each cites the
+ * reference interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - objects are opaque, reference counted handles (mirrors the reference's `Clone` over `Arc`,
+ *     buffer.rs:22-29, pipeline.rs:51-54): wgb_retain / wgb_release; command buffers keep the
+ *     resources they use alive until they have executed;
+ *   - every call returns a wgb_status (0 = ok) and never unwinds or aborts across the boundary;
+ *     wgb_last_error() returns a thread-local description of the last failure.  Where the
+ *     reference `todo!()`s or panics the call returns WGB_ERROR_UNSUPPORTED / WGB_ERROR_VALIDATION;
+ *   - all calls are thread safe; submissions execute in submission order on one CUDA stream per
+ *     device (engine.rs:26-36 executes them in order on one thread);
+ *   - plain pointers and sizes only.  There is no CPU fallback: without a CUDA device
+ *     wgb_adapter_request_device fails.
+ */
+#ifndef WGPU_B200_H
+#define WGPU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WGB_API __attribute__((visibility("default")))
+
+typedef int32_t wgb_status;
+enum {
+    WGB_OK = 0,
+    WGB_ERROR_VALIDATION = 1,    /* the reference would panic / assert */
+    WGB_ERROR_UNSUPPORTED = 2,   /* the reference `todo!()`s, or a state combination this backend does not run */
+    WGB_ERROR_OUT_OF_MEMORY = 3,
+    WGB_ERROR_DEVICE = 4,        /* CUDA / NVRTC failure (no device, compile error, launch error) */
+    WGB_ERROR_SHADER = 5,        /* WGSL translation or CUDA compilation of a shader failed */
+    WGB_ERROR_OUT_OF_BOUNDS = 6, /* an index / vertex fetch left its buffer (the reference panics on the slice) */
+    WGB_ERROR_TIMEOUT = 7
+};
+
+typedef struct wgb_object_t* wgb_object; /* any handle */
+typedef struct wgb_instance_t* wgb_instance;
+typedef struct wgb_adapter_t* wgb_adapter;
+typedef struct wgb_device_t* wgb_device;
+typedef struct wgb_queue_t* wgb_queue;
+typedef struct wgb_buffer_t* wgb_buffer;
+typedef struct wgb_texture_t* wgb_texture;
+typedef struct wgb_texture_view_t* wgb_texture_view;
+typedef struct wgb_sampler_t* wgb_sampler;
+typedef struct wgb_shader_module_t* wgb_shader_module;
+typedef struct wgb_bind_group_layout_t* wgb_bind_group_layout;
+typedef struct wgb_pipeline_layout_t* wgb_pipeline_layout;
+typedef struct wgb_bind_group_t* wgb_bind_group;
+typedef struct wgb_render_pipeline_t* wgb_render_pipeline;
+typedef struct wgb_command_encoder_t* wgb_command_encoder;
+typedef struct wgb_render_pass_t* wgb_render_pass;
+typedef struct wgb_command_buffer_t* wgb_command_buffer;
+
+/* ---- enumerations (names follow wgpu-types) ---- */
+enum { WGB_TOPOLOGY_POINT_LIST = 0, WGB_TOPOLOGY_LINE_LIST = 1, WGB_TOPOLOGY_LINE_STRIP = 2,
+       WGB_TOPOLOGY_TRIANGLE_LIST = 3, WGB_TOPOLOGY_TRIANGLE_STRIP = 4 };
+enum { WGB_INDEX_FORMAT_NONE = 0, WGB_INDEX_FORMAT_UINT16 = 1, WGB_INDEX_FORMAT_UINT32 = 2 };
+enum { WGB_FRONT_FACE_CCW = 0, WGB_FRONT_FACE_CW = 1 };
+enum { WGB_CULL_MODE_NONE = 0, WGB_CULL_MODE_FRONT = 1, WGB_CULL_MODE_BACK = 2 };
+enum { WGB_POLYGON_MODE_FILL = 0, WGB_POLYGON_MODE_LINE = 1, WGB_POLYGON_MODE_POINT = 2 };
+enum { WGB_COMPARE_NEVER = 1, WGB_COMPARE_LESS = 2, WGB_COMPARE_EQUAL = 3, WGB_COMPARE_LESS_EQUAL = 4,
+       WGB_COMPARE_GREATER = 5, WGB_COMPARE_NOT_EQUAL = 6, WGB_COMPARE_GREATER_EQUAL = 7, WGB_COMPARE_ALWAYS = 8 };
+enum { WGB_TEXTURE_FORMAT_RGBA8_UNORM = 0, WGB_TEXTURE_FORMAT_RGBA8_UNORM_SRGB = 1,
+       WGB_TEXTURE_FORMAT_BGRA8_UNORM = 2, WGB_TEXTURE_FORMAT_BGRA8_UNORM_SRGB = 3,
+       WGB_TEXTURE_FORMAT_R8_UNORM = 4, WGB_TEXTURE_FORMAT_RG8_UNORM = 5,
+       WGB_TEXTURE_FORMAT_RGBA8_SNORM = 6, WGB_TEXTURE_FORMAT_DEPTH32_FLOAT = 7 };
+enum { WGB_ADDRESS_MODE_CLAMP_TO_EDGE = 0, WGB_ADDRESS_MODE_REPEAT = 1, WGB_ADDRESS_MODE_MIRROR_REPEAT = 2,
+       WGB_ADDRESS_MODE_CLAMP_TO_BORDER = 3 };
+enum { WGB_FILTER_MODE_NEAREST = 0, WGB_FILTER_MODE_LINEAR = 1 };
+enum { WGB_VERTEX_STEP_MODE_VERTEX = 0, WGB_VERTEX_STEP_MODE_INSTANCE = 1 };
+enum { WGB_VERTEX_FORMAT_FLOAT32 = 0, WGB_VERTEX_FORMAT_FLOAT32X2 = 1, WGB_VERTEX_FORMAT_FLOAT32X3 = 2,
+       WGB_VERTEX_FORMAT_FLOAT32X4 = 3, WGB_VERTEX_FORMAT_UINT32 = 4, WGB_VERTEX_FORMAT_SINT32 = 5 };
+enum { WGB_LOAD_OP_CLEAR = 0, WGB_LOAD_OP_LOAD = 1 };
+enum { WGB_STORE_OP_STORE = 0, WGB_STORE_OP_DISCARD = 1 };
+enum { WGB_SHADER_STAGE_VERTEX = 1, WGB_SHADER_STAGE_FRAGMENT = 2 };
+enum { WGB_BINDING_BUFFER = 1, WGB_BINDING_TEXTURE_VIEW = 2, WGB_BINDING_SAMPLER = 3 };
+enum { WGB_MAP_MODE_READ = 1, WGB_MAP_MODE_WRITE = 2 };
+/* wgpu::BufferUsages bits */
+enum { WGB_BUFFER_USAGE_MAP_READ = 1, WGB_BUFFER_USAGE_MAP_WRITE = 2, WGB_BUFFER_USAGE_COPY_SRC = 4,
+       WGB_BUFFER_USAGE_COPY_DST = 8, WGB_BUFFER_USAGE_INDEX = 16, WGB_BUFFER_USAGE_VERTEX = 32,
+       WGB_BUFFER_USAGE_UNIFORM = 64, WGB_BUFFER_USAGE_STORAGE = 128 };
+enum { WGB_POLL_OK = 0, WGB_POLL_QUEUE_EMPTY = 1, WGB_POLL_TIMEOUT = 2 };
+#define WGB_WHOLE_SIZE UINT64_MAX
+#define WGB_SUBMISSION_ANY UINT64_MAX
+
+/* ---- error reporting ---- */
+WGB_API const char* wgb_last_error(void);
+WGB_API void wgb_retain(wgb_object obj);
+WGB_API void wgb_release(wgb_object obj);
+/* version / build information: "wgpu-b200 <n> sm_100a" */
+WGB_API const char* wgb_version(void);
+
+/* ---- instance / adapter / device ---- */
+/* replaces wgpu_cpu::instance(Config) (wgpu-cpu/src/lib.rs:22-27), InstanceConfig (instance.rs:23-26) */
+typedef struct { uint32_t reserved; } wgb_instance_config;
+WGB_API wgb_status wgb_create_instance(const wgb_instance_config* config, wgb_instance* out);
+/* InstanceInterface::request_adapter / enumerate_adapters (instance.rs:72-110) */
+WGB_API wgb_status wgb_instance_request_adapter(wgb_instance instance, wgb_adapter* out);
+/* AdapterInterface::get_info (adapter.rs:60-75): name, device type, backend */
+typedef struct {
+    char name[128];          /* "wgpu-b200 (<CUDA device name>)" */
+    uint32_t device_type;    /* 1 = discrete GPU (wgpu::DeviceType::DiscreteGpu) */
+    uint32_t cuda_device_count;
+} wgb_adapter_info;
+WGB_API wgb_status wgb_adapter_get_info(wgb_adapter adapter, wgb_adapter_info* out);
+/* AdapterInterface::request_device -> create_device_and_queue (adapter.rs:24-42, device.rs:40-74).
+ * The descriptor adds what the reference's empty Config gains on a multi-GPU box:
+ * the CUDA ordinal and this device's share of a sort-first screen partition. */
+typedef struct {
+    int32_t cuda_device;     /* CUDA ordinal; -1 = the calling thread's current device */
+    uint32_t band_rank;      /* this device renders tile-row band `band_rank` ... */
+    uint32_t band_count;     /* ... of `band_count` contiguous bands (0 or 1 = whole framebuffer) */
+} wgb_device_descriptor;
+WGB_API wgb_status wgb_adapter_request_device(wgb_adapter adapter, const wgb_device_descriptor* desc,
+                                              wgb_device* out_device, wgb_queue* out_queue);
+/* DeviceInterface::poll (device.rs:237-295): wait != 0 blocks until `submission_index` (or, for
+ * WGB_SUBMISSION_ANY, the next completion) has left the in-flight set; *out_poll is WGB_POLL_*.
+ * An error raised while a submission executed (the reference would have panicked on its engine
+ * thread) is returned here. */
+WGB_API wgb_status wgb_device_poll(wgb_device device, int32_t wait, uint64_t submission_index, uint64_t timeout_ns,
+                                   int32_t* out_poll);
+
+/* ---- buffers ---- */
+/* DeviceInterface::create_buffer (device.rs:150-160) + Buffer (buffer.rs:23-109).  The reference always
+ * creates buffers mapped for writing regardless of mapped_at_creation (buffer.rs:36-38); here the flag is honoured. */
+typedef struct { uint64_t size; uint32_t usage; uint32_t mapped_at_creation; } wgb_buffer_descriptor;
+WGB_API wgb_status wgb_device_create_buffer(wgb_device device, const wgb_buffer_descriptor* desc, wgb_buffer* out);
+/* BufferInterface::map_async (buffer.rs:112-135): completes before returning; callback may be NULL */
+typedef void (*wgb_map_callback)(wgb_status status, void* userdata);
+WGB_API wgb_status wgb_buffer_map_async(wgb_buffer buffer, uint32_t mode, uint64_t offset, uint64_t size,
+                                        wgb_map_callback callback, void* userdata);
+/* BufferInterface::get_mapped_range (buffer.rs:137-160): host pointer valid until unmap */
+WGB_API wgb_status wgb_buffer_get_mapped_range(wgb_buffer buffer, uint64_t offset, uint64_t size, void** out_ptr);
+/* BufferInterface::unmap (buffer.rs:162-172): uploads a write mapping to the device */
+WGB_API wgb_status wgb_buffer_unmap(wgb_buffer buffer);
+/* QueueInterface::write_buffer (device.rs:332-344): immediate, ordered after earlier submissions */
+WGB_API wgb_status wgb_queue_write_buffer(wgb_queue queue, wgb_buffer buffer, uint64_t offset, const void* data, uint64_t size);
+
+/* ---- textures / samplers ---- */
+/* DeviceInterface::create_texture (device.rs:162-175), Texture::new (texture.rs:28-50) */
+typedef struct {
+    uint32_t width, height, depth_or_array_layers;
+    uint32_t mip_level_count, sample_count;
+    uint32_t format;
+    uint32_t usage;
+} wgb_texture_descriptor;
+WGB_API wgb_status wgb_device_create_texture(wgb_device device, const wgb_texture_descriptor* desc, wgb_texture* out);
+/* TextureInterface::create_view (texture.rs:52-75); desc may be NULL (default view) */
+typedef struct { uint32_t base_array_layer; uint32_t reserved; } wgb_texture_view_descriptor;
+WGB_API wgb_status wgb_texture_create_view(wgb_texture texture, const wgb_texture_view_descriptor* desc, wgb_texture_view* out);
+/* QueueInterface::write_texture (device.rs:371-434): mip 0, all aspects.  Copies `height` rows of
+ * width*bytes_per_texel bytes from rows `bytes_per_row` apart (0 = tightly packed) to origin (x, y). */
+WGB_API wgb_status wgb_queue_write_texture(wgb_queue queue, wgb_texture texture, uint32_t x, uint32_t y,
+                                           const void* data, uint64_t data_size, uint32_t bytes_per_row,
+                                           uint32_t width, uint32_t height);
+/* Read-back of a texture's texels, row-major and tightly packed: what wgpu_cpu::dump_texture /
+ * image::rgba_texture_image observe (lib.rs:111-173).  Waits for earlier submissions. */
+WGB_API wgb_status wgb_texture_read(wgb_texture texture, void* dst, uint64_t dst_size);
+/* device address of the texel storage (linear, row-major), for collectives over NVLink */
+WGB_API wgb_status wgb_texture_device_pointer(wgb_texture texture, uint64_t* out_ptr, uint64_t* out_size);
+/* DeviceInterface::create_sampler (device.rs:177-180), Sampler (sampler.rs:4-27) */
+typedef struct {
+    uint32_t address_mode_u, address_mode_v, address_mode_w;
+    uint32_t mag_filter, min_filter, mipmap_filter;
+} wgb_sampler_descriptor;
+WGB_API wgb_status wgb_device_create_sampler(wgb_device device, const wgb_sampler_descriptor* desc, wgb_sampler* out);
+
+/* ---- shaders ---- */
+/* DeviceInterface::create_shader_module (device.rs:88-100): WGSL source.  Entry points are translated to
+ * CUDA C++ at pipeline creation (the replacement of naga-cranelift's compile_jit, lib.rs:83-113).  A caller
+ * that already holds emitter output for an entry point (the Rust host's naga-IR emitter) passes it in
+ * `emitted` and the WGSL front end is skipped for that entry point. */
+typedef struct { uint32_t stage; const char* entry_point; const char* cuda_source; } wgb_emitted_entry_point;
+typedef struct {
+    const char* wgsl;                          /* may be NULL if every used entry point is in `emitted` */
+    uint32_t emitted_count;
+    const wgb_emitted_entry_point* emitted;
+} wgb_shader_module_descriptor;
+WGB_API wgb_status wgb_device_create_shader_module(wgb_device device, const wgb_shader_module_descriptor* desc,
+                                                   wgb_shader_module* out);
+/* the WGSL -> CUDA C++ emitter on its own (no device needed); *out_cuda is malloc'ed, free with wgb_free */
+WGB_API wgb_status wgb_translate_wgsl(const char* wgsl, uint32_t stage, const char* entry_point, char** out_cuda);
+WGB_API void wgb_free(void* p);
+
+/* ---- binding model ---- */
+/* DeviceInterface::create_bind_group_layout / create_pipeline_layout (device.rs:102-127): descriptors are kept, not interpreted */
+typedef struct { uint32_t binding; uint32_t visibility; uint32_t kind; } wgb_bind_group_layout_entry;
+WGB_API wgb_status wgb_device_create_bind_group_layout(wgb_device device, const wgb_bind_group_layout_entry* entries,
+                                                       uint32_t count, wgb_bind_group_layout* out);
+WGB_API wgb_status wgb_device_create_pipeline_layout(wgb_device device, const wgb_bind_group_layout* layouts,
+                                                     uint32_t count, wgb_pipeline_layout* out);
+/* DeviceInterface::create_bind_group (device.rs:109-116), BindGroup (bind_group.rs:52-117) */
+typedef struct {
+    uint32_t binding;
+    uint32_t kind;                 /* WGB_BINDING_* */
+    wgb_buffer buffer; uint64_t offset; uint64_t size;   /* size WGB_WHOLE_SIZE = to the end */
+    wgb_texture_view texture_view;
+    wgb_sampler sampler;
+} wgb_bind_group_entry;
+WGB_API wgb_status wgb_device_create_bind_group(wgb_device device, wgb_bind_group_layout layout,
+                                                const wgb_bind_group_entry* entries, uint32_t count, wgb_bind_group* out);
+
+/* ---- render pipeline ---- */
+typedef struct { uint32_t format; uint64_t offset; uint32_t shader_location; } wgb_vertex_attribute;
+typedef struct { uint64_t array_stride; uint32_t step_mode; uint32_t attribute_count; const wgb_vertex_attribute* attributes; } wgb_vertex_buffer_layout;
+typedef struct { uint32_t format; uint32_t has_blend; uint32_t write_mask; } wgb_color_target_state;
+typedef struct {
+    wgb_pipeline_layout layout;                /* may be NULL */
+    /* VertexState (render_pass/vertex.rs:43-93) */
+    wgb_shader_module vertex_module; const char* vertex_entry_point;
+    uint32_t vertex_buffer_count; const wgb_vertex_buffer_layout* vertex_buffers;
+    /* PrimitiveState (state.rs:433-478) */
+    uint32_t topology, strip_index_format, front_face, cull_mode, polygon_mode;
+    uint32_t unclipped_depth, conservative;
+    /* DepthStencilState (fragment.rs:427-453); has_depth_stencil = 0 -> no depth test */
+    uint32_t has_depth_stencil, depth_format, depth_write_enabled, depth_compare;
+    uint32_t multisample_count;
+    /* FragmentState (render_pass/fragment.rs:61-89); fragment_module NULL -> vertex stage only (state.rs:583-588) */
+    wgb_shader_module fragment_module; const char* fragment_entry_point;
+    uint32_t target_count; const wgb_color_target_state* targets;
+} wgb_render_pipeline_descriptor;
+/* DeviceInterface::create_render_pipeline (device.rs:129-134) -> RenderPipeline::new (pipeline.rs:57-76):
+ * translates both entry points and compiles the pipeline's kernels for sm_100a with NVRTC. */
+WGB_API wgb_status wgb_device_create_render_pipeline(wgb_device device, const wgb_render_pipeline_descriptor* desc,
+                                                     wgb_render_pipeline* out);
+/* the generated CUDA translation unit of the pipeline (diagnostics; *out is malloc'ed) */
+WGB_API wgb_status wgb_render_pipeline_get_source(wgb_render_pipeline pipeline, char** out);
+
+/* ---- command encoding ---- */
+/* DeviceInterface::create_command_encoder (device.rs:190-196), CommandEncoder (command.rs:11-171) */
+WGB_API wgb_status wgb_device_create_command_encoder(wgb_device device, wgb_command_encoder* out);
+typedef struct { wgb_texture_view view; uint32_t load_op, store_op; double clear_value[4]; } wgb_color_attachment;
+typedef struct { wgb_texture_view view; uint32_t has_depth_ops, depth_load_op, depth_store_op; float depth_clear_value;
+                 uint32_t has_stencil_ops; } wgb_depth_stencil_attachment;
+typedef struct {
+    uint32_t color_attachment_count; const wgb_color_attachment* color_attachments;   /* view NULL = empty slot */
+    const wgb_depth_stencil_attachment* depth_stencil_attachment;                       /* may be NULL */
+} wgb_render_pass_descriptor;
+/* CommandEncoderInterface::begin_render_pass (command.rs:82-87) -> RenderPassEncoder::new (render_pass/mod.rs:53-70) */
+WGB_API wgb_status wgb_command_encoder_begin_render_pass(wgb_command_encoder encoder, const wgb_render_pass_descriptor* desc,
+                                                         wgb_render_pass* out);
+/* RenderPassInterface (render_pass/mod.rs:73-176): every call records one RenderPassSubCommand */
+WGB_API wgb_status wgb_render_pass_set_pipeline(wgb_render_pass pass, wgb_render_pipeline pipeline);
+WGB_API wgb_status wgb_render_pass_set_bind_group(wgb_render_pass pass, uint32_t index, wgb_bind_group group,
+                                                  const uint32_t* dynamic_offsets, uint32_t dynamic_offset_count);
+WGB_API wgb_status wgb_render_pass_set_index_buffer(wgb_render_pass pass, wgb_buffer buffer, uint32_t index_format,
+                                                    uint64_t offset, uint64_t size);
+WGB_API wgb_status wgb_render_pass_set_vertex_buffer(wgb_render_pass pass, uint32_t slot, wgb_buffer buffer,
+                                                     uint64_t offset, uint64_t size);
+WGB_API wgb_status wgb_render_pass_set_viewport(wgb_render_pass pass, float x, float y, float width, float height,
+                                                float min_depth, float max_depth);
+WGB_API wgb_status wgb_render_pass_set_scissor_rect(wgb_render_pass pass, uint32_t x, uint32_t y, uint32_t width, uint32_t height);
+WGB_API wgb_status wgb_render_pass_set_blend_constant(wgb_render_pass pass, const double color[4]);
+WGB_API wgb_status wgb_render_pass_set_stencil_reference(wgb_render_pass pass, uint32_t reference);
+WGB_API wgb_status wgb_render_pass_draw(wgb_render_pass pass, uint32_t first_vertex, uint32_t vertex_count,
+                                        uint32_t first_instance, uint32_t instance_count);
+WGB_API wgb_status wgb_render_pass_draw_indexed(wgb_render_pass pass, uint32_t first_index, uint32_t index_count,
+                                                int32_t base_vertex, uint32_t first_instance, uint32_t instance_count);
+/* RenderPassInterface::end (render_pass/mod.rs:309-329): pushes Command::RenderPass into the encoder */
+WGB_API wgb_status wgb_render_pass_end(wgb_render_pass pass);
+/* CommandEncoderInterface::finish (command.rs:89-98) */
+WGB_API wgb_status wgb_command_encoder_finish(wgb_command_encoder encoder, wgb_command_buffer* out);
+/* QueueInterface::submit (device.rs:436-462): monotonically increasing submission index */
+WGB_API wgb_status wgb_queue_submit(wgb_queue queue, const wgb_command_buffer* command_buffers, uint32_t count,
+                                    uint64_t* out_submission_index);
+
+/* ---- measurement (mirrors the reference's per-pass Instant timer and per-draw counters,
+ *      render_pass/mod.rs:346,392-393 and state.rs:516-517,592) ---- */
+typedef struct {
+    uint64_t primitives;          /* submitted (assembled) primitives */
+    uint64_t fragments;           /* rasterised fragments = the reference's fragment-stage invocations */
+    uint64_t shaded;              /* fragment-shader invocations this backend ran for surviving fragments */
+    uint64_t bin_pairs;           /* (primitive, tile) pairs in the per-tile bins */
+    uint64_t big_primitives;      /* primitives on the all-tiles list */
+    uint64_t clipped_primitives;  /* primitives that went through the clipper */
+    uint64_t clip_records;
+    uint32_t draws, kernel_launches;
+    float geometry_ms;            /* geometry + clip + scan + fill kernels (CUDA events) */
+    float tile_ms;                /* tile kernels */
+    float total_ms;               /* whole pass on the device */
+    uint32_t replays;             /* draws replayed after growing a work buffer */
+} wgb_pass_stats;
+/* statistics of the most recently executed render pass on this device */
+WGB_API wgb_status wgb_device_get_last_pass_stats(wgb_device device, wgb_pass_stats* out);
+/* parity instrumentation: when enabled, every pass also accumulates a per-pixel count of rasterised
+ * fragments (the coverage the reference's rasteriser emits), readable with wgb_device_read_coverage */
+WGB_API wgb_status wgb_device_set_coverage_capture(wgb_device device, int32_t enabled);
+WGB_API wgb_status wgb_device_read_coverage(wgb_device device, uint32_t* dst, uint64_t pixel_count);
+/* change this device's share of the sort-first partition (see wgb_device_descriptor) */
+WGB_API wgb_status wgb_device_set_band(wgb_device device, uint32_t band_rank, uint32_t band_count);
+/* first and one-past-last pixel row of the band for a framebuffer of `height` rows */
+WGB_API wgb_status wgb_device_get_band_rows(wgb_device device, uint32_t height, uint32_t* out_row0, uint32_t* out_row1);
+/* the CUDA stream submissions run on (cudaStream_t), for interop with collectives */
+WGB_API wgb_status wgb_device_get_stream(wgb_device device, void** out_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,138 @@
+"""Parity of the B200 draw path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): coverage masks and depth-test outcomes bit-exact, shaded colour
+within 1 LSB for unorm8 targets -- the tests below demand byte-exact colour as well, since both
+sides run the same IEEE operation sequence."""
+import numpy as np
+import pytest
+
+from wgpu_cpu_b200 import scenes as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from wgpu_cpu_b200 import api
+    dev, queue = api.instance().request_adapter().request_device(0)
+    return dev, queue
+
+
+def _compare(scene, gpu, use_emitted=True):
+    from oracle import pyoracle
+    from wgpu_cpu_b200.render import render_scene
+    dev, queue = gpu
+    ref = pyoracle.render(scene)
+    got = render_scene(dev, queue, scene, want_coverage=True, use_emitted=use_emitted)
+    msg = []
+    if not np.array_equal(got.coverage, ref.coverage):
+        bad = np.argwhere(got.coverage != ref.coverage)
+        msg.append(f"coverage differs at {len(bad)} pixels, first (y,x)={bad[:5].tolist()} "
+                   f"got={got.coverage[tuple(bad[0])]} ref={ref.coverage[tuple(bad[0])]}")
+    if ref.depth is not None:
+        gd, rd = got.depth.view(np.uint32), ref.depth.view(np.uint32)
+        if not np.array_equal(gd, rd):
+            bad = np.argwhere(gd != rd)
+            msg.append(f"depth differs at {len(bad)} pixels, first (y,x)={bad[:5].tolist()} "
+                       f"got={got.depth[tuple(bad[0])]!r} ref={ref.depth[tuple(bad[0])]!r}")
+    if not np.array_equal(got.color, ref.color):
+        bad = np.argwhere((got.color != ref.color).any(axis=2))
+        msg.append(f"colour differs at {len(bad)} pixels, first (y,x)={bad[:5].tolist()} "
+                   f"got={got.color[tuple(bad[0])].tolist()} ref={ref.color[tuple(bad[0])].tolist()}")
+    assert not msg, f"{scene.name}: " + "; ".join(msg)
+    assert got.stats["fragments"] == ref.stats["fragments_shaded"] or scene.shader in ("features",), \
+        f"{scene.name}: fragment count {got.stats['fragments']} != {ref.stats['fragments_shaded']}"
+    return got, ref
+
+
+@pytest.mark.parametrize("variant", ["default", "cull_front", "draw_backwards", "draw_backwards_no_cull", "lines"])
+def test_colored_triangle(gpu, variant):
+    _compare(S.colored_triangle(variant), gpu)
+
+
+def test_colored_triangle_golden_identities(gpu):
+    """tests/reference/*.png are LFS pointers; their oids still pin A == D and B == C == clear."""
+    from wgpu_cpu_b200.render import render_scene
+    dev, queue = gpu
+    img = {v: render_scene(dev, queue, S.colored_triangle(v), use_emitted=True).color
+           for v in ["default", "cull_front", "draw_backwards", "draw_backwards_no_cull"]}
+    assert np.array_equal(img["default"], img["draw_backwards_no_cull"])
+    assert np.array_equal(img["cull_front"], img["draw_backwards"])
+    assert (img["cull_front"][..., :3] == 0).all() and (img["cull_front"][..., 3] == 255).all()
+    assert img["default"][..., :3].any()
+
+
+def test_hello_mesh_c1(gpu):
+    _compare(S.hello_mesh(512, 512), gpu)
+
+
+def test_hello_texture_c2_small(gpu):
+    _compare(S.hello_texture(640, 360), gpu)
+
+
+def test_synthetic_c3_small(gpu):
+    _compare(S.synthetic_grid(384, 216, n=113, layers=4), gpu)
+
+
+def test_procedural_c4_small(gpu):
+    _compare(S.procedural(480, 270), gpu)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_triangles_clipped(gpu, seed):
+    got, ref = _compare(S.random_triangles(seed=seed), gpu)
+    assert got.stats["clipped_primitives"] > 0
+
+
+@pytest.mark.parametrize("compare,write", [("less", True), ("less-equal", True), ("greater", True), ("greater-equal", True),
+                                           ("always", True), ("always", False), ("never", True), ("less", False),
+                                           ("equal", True), ("not-equal", False), ("greater", False)])
+def test_depth_modes(gpu, compare, write):
+    s = S.random_triangles(count=150, seed=41, depth_compare=compare, depth_write=write,
+                           clear_depth=0.5 if compare in ("greater", "greater-equal", "equal", "not-equal") else 1.0)
+    s.name += f"_{compare}_{int(write)}"
+    _compare(s, gpu)
+
+
+def test_no_depth_attachment_last_wins(gpu):
+    s = S.random_triangles(count=200, seed=43, has_depth=False, clear_depth=None, depth_compare=None, depth_write=False)
+    _compare(s, gpu)
+
+
+@pytest.mark.parametrize("index_format,restart", [("uint16", True), ("uint32", True), ("uint16", False)])
+def test_triangle_strip(gpu, index_format, restart):
+    _compare(S.quad_strip(index_format=index_format, restart=restart), gpu)
+
+
+@pytest.mark.parametrize("topology", ["line-list", "line-strip"])
+def test_lines(gpu, topology):
+    _compare(S.random_lines(topology=topology), gpu)
+
+
+def test_points(gpu):
+    _compare(S.random_points(), gpu)
+
+
+def test_features_instancing_flat_discard(gpu):
+    _compare(S.features(), gpu)
+
+
+def test_frag_depth(gpu):
+    _compare(S.frag_depth(), gpu)
+
+
+def test_viewport_and_scissor(gpu):
+    s = S.random_triangles(count=120, seed=47)
+    s.viewport = (20.0, 10.0, 200.0, 150.0, 0.0, 1.0)
+    s.scissor = (40, 30, 120, 90)
+    s.name += "_vp_sc"
+    _compare(s, gpu)
+
+
+def test_load_op_load(gpu):
+    rng = np.random.default_rng(3)
+    s = S.random_triangles(count=100, seed=49, clear_color=None, clear_depth=None)
+    s.initial_color = rng.integers(0, 255, (s.height, s.width, 4), dtype=np.uint8)
+    s.initial_depth = rng.random((s.height, s.width), dtype=np.float32)
+    s.name += "_load"
+    _compare(s, gpu)

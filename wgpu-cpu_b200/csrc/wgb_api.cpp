@@ -1,0 +1,1534 @@
+// wgb_api.cpp -- host runtime behind include/wgpu_b200.h.
+//
+// Mirrors wgpu-cpu's backend objects (instance/adapter/device/queue, buffers, textures, samplers,
+// shader modules, bind groups, render pipelines, command encoder / render pass) as thin host-side
+// handles whose storage lives in B200 device memory, records render passes exactly like the
+// reference's RenderPassEncoder (render_pass/mod.rs:46-322), and executes them as CUDA kernel
+// sequences on one stream per device.  All arithmetic of the draw path is in wgb_raster.cuh; the
+// kernels are compiled per pipeline with NVRTC for sm_100a.  There is no CPU fallback.
+#include "../../include/wgpu_b200.h"
+#include "wgb_shared.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+extern const char* const wgb_embedded_shared_h;
+extern const char* const wgb_embedded_prelude_cuh;
+extern const char* const wgb_embedded_raster_cuh;
+// wgsl_emit.cpp
+std::string wgb_emit_wgsl(const std::string& wgsl, uint32_t stage, const std::string& entry_point);
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+thread_local std::string g_last_error;
+
+struct Error : std::runtime_error {
+    wgb_status status;
+    Error(wgb_status s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+[[noreturn]] void fail(wgb_status s, const char* fmt, ...) {
+    char buf[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    throw Error(s, buf);
+}
+#define CUDA_CHECK(expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess) fail(e_ == cudaErrorMemoryAllocation ? WGB_ERROR_OUT_OF_MEMORY : WGB_ERROR_DEVICE, \
+                                    "%s failed: %s", #expr, cudaGetErrorString(e_));                  \
+    } while (0)
+
+template <class F>
+wgb_status guarded(F f) {
+    try {
+        f();
+        return WGB_OK;
+    } catch (const Error& e) {
+        g_last_error = e.what();
+        return e.status;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "host allocation failed";
+        return WGB_ERROR_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return WGB_ERROR_DEVICE;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return WGB_ERROR_DEVICE;
+    }
+}
+#define REQUIRE(cond, ...) do { if (!(cond)) fail(WGB_ERROR_VALIDATION, __VA_ARGS__); } while (0)
+
+// ------------------------------------------------------------------------------------------
+// reference-counted objects
+// ------------------------------------------------------------------------------------------
+struct Object {
+    std::atomic<int> rc{1};
+    virtual ~Object() {}
+};
+template <class T>
+struct Ref {
+    T* p = nullptr;
+    Ref() {}
+    Ref(T* q) : p(q) { if (p) p->rc.fetch_add(1); }
+    Ref(const Ref& o) : p(o.p) { if (p) p->rc.fetch_add(1); }
+    Ref(Ref&& o) noexcept : p(o.p) { o.p = nullptr; }
+    Ref& operator=(Ref o) { std::swap(p, o.p); return *this; }
+    ~Ref() { if (p && p->rc.fetch_sub(1) == 1) delete p; }
+    T* operator->() const { return p; }
+    T* get() const { return p; }
+    explicit operator bool() const { return p != nullptr; }
+};
+template <class T, class H>
+T* from_handle(H h, const char* what) {
+    if (!h) fail(WGB_ERROR_VALIDATION, "null %s handle", what);
+    T* t = dynamic_cast<T*>(reinterpret_cast<Object*>(h));
+    if (!t) fail(WGB_ERROR_VALIDATION, "handle is not a %s", what);
+    return t;
+}
+template <class H, class T>
+H to_handle(T* t) { return reinterpret_cast<H>(static_cast<Object*>(t)); }
+
+// ------------------------------------------------------------------------------------------
+// CUDA driver entry points (through the statically linked runtime, so the library loads on
+// machines without libcuda) and NVRTC (dlopen'ed on first use)
+// ------------------------------------------------------------------------------------------
+struct DriverApi {
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    bool loaded = false;
+};
+DriverApi g_drv;
+std::mutex g_global_mu;
+
+void load_driver_api() {
+    std::lock_guard<std::mutex> lk(g_global_mu);
+    if (g_drv.loaded) return;
+    auto get = [](const char* name, void** fn) {
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fn)
+            fail(WGB_ERROR_DEVICE, "cudaGetDriverEntryPoint(%s) failed: %s", name, cudaGetErrorString(e));
+    };
+    get("cuModuleLoadData", (void**)&g_drv.ModuleLoadData);
+    get("cuModuleUnload", (void**)&g_drv.ModuleUnload);
+    get("cuModuleGetFunction", (void**)&g_drv.ModuleGetFunction);
+    get("cuLaunchKernel", (void**)&g_drv.LaunchKernel);
+    get("cuGetErrorString", (void**)&g_drv.GetErrorString);
+    g_drv.loaded = true;
+}
+const char* cu_error(CUresult r) {
+    const char* s = nullptr;
+    if (g_drv.GetErrorString) g_drv.GetErrorString(r, &s);
+    return s ? s : "unknown CUDA driver error";
+}
+
+struct NvrtcApi {
+    void* lib = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    const char* (*GetErrorString)(nvrtcResult) = nullptr;
+};
+NvrtcApi g_nvrtc;
+
+void load_nvrtc() {
+    std::lock_guard<std::mutex> lk(g_global_mu);
+    if (g_nvrtc.lib) return;
+    const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
+                           "/usr/local/cuda/lib64/libnvrtc.so"};
+    void* lib = nullptr;
+    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (lib) break; }
+    if (!lib) fail(WGB_ERROR_DEVICE, "cannot load NVRTC (libnvrtc.so.12): %s", dlerror());
+    auto sym = [&](const char* n) { void* p = dlsym(lib, n); if (!p) fail(WGB_ERROR_DEVICE, "NVRTC symbol %s missing", n); return p; };
+    g_nvrtc.CreateProgram = (decltype(g_nvrtc.CreateProgram))sym("nvrtcCreateProgram");
+    g_nvrtc.DestroyProgram = (decltype(g_nvrtc.DestroyProgram))sym("nvrtcDestroyProgram");
+    g_nvrtc.CompileProgram = (decltype(g_nvrtc.CompileProgram))sym("nvrtcCompileProgram");
+    g_nvrtc.GetCUBINSize = (decltype(g_nvrtc.GetCUBINSize))sym("nvrtcGetCUBINSize");
+    g_nvrtc.GetCUBIN = (decltype(g_nvrtc.GetCUBIN))sym("nvrtcGetCUBIN");
+    g_nvrtc.GetProgramLogSize = (decltype(g_nvrtc.GetProgramLogSize))sym("nvrtcGetProgramLogSize");
+    g_nvrtc.GetProgramLog = (decltype(g_nvrtc.GetProgramLog))sym("nvrtcGetProgramLog");
+    g_nvrtc.GetErrorString = (decltype(g_nvrtc.GetErrorString))sym("nvrtcGetErrorString");
+    g_nvrtc.lib = lib;
+}
+
+// compile one pipeline translation unit to an sm_100a cubin
+std::vector<char> nvrtc_compile(const std::string& source) {
+    load_nvrtc();
+    const char* header_names[] = {"wgb_shared.h", "wgb_prelude.cuh", "wgb_raster.cuh"};
+    const char* headers[] = {wgb_embedded_shared_h, wgb_embedded_prelude_cuh, wgb_embedded_raster_cuh};
+    nvrtcProgram prog;
+    nvrtcResult r = g_nvrtc.CreateProgram(&prog, source.c_str(), "wgb_pipeline.cu", 3, headers, header_names);
+    if (r != NVRTC_SUCCESS) fail(WGB_ERROR_DEVICE, "nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(r));
+    // --fmad=false: the reference never fuses a multiply with an add; division and
+    // square root stay IEEE (--prec-div / --prec-sqrt default true), no flush-to-zero
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo", "-w"};
+    r = g_nvrtc.CompileProgram(prog, 5, opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        g_nvrtc.GetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) g_nvrtc.GetProgramLog(prog, &log[0]);
+        g_nvrtc.DestroyProgram(&prog);
+        if (log.size() > 3500) log.resize(3500);
+        fail(WGB_ERROR_SHADER, "NVRTC compilation failed: %s\n%s", g_nvrtc.GetErrorString(r), log.c_str());
+    }
+    size_t n = 0;
+    g_nvrtc.GetCUBINSize(prog, &n);
+    std::vector<char> cubin(n);
+    g_nvrtc.GetCUBIN(prog, cubin.data());
+    g_nvrtc.DestroyProgram(&prog);
+    return cubin;
+}
+
+// ------------------------------------------------------------------------------------------
+// formats
+// ------------------------------------------------------------------------------------------
+uint32_t bytes_per_texel(uint32_t format) {          // texture.rs:457-509
+    switch (format) {
+        case WGB_TEXTURE_FORMAT_R8_UNORM: return 1;
+        case WGB_TEXTURE_FORMAT_RG8_UNORM: return 2;
+        case WGB_TEXTURE_FORMAT_RGBA8_UNORM: case WGB_TEXTURE_FORMAT_RGBA8_UNORM_SRGB:
+        case WGB_TEXTURE_FORMAT_BGRA8_UNORM: case WGB_TEXTURE_FORMAT_BGRA8_UNORM_SRGB:
+        case WGB_TEXTURE_FORMAT_RGBA8_SNORM: case WGB_TEXTURE_FORMAT_DEPTH32_FLOAT: return 4;
+        default: return 0;
+    }
+}
+bool is_color_format(uint32_t f) { return f <= WGB_TEXTURE_FORMAT_RGBA8_SNORM; }
+// TexelWriter::from_color (texture.rs:373-411) for the clear colour, on the host
+uint32_t f32_to_u8(float v) {
+    float s = v * 255.0f;
+    if (!(s == s)) return 0;
+    if (s < 0.0f) s = 0.0f;
+    if (s > 255.0f) s = 255.0f;
+    return (uint32_t)s;
+}
+uint32_t encode_color(const double c[4], uint32_t format) {
+    // wgpu_color_to_vec4 casts the f64 colour to f32 first (texture.rs:505-507)
+    const uint32_t r = f32_to_u8((float)c[0]), g = f32_to_u8((float)c[1]), b = f32_to_u8((float)c[2]), a = f32_to_u8((float)c[3]);
+    if (format == WGB_TEXTURE_FORMAT_BGRA8_UNORM || format == WGB_TEXTURE_FORMAT_BGRA8_UNORM_SRGB)
+        return b | (g << 8) | (r << 16) | (a << 24);
+    return r | (g << 8) | (b << 16) | (a << 24);
+}
+uint32_t vertex_format_size(uint32_t f) {
+    switch (f) {
+        case WGB_VERTEX_FORMAT_FLOAT32: case WGB_VERTEX_FORMAT_UINT32: case WGB_VERTEX_FORMAT_SINT32: return 4;
+        case WGB_VERTEX_FORMAT_FLOAT32X2: return 8;
+        case WGB_VERTEX_FORMAT_FLOAT32X3: return 12;
+        case WGB_VERTEX_FORMAT_FLOAT32X4: return 16;
+        default: return 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// device memory helper
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        CUDA_CHECK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    uint64_t addr() const { return (uint64_t)(uintptr_t)p; }
+};
+
+// kernels of one compiled pipeline variant
+struct KernelSet {
+    CUmodule module = nullptr;
+    CUfunction geometry = nullptr, clip = nullptr, scan = nullptr, fill = nullptr, tile = nullptr, clear = nullptr, strip_map = nullptr;
+};
+
+struct Instance : Object {};
+struct Adapter : Object { Ref<Instance> instance; };
+
+struct Device : Object {
+    int ordinal = -1;
+    bool compile_only = false;
+    cudaStream_t stream = nullptr;
+    std::recursive_mutex mu;
+    uint32_t band_rank = 0, band_count = 1;
+    // submissions (device.rs:436-462, 517-541)
+    uint64_t next_submission = 1;
+    struct InFlight { uint64_t index; cudaEvent_t done; };
+    std::deque<InFlight> inflight;
+    wgb_status deferred_status = WGB_OK;   // error raised while executing a submission
+    std::string deferred_error;
+    // work buffers, grown on demand and reused across passes
+    DevBuf counters, prim_box, slow_list, clip_records, big_list, tile_count, tile_offset, tile_cursor, bins, coverage, strip_map, strip_count;
+    WgbCounters* host_counters = nullptr;   // pinned
+    uint32_t clip_capacity = 0, big_capacity = 0;
+    bool coverage_capture = false;
+    uint32_t coverage_w = 0, coverage_h = 0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    wgb_pass_stats last_stats{};
+    std::map<std::string, std::shared_ptr<KernelSet>> kernel_cache;   // by translation-unit text
+
+    void make_current() const { if (!compile_only) CUDA_CHECK(cudaSetDevice(ordinal)); }
+    ~Device() override {
+        if (compile_only) return;
+        cudaSetDevice(ordinal);
+        if (stream) cudaStreamSynchronize(stream);
+        for (auto& f : inflight) cudaEventDestroy(f.done);
+        for (auto& kv : kernel_cache) if (kv.second->module && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->module);
+        DevBuf* bufs[] = {&counters, &prim_box, &slow_list, &clip_records, &big_list, &tile_count, &tile_offset, &tile_cursor, &bins, &coverage, &strip_map, &strip_count};
+        for (DevBuf* b : bufs) b->release();
+        if (host_counters) cudaFreeHost(host_counters);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+struct Queue : Object { Ref<Device> device; };
+
+struct Buffer : Object {
+    Ref<Device> device;
+    uint64_t size = 0;
+    uint32_t usage = 0;
+    void* dptr = nullptr;
+    std::mutex mu;
+    std::vector<uint8_t> staging;   // host mapping
+    bool mapped = false;
+    uint32_t map_mode = 0;
+    uint64_t map_offset = 0, map_size = 0;
+    ~Buffer() override { if (dptr) { cudaSetDevice(device->ordinal); cudaFree(dptr); } }
+};
+
+struct Texture : Object {
+    Ref<Device> device;
+    wgb_texture_descriptor desc{};
+    uint32_t bpp = 0;
+    uint64_t size = 0;
+    void* dptr = nullptr;
+    cudaTextureObject_t texobj = 0;
+    std::mutex mu;
+    ~Texture() override {
+        if (device->compile_only) return;
+        cudaSetDevice(device->ordinal);
+        if (texobj) cudaDestroyTextureObject(texobj);
+        if (dptr) cudaFree(dptr);
+    }
+    // bindless texture object over the linear texel storage (element fetch, no filtering)
+    cudaTextureObject_t texture_object() {
+        std::lock_guard<std::mutex> lk(mu);
+        if (texobj) return texobj;
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = dptr;
+        rd.res.linear.desc = cudaCreateChannelDesc<uchar4>();
+        rd.res.linear.sizeInBytes = size;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.readMode = cudaReadModeElementType;
+        td.filterMode = cudaFilterModePoint;
+        td.addressMode[0] = cudaAddressModeClamp;
+        td.normalizedCoords = 0;
+        CUDA_CHECK(cudaCreateTextureObject(&texobj, &rd, &td, nullptr));
+        return texobj;
+    }
+};
+struct TextureView : Object { Ref<Texture> texture; uint32_t base_layer = 0; };
+struct Sampler : Object { wgb_sampler_descriptor desc{}; };
+
+struct ShaderModule : Object {
+    std::string wgsl;
+    struct Emitted { uint32_t stage; std::string entry, cuda; };
+    std::vector<Emitted> emitted;
+    std::string cuda_for(uint32_t stage, const std::string& entry) const {
+        for (const auto& e : emitted)
+            if (e.stage == stage && e.entry == entry) return e.cuda;
+        if (wgsl.empty()) fail(WGB_ERROR_SHADER, "shader module has neither WGSL nor emitted CUDA for entry point '%s'", entry.c_str());
+        return wgb_emit_wgsl(wgsl, stage, entry);
+    }
+};
+struct BindGroupLayout : Object { std::vector<wgb_bind_group_layout_entry> entries; };
+struct PipelineLayout : Object { std::vector<Ref<BindGroupLayout>> layouts; };
+struct BindGroup : Object {
+    struct Entry {
+        uint32_t binding, kind;
+        Ref<Buffer> buffer; uint64_t offset = 0, size = 0;
+        Ref<TextureView> view;
+        Ref<Sampler> sampler;
+    };
+    std::vector<Entry> entries;
+};
+
+struct RenderPipeline : Object {
+    Ref<Device> device;
+    std::string vs_text, fs_text;
+    bool has_fragment = false;
+    struct VB { uint64_t stride; uint32_t step_mode; std::vector<wgb_vertex_attribute> attrs; };
+    std::vector<VB> vbs;
+    uint32_t topology = 0, strip_index_format = 0, front_face = 0, cull_mode = 0;
+    bool has_depth_stencil = false;
+    uint32_t depth_format = 0, depth_write = 0, depth_compare = 0;
+    std::vector<wgb_color_target_state> targets;
+    std::mutex mu;
+    std::map<uint32_t, std::shared_ptr<KernelSet>> variants;   // key: has_depth_attachment | separated << 1
+    std::map<uint32_t, std::string> variant_source;
+
+    int prim_size() const {
+        return topology == WGB_TOPOLOGY_POINT_LIST ? 1 : (topology == WGB_TOPOLOGY_LINE_LIST || topology == WGB_TOPOLOGY_LINE_STRIP) ? 2 : 3;
+    }
+    bool is_strip() const { return topology == WGB_TOPOLOGY_LINE_STRIP || topology == WGB_TOPOLOGY_TRIANGLE_STRIP; }
+
+    // closed form of the serial depth-test fold for this state (see wgb_raster.cuh)
+    static int resolve_mode(bool test, uint32_t compare, bool write) {
+        if (!test) return 0;
+        switch (compare) {
+            case WGB_COMPARE_NEVER: return 6;
+            case WGB_COMPARE_ALWAYS: return 0;
+            case WGB_COMPARE_LESS: return write ? 1 : 5;
+            case WGB_COMPARE_LESS_EQUAL: return write ? 2 : 5;
+            case WGB_COMPARE_GREATER: return write ? 3 : 5;
+            case WGB_COMPARE_GREATER_EQUAL: return write ? 4 : 5;
+            case WGB_COMPARE_EQUAL: return 5;
+            case WGB_COMPARE_NOT_EQUAL:
+                if (write) fail(WGB_ERROR_UNSUPPORTED, "depth compare NotEqual with depth writes is order-dependent per fragment and is not supported");
+                return 5;
+            default: fail(WGB_ERROR_VALIDATION, "invalid depth compare function %u", compare);
+        }
+    }
+
+    std::string build_source(bool has_depth_attachment, bool separated) const {
+        const bool test = has_depth_stencil && has_depth_attachment;
+        const int mode = resolve_mode(test, depth_compare, depth_write != 0);
+        std::string s;
+        char line[256];
+        auto def = [&](const char* name, long long v) { snprintf(line, sizeof(line), "#define %s %lld\n", name, v); s += line; };
+        s += "// generated by wgpu-b200: one translation unit per render pipeline variant\n";
+        def("WGB_PRIM_SIZE", prim_size());
+        def("WGB_STRIP", is_strip() ? 1 : 0);
+        def("WGB_STRIP_SEPARATED", separated ? 1 : 0);
+        def("WGB_FRONT_FACE_CW", front_face == WGB_FRONT_FACE_CW ? 1 : 0);
+        def("WGB_CULL", cull_mode);
+        def("WGB_RESOLVE", mode);
+        def("WGB_DEPTH_COMPARE", test ? depth_compare : WGB_COMPARE_ALWAYS);
+        def("WGB_DEPTH_WRITE", (test && depth_write) ? 1 : 0);
+        def("WGB_HAS_DEPTH", has_depth_attachment ? 1 : 0);
+        def("WGB_NUM_COLOR", (long long)targets.size());
+        for (size_t b = 0; b < vbs.size(); b++)
+            for (const auto& a : vbs[b].attrs) {
+                snprintf(line, sizeof(line), "#define WGB_ATTR%u_SLOT %zu\n#define WGB_ATTR%u_STRIDE %lluu\n#define WGB_ATTR%u_OFFSET %lluu\n#define WGB_ATTR%u_INSTANCE %s\n",
+                         a.shader_location, b, a.shader_location, (unsigned long long)vbs[b].stride, a.shader_location,
+                         (unsigned long long)a.offset, a.shader_location, vbs[b].step_mode == WGB_VERTEX_STEP_MODE_INSTANCE ? "true" : "false");
+                s += line;
+            }
+        s += "#include \"wgb_prelude.cuh\"\n";
+        s += vs_text;
+        s += "\n";
+        if (has_fragment) s += fs_text;
+        else s += "#define WGB_FS_COLOR_MASK 0\n#define WGB_FS_WRITES_FRAG_DEPTH 0\n#define WGB_FS_MAY_DISCARD 0\n#define WGB_FS_EARLY_DEPTH 0\n"
+                  "WGB_DEV constexpr int wgb_fs_interp(int) { return 0; }\n"
+                  "WGB_DEV bool wgb_fs_entry(const WgbDraw&, const WgbFragIn&, const u32*, WgbFragOut&) { return true; }\n";
+        s += "\n#if WGB_FS_EARLY_DEPTH && WGB_FS_MAY_DISCARD\n#error \"early depth test combined with discard is not supported\"\n#endif\n";
+        s += "#include \"wgb_raster.cuh\"\n";
+        return s;
+    }
+
+    std::shared_ptr<KernelSet> variant(bool has_depth_attachment, bool separated) {
+        std::lock_guard<std::mutex> lk(mu);
+        const uint32_t key = (has_depth_attachment ? 1u : 0u) | (separated ? 2u : 0u);
+        auto it = variants.find(key);
+        if (it != variants.end()) return it->second;
+        const std::string src = build_source(has_depth_attachment, separated);
+        variant_source[key] = src;
+        std::shared_ptr<KernelSet> ks;
+        {
+            std::lock_guard<std::recursive_mutex> dl(device->mu);
+            auto c = device->kernel_cache.find(src);
+            if (c != device->kernel_cache.end()) ks = c->second;
+        }
+        if (!ks) {
+            const std::vector<char> cubin = nvrtc_compile(src);
+            ks = std::make_shared<KernelSet>();
+            if (!device->compile_only) {
+                load_driver_api();
+                device->make_current();
+                CUresult r = g_drv.ModuleLoadData(&ks->module, cubin.data());
+                if (r != CUDA_SUCCESS) fail(WGB_ERROR_DEVICE, "cuModuleLoadData failed: %s", cu_error(r));
+                auto fn = [&](const char* n, CUfunction* f) {
+                    CUresult q = g_drv.ModuleGetFunction(f, ks->module, n);
+                    if (q != CUDA_SUCCESS) fail(WGB_ERROR_DEVICE, "kernel %s missing: %s", n, cu_error(q));
+                };
+                fn("wgb_geometry_kernel", &ks->geometry);
+                fn("wgb_clip_kernel", &ks->clip);
+                fn("wgb_scan_kernel", &ks->scan);
+                fn("wgb_fill_kernel", &ks->fill);
+                fn("wgb_tile_kernel", &ks->tile);
+                fn("wgb_clear_kernel", &ks->clear);
+                fn("wgb_strip_map_kernel", &ks->strip_map);
+            }
+            std::lock_guard<std::recursive_mutex> dl(device->mu);
+            device->kernel_cache[src] = ks;
+        }
+        variants[key] = ks;
+        return ks;
+    }
+};
+
+// ---- recorded commands (render_pass/mod.rs:397-423 RenderPassSubCommand) ----
+struct SubCommand {
+    enum Kind { SetPipeline, SetBindGroup, SetIndexBuffer, SetVertexBuffer, SetViewport, SetScissor, SetBlendConstant, SetStencilReference, Draw, DrawIndexed } kind;
+    Ref<RenderPipeline> pipeline;
+    Ref<BindGroup> bind_group;
+    Ref<Buffer> buffer;
+    uint32_t index = 0, index_format = 0;
+    uint64_t offset = 0, size = 0;
+    float vp[6] = {0, 0, 0, 0, 0, 1};
+    uint32_t sc[4] = {0, 0, 0, 0};
+    uint32_t first = 0, count = 0, first_instance = 0, instance_count = 0;
+    int32_t base_vertex = 0;
+};
+struct PassCommand {
+    struct Color { Ref<TextureView> view; uint32_t load_op, store_op; double clear[4]; };
+    std::vector<Color> colors;
+    bool has_depth = false;
+    Ref<TextureView> depth_view;
+    bool has_depth_ops = false;
+    uint32_t depth_load_op = 0;
+    float depth_clear = 0.0f;
+    bool has_stencil_ops = false;
+    std::vector<SubCommand> sub;
+};
+struct CommandBuffer : Object { Ref<Device> device; std::vector<std::shared_ptr<PassCommand>> passes; bool submitted = false; };
+struct CommandEncoder : Object { Ref<Device> device; std::vector<std::shared_ptr<PassCommand>> passes; bool finished = false; std::mutex mu; };
+struct RenderPass : Object {
+    Ref<CommandEncoder> encoder;
+    std::shared_ptr<PassCommand> cmd;
+    bool ended = false;
+    std::mutex mu;
+    void end() {   // render_pass/mod.rs:309-329 (also called from Drop)
+        std::lock_guard<std::mutex> lk(mu);
+        if (ended) return;
+        ended = true;
+        std::lock_guard<std::mutex> el(encoder->mu);
+        encoder->passes.push_back(cmd);
+    }
+    ~RenderPass() override { end(); }
+};
+
+// ------------------------------------------------------------------------------------------
+// pass execution (RenderPassCommand::execute, render_pass/mod.rs:345-394)
+// ------------------------------------------------------------------------------------------
+struct PassState {   // render_pass/state.rs:58-75
+    Ref<RenderPipeline> pipeline;
+    Ref<BindGroup> bind_groups[WGB_MAX_GROUPS];
+    struct Slice { Ref<Buffer> buffer; uint64_t offset = 0, size = 0; };
+    Slice vertex_buffers[WGB_MAX_VERTEX_BUFFERS];
+    Slice index_buffer;
+    uint32_t index_format = 0;
+    float vp[6];
+    uint32_t sc[4];
+};
+
+void launch(Device* dev, CUfunction f, dim3 grid, dim3 block, WgbDraw* d) {
+    void* args[] = {d};
+    CUresult r = g_drv.LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, 0, (CUstream)dev->stream, args, nullptr);
+    if (r != CUDA_SUCCESS) fail(WGB_ERROR_DEVICE, "kernel launch failed: %s", cu_error(r));
+    dev->last_stats.kernel_launches++;
+}
+
+void band_rows(const Device* dev, uint32_t tiles_y, uint32_t& ty0, uint32_t& ty1) {
+    // contiguous bands of whole tile rows, the first (tiles_y % n) bands one row taller
+    const uint32_t n = dev->band_count ? dev->band_count : 1u, r = dev->band_rank;
+    const uint32_t q = tiles_y / n, rem = tiles_y % n;
+    ty0 = r * q + (r < rem ? r : rem);
+    ty1 = ty0 + q + (r < rem ? 1u : 0u);
+}
+
+struct PassTargets {
+    uint32_t width = 0, height = 0;
+    uint32_t num_color = 0;
+    WgbAttachment color[WGB_MAX_COLOR];
+    bool has_depth = false;
+    WgbAttachment depth;
+};
+
+void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand& sc) {
+    RenderPipeline* pipe = st.pipeline.get();
+    if (!pipe) fail(WGB_ERROR_VALIDATION, "No pipeline bound");                       // state.rs:240-243
+    if (!pipe->has_fragment) return;     // no fragment state: only the vertex stage would run (state.rs:583-588)
+    const bool indexed = sc.kind == SubCommand::DrawIndexed;
+    if (indexed && !st.index_buffer.buffer) fail(WGB_ERROR_VALIDATION, "No index buffer bound");   // state.rs:393-397
+    bool separated = false;
+    if (indexed && pipe->strip_index_format != WGB_INDEX_FORMAT_NONE) {               // state.rs:296-305, 357-359
+        REQUIRE(pipe->is_strip(), "strip_index_format set, but not a strip topology");
+        REQUIRE(pipe->strip_index_format == st.index_format, "strip_index_format does not match the bound index format");
+        separated = true;
+    }
+    REQUIRE(tg.num_color == pipe->targets.size(), "pipeline has %zu colour targets, pass has %u attachments", pipe->targets.size(), tg.num_color);
+    for (uint32_t c = 0; c < tg.num_color; c++)
+        REQUIRE(tg.color[c].format == pipe->targets[c].format, "colour target %u format mismatch", c);
+    const int ps = pipe->prim_size();
+    uint64_t ppi;
+    if (!pipe->is_strip()) ppi = sc.count / ps;
+    else ppi = sc.count >= (uint32_t)ps ? sc.count - (ps - 1) : 0;
+    if (sc.instance_count == 0 || ppi == 0) return;
+
+    std::shared_ptr<KernelSet> ks = pipe->variant(tg.has_depth, separated);
+    if (dev->compile_only) fail(WGB_ERROR_DEVICE, "a compile-only device cannot execute draws");
+
+    WgbDraw d;
+    memset(&d, 0, sizeof(d));
+    d.fb_width = tg.width; d.fb_height = tg.height;
+    d.tiles_x = (tg.width + WGB_TILE_W - 1) / WGB_TILE_W;
+    d.tiles_y = (tg.height + WGB_TILE_H - 1) / WGB_TILE_H;
+    band_rows(dev, d.tiles_y, d.band_ty0, d.band_ty1);
+    // ToRaster::new (raster.rs:129-143)
+    d.vp_tx = st.vp[0] + 0.5f * st.vp[2];
+    d.vp_ty = st.vp[1] + 0.5f * st.vp[3];
+    d.vp_sx = 0.5f * st.vp[2];
+    d.vp_sy = 0.5f * st.vp[3];
+    d.vp_sy *= -1.0f;
+    d.sc_x0 = st.sc[0]; d.sc_y0 = st.sc[1]; d.sc_x1 = st.sc[0] + st.sc[2]; d.sc_y1 = st.sc[1] + st.sc[3];
+    d.indexed = indexed ? st.index_format : 0u;
+    d.first = sc.first; d.count = sc.count; d.base_vertex = sc.base_vertex;
+    d.first_instance = sc.first_instance; d.instance_count = sc.instance_count;
+    if (indexed) {
+        Buffer* ib = st.index_buffer.buffer.get();
+        REQUIRE(st.index_buffer.offset <= ib->size, "index buffer offset out of range");
+        d.index_ptr = (uint64_t)(uintptr_t)ib->dptr + st.index_buffer.offset;
+        d.index_size = std::min<uint64_t>(st.index_buffer.size, ib->size - st.index_buffer.offset);
+    }
+    for (size_t b = 0; b < pipe->vbs.size(); b++) {                                     // vertex.rs:262-272
+        Buffer* vb = st.vertex_buffers[b].buffer.get();
+        if (!vb) fail(WGB_ERROR_VALIDATION, "Buffer %zu not bound", b);
+        REQUIRE(st.vertex_buffers[b].offset <= vb->size, "vertex buffer offset out of range");
+        d.vb[b].ptr = (uint64_t)(uintptr_t)vb->dptr + st.vertex_buffers[b].offset;
+        d.vb[b].size = std::min<uint64_t>(st.vertex_buffers[b].size, vb->size - st.vertex_buffers[b].offset);
+    }
+    for (uint32_t g = 0; g < WGB_MAX_GROUPS; g++) {                                     // binding.rs:22-52
+        BindGroup* bg = st.bind_groups[g].get();
+        if (!bg) continue;
+        for (const auto& e : bg->entries) {
+            if (e.binding >= WGB_MAX_BINDINGS) fail(WGB_ERROR_UNSUPPORTED, "binding index %u exceeds the supported %d", e.binding, WGB_MAX_BINDINGS);
+            WgbResource& r = d.res[g][e.binding];
+            r.kind = e.kind;
+            if (e.kind == WGB_BINDING_BUFFER) {
+                REQUIRE(e.offset <= e.buffer->size, "bind group buffer offset out of range");
+                r.ptr = (uint64_t)(uintptr_t)e.buffer->dptr + e.offset;
+                r.a = (uint32_t)std::min<uint64_t>(e.size, e.buffer->size - e.offset);
+            } else if (e.kind == WGB_BINDING_TEXTURE_VIEW) {
+                Texture* t = e.view->texture.get();
+                if (t->desc.format != WGB_TEXTURE_FORMAT_RGBA8_UNORM && t->desc.format != WGB_TEXTURE_FORMAT_RGBA8_UNORM_SRGB)
+                    fail(WGB_ERROR_UNSUPPORTED, "sampled texture format %u (the reference reads Rgba8Unorm[Srgb] only, texture.rs:176-186)", t->desc.format);
+                r.ptr = (uint64_t)(uintptr_t)t->dptr;
+                r.tex = (uint64_t)t->texture_object();
+                r.a = t->desc.width; r.b = t->desc.height; r.c = t->desc.format;
+            } else if (e.kind == WGB_BINDING_SAMPLER) {
+                r.a = e.sampler->desc.address_mode_u; r.b = e.sampler->desc.address_mode_v;
+            }
+        }
+    }
+    d.num_color = tg.num_color;
+    d.has_depth = tg.has_depth ? 1u : 0u;
+    for (uint32_t c = 0; c < tg.num_color; c++) d.color[c] = tg.color[c];
+    if (tg.has_depth) d.depth = tg.depth;
+    d.stats = dev->coverage_capture ? 1u : 0u;
+
+    const uint32_t band_tiles = d.tiles_x * (d.band_ty1 - d.band_ty0);
+    if (band_tiles == 0) return;
+
+    // primitive restart: positions of every primitive's vertices in the index range
+    if (separated) {
+        dev->strip_map.ensure((size_t)ppi * ps * 4);
+        dev->strip_count.ensure(4);
+        d.strip_map = dev->strip_map.addr();
+        CUDA_CHECK(cudaMemsetAsync(dev->strip_map.p, 0xFF, (size_t)ppi * ps * 4, dev->stream));
+        void* args[] = {&d, &dev->strip_count.p};
+        CUresult r = g_drv.LaunchKernel(ks->strip_map, 1, 1, 1, 32, 1, 1, 0, (CUstream)dev->stream, args, nullptr);
+        if (r != CUDA_SUCCESS) fail(WGB_ERROR_DEVICE, "strip map launch failed: %s", cu_error(r));
+        dev->last_stats.kernel_launches++;
+        uint32_t n = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&n, dev->strip_count.p, 4, cudaMemcpyDeviceToHost, dev->stream));
+        CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+        ppi = n;
+        if (ppi == 0) return;
+    }
+    d.prims_per_instance = (uint32_t)ppi;
+    const uint64_t total_prims = ppi * (uint64_t)sc.instance_count;
+    const uint64_t max_batch = (1ull << 26) - 1;        // order = 1 + 64 * p + sub has to fit 32 bits
+
+    if (dev->coverage_capture && (dev->coverage_w != tg.width || dev->coverage_h != tg.height)) {
+        dev->coverage.ensure((size_t)tg.width * tg.height * 4);
+        CUDA_CHECK(cudaMemsetAsync(dev->coverage.p, 0, (size_t)tg.width * tg.height * 4, dev->stream));
+        dev->coverage_w = tg.width; dev->coverage_h = tg.height;
+    }
+    d.coverage = dev->coverage.addr();
+
+    for (uint64_t base = 0; base < total_prims; base += max_batch) {
+        const uint32_t np = (uint32_t)std::min<uint64_t>(max_batch, total_prims - base);
+        d.prim_base = (uint32_t)base;   // batches beyond 2^32 primitives are not addressable
+        REQUIRE(base + np <= 0xFFFFFFFFull, "draw exceeds 2^32 primitives");
+        d.num_prims = np;
+        if (dev->clip_capacity == 0) dev->clip_capacity = 65536;
+        for (int attempt = 0;; attempt++) {
+            const uint32_t clip_cap = std::max<uint32_t>(dev->clip_capacity, np / 16);
+            const uint32_t big_cap = std::max<uint32_t>(dev->big_capacity, std::max<uint32_t>(65536, np / 8));
+            dev->clip_capacity = clip_cap; dev->big_capacity = big_cap;
+            dev->counters.ensure(sizeof(WgbCounters));
+            dev->prim_box.ensure((size_t)np * 4);
+            dev->slow_list.ensure((size_t)np * 4);
+            dev->clip_records.ensure((size_t)clip_cap * sizeof(WgbClipRecord));
+            dev->big_list.ensure((size_t)big_cap * sizeof(WgbBigEntry));
+            dev->tile_count.ensure((size_t)(band_tiles + 1) * 4);
+            dev->tile_offset.ensure((size_t)(band_tiles + 1) * 4);
+            dev->tile_cursor.ensure((size_t)(band_tiles + 1) * 4);
+            dev->bins.ensure(((size_t)np + clip_cap) * WGB_SMALL_MAX_TILES * 4);
+            d.counters = dev->counters.addr(); d.prim_box = dev->prim_box.addr(); d.slow_list = dev->slow_list.addr();
+            d.clip_records = dev->clip_records.addr(); d.clip_capacity = clip_cap;
+            d.big_list = dev->big_list.addr(); d.big_capacity = big_cap;
+            d.tile_count = dev->tile_count.addr(); d.tile_offset = dev->tile_offset.addr(); d.tile_cursor = dev->tile_cursor.addr();
+            d.bins = dev->bins.addr();
+
+            CUDA_CHECK(cudaEventRecord(dev->ev[0], dev->stream));
+            CUDA_CHECK(cudaMemsetAsync(dev->counters.p, 0, sizeof(WgbCounters), dev->stream));
+            CUDA_CHECK(cudaMemsetAsync(dev->tile_count.p, 0, (size_t)(band_tiles + 1) * 4, dev->stream));
+            const uint32_t gblocks = (np + 255) / 256;
+            launch(dev, ks->geometry, dim3(gblocks), dim3(256), &d);
+            launch(dev, ks->clip, dim3(std::min<uint32_t>((np + 127) / 128, 148 * 8)), dim3(128), &d);
+            launch(dev, ks->scan, dim3(1), dim3(1024), &d);
+            launch(dev, ks->fill, dim3(gblocks), dim3(256), &d);
+            CUDA_CHECK(cudaEventRecord(dev->ev[1], dev->stream));
+            launch(dev, ks->tile, dim3(d.tiles_x, d.band_ty1 - d.band_ty0), dim3(256), &d);
+            CUDA_CHECK(cudaEventRecord(dev->ev[2], dev->stream));
+            CUDA_CHECK(cudaMemcpyAsync(dev->host_counters, dev->counters.p, sizeof(WgbCounters), cudaMemcpyDeviceToHost, dev->stream));
+            CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+            const WgbCounters c = *dev->host_counters;
+            float g_ms = 0, t_ms = 0;
+            cudaEventElapsedTime(&g_ms, dev->ev[0], dev->ev[1]);
+            cudaEventElapsedTime(&t_ms, dev->ev[1], dev->ev[2]);
+            dev->last_stats.geometry_ms += g_ms;
+            dev->last_stats.tile_ms += t_ms;
+            dev->last_stats.total_ms += g_ms + t_ms;
+            if (c.status & (WGB_STATUS_CLIP_OVERFLOW | WGB_STATUS_BIG_OVERFLOW)) {
+                // the tile kernel saw the flag and left the attachments untouched: grow and replay
+                if (attempt >= 8) fail(WGB_ERROR_OUT_OF_MEMORY, "work buffers still too small after %d replays", attempt);
+                if (c.status & WGB_STATUS_CLIP_OVERFLOW) dev->clip_capacity = std::max<uint32_t>(dev->clip_capacity * 2, c.num_clip_records + 1024);
+                if (c.status & WGB_STATUS_BIG_OVERFLOW) dev->big_capacity = std::max<uint32_t>(dev->big_capacity * 2, c.num_big + 1024);
+                dev->last_stats.replays++;
+                continue;
+            }
+            if (c.status & WGB_STATUS_INDEX_OOB) fail(WGB_ERROR_OUT_OF_BOUNDS, "an index lies outside the bound index buffer or overflows with base_vertex (index.rs:45-62)");
+            if (c.status & WGB_STATUS_VERTEX_OOB) fail(WGB_ERROR_OUT_OF_BOUNDS, "a vertex attribute fetch lies outside its vertex buffer (vertex.rs:143-154)");
+            if (c.status & WGB_STATUS_W_ZERO) fail(WGB_ERROR_VALIDATION, "a clip position has w = 0 (the reference panics: raster.rs:146, primitive.rs:175-177)");
+            dev->last_stats.primitives += np;
+            dev->last_stats.fragments += c.fragments;
+            dev->last_stats.shaded += c.shaded;
+            dev->last_stats.bin_pairs += c.num_small_pairs;
+            dev->last_stats.big_primitives += c.num_big;
+            dev->last_stats.clipped_primitives += c.num_slow;
+            dev->last_stats.clip_records += c.num_clip_records;
+            break;
+        }
+        // the clear has been applied by the first executed batch
+        for (uint32_t c = 0; c < tg.num_color; c++) { tg.color[c].load_clear = 0; d.color[c].load_clear = 0; }
+        if (tg.has_depth) { tg.depth.load_clear = 0; d.depth.load_clear = 0; }
+    }
+    dev->last_stats.draws++;
+}
+
+void execute_pass(Device* dev, const PassCommand& pass) {
+    dev->last_stats = wgb_pass_stats{};
+    PassTargets tg;
+    bool have_size = false;
+    auto check_size = [&](const Texture* t) {                                          // state.rs:84-96
+        if (have_size) REQUIRE(t->desc.width == tg.width && t->desc.height == tg.height, "All render attachments must be the same size");
+        tg.width = t->desc.width; tg.height = t->desc.height; have_size = true;
+    };
+    for (const auto& c : pass.colors) {
+        if (!c.view) fail(WGB_ERROR_UNSUPPORTED, "empty colour attachment slots are not supported");
+        Texture* t = c.view->texture.get();
+        REQUIRE(is_color_format(t->desc.format), "colour attachment has a non-colour format");
+        REQUIRE(t->device.get() == dev, "attachment belongs to another device");
+        check_size(t);
+        REQUIRE(tg.num_color < WGB_MAX_COLOR, "too many colour attachments");
+        WgbAttachment& a = tg.color[tg.num_color++];
+        a.ptr = (uint64_t)(uintptr_t)t->dptr + (uint64_t)c.view->base_layer * t->desc.width * t->desc.height * t->bpp;
+        a.format = t->desc.format;
+        a.bytes_per_texel = t->bpp;
+        a.load_clear = c.load_op == WGB_LOAD_OP_CLEAR ? 1u : 0u;
+        a.clear_texel = encode_color(c.clear, t->desc.format);
+    }
+    if (pass.has_depth) {
+        Texture* t = pass.depth_view->texture.get();
+        if (pass.has_stencil_ops) fail(WGB_ERROR_UNSUPPORTED, "stencil_ops (fragment.rs:618-620 todo!)");
+        if (t->desc.format != WGB_TEXTURE_FORMAT_DEPTH32_FLOAT) fail(WGB_ERROR_UNSUPPORTED, "depth attachments must be Depth32Float (texture.rs:220-239 reads raw f32)");
+        check_size(t);
+        tg.has_depth = true;
+        tg.depth.ptr = (uint64_t)(uintptr_t)t->dptr;
+        tg.depth.format = t->desc.format;
+        tg.depth.bytes_per_texel = 4;
+        tg.depth.load_clear = (pass.has_depth_ops && pass.depth_load_op == WGB_LOAD_OP_CLEAR) ? 1u : 0u;
+        memcpy(&tg.depth.clear_texel, &pass.depth_clear, 4);
+    }
+    PassState st;
+    // default viewport / scissor: the whole framebuffer (state.rs:604-628)
+    st.vp[0] = 0; st.vp[1] = 0; st.vp[2] = (float)tg.width; st.vp[3] = (float)tg.height; st.vp[4] = 0; st.vp[5] = 1;
+    st.sc[0] = 0; st.sc[1] = 0; st.sc[2] = tg.width; st.sc[3] = tg.height;
+
+    if (dev->coverage_capture && have_size) {
+        dev->coverage.ensure((size_t)tg.width * tg.height * 4);
+        CUDA_CHECK(cudaMemsetAsync(dev->coverage.p, 0, (size_t)tg.width * tg.height * 4, dev->stream));
+        dev->coverage_w = tg.width; dev->coverage_h = tg.height;
+    }
+
+    for (const SubCommand& sc : pass.sub) {                                            // render_pass/mod.rs:351-388
+        switch (sc.kind) {
+            case SubCommand::SetPipeline: st.pipeline = sc.pipeline; break;
+            case SubCommand::SetBindGroup:
+                if (sc.index >= WGB_MAX_GROUPS) fail(WGB_ERROR_UNSUPPORTED, "bind group index %u", sc.index);
+                st.bind_groups[sc.index] = sc.bind_group;          // dynamic offsets are stored then ignored (state.rs:194-205)
+                break;
+            case SubCommand::SetIndexBuffer:
+                st.index_buffer.buffer = sc.buffer; st.index_buffer.offset = sc.offset; st.index_buffer.size = sc.size;
+                st.index_format = sc.index_format;
+                break;
+            case SubCommand::SetVertexBuffer:
+                if (sc.index >= WGB_MAX_VERTEX_BUFFERS) fail(WGB_ERROR_UNSUPPORTED, "vertex buffer slot %u", sc.index);
+                st.vertex_buffers[sc.index].buffer = sc.buffer; st.vertex_buffers[sc.index].offset = sc.offset; st.vertex_buffers[sc.index].size = sc.size;
+                break;
+            case SubCommand::SetViewport: memcpy(st.vp, sc.vp, sizeof(st.vp)); break;
+            case SubCommand::SetScissor: memcpy(st.sc, sc.sc, sizeof(st.sc)); break;
+            case SubCommand::SetBlendConstant: case SubCommand::SetStencilReference: break;   // stored, unused (state.rs:207-221)
+            case SubCommand::Draw: case SubCommand::DrawIndexed: execute_draw(dev, st, tg, sc); break;
+        }
+    }
+    // LoadOp::Clear of a pass whose draws never reached the tile kernel (State::load, state.rs:135-145)
+    bool pending = tg.has_depth && tg.depth.load_clear;
+    for (uint32_t c = 0; c < tg.num_color; c++) pending = pending || tg.color[c].load_clear;
+    if (pending && have_size && !dev->compile_only) {
+        // any compiled variant carries the clear kernel; build a minimal one if no pipeline was used
+        static const char* kClearSrc =
+            "#define WGB_PRIM_SIZE 3\n#define WGB_STRIP 0\n#define WGB_STRIP_SEPARATED 0\n#define WGB_FRONT_FACE_CW 0\n#define WGB_CULL 0\n"
+            "#define WGB_RESOLVE 0\n#define WGB_DEPTH_COMPARE 8\n#define WGB_DEPTH_WRITE 0\n#define WGB_HAS_DEPTH 0\n#define WGB_NUM_COLOR 0\n"
+            "#include \"wgb_prelude.cuh\"\n#define WGB_VS_VARYING_SLOTS 0\n"
+            "WGB_DEV void wgb_vs_entry(const WgbDraw&, u32, u32, vec4f& p, u32*, u32&) { p = vec4f(); }\n"
+            "#define WGB_FS_COLOR_MASK 0\n#define WGB_FS_WRITES_FRAG_DEPTH 0\n#define WGB_FS_MAY_DISCARD 0\n#define WGB_FS_EARLY_DEPTH 0\n"
+            "WGB_DEV constexpr int wgb_fs_interp(int) { return 0; }\n"
+            "WGB_DEV bool wgb_fs_entry(const WgbDraw&, const WgbFragIn&, const u32*, WgbFragOut&) { return true; }\n"
+            "#include \"wgb_raster.cuh\"\n";
+        std::shared_ptr<KernelSet> ks;
+        {
+            auto it = dev->kernel_cache.find(kClearSrc);
+            if (it != dev->kernel_cache.end()) ks = it->second;
+        }
+        if (!ks) {
+            const std::vector<char> cubin = nvrtc_compile(kClearSrc);
+            ks = std::make_shared<KernelSet>();
+            load_driver_api();
+            CUresult r = g_drv.ModuleLoadData(&ks->module, cubin.data());
+            if (r != CUDA_SUCCESS) fail(WGB_ERROR_DEVICE, "cuModuleLoadData failed: %s", cu_error(r));
+            r = g_drv.ModuleGetFunction(&ks->clear, ks->module, "wgb_clear_kernel");
+            if (r != CUDA_SUCCESS) fail(WGB_ERROR_DEVICE, "clear kernel missing: %s", cu_error(r));
+            dev->kernel_cache[kClearSrc] = ks;
+        }
+        WgbDraw d;
+        memset(&d, 0, sizeof(d));
+        d.fb_width = tg.width; d.fb_height = tg.height;
+        d.tiles_x = (tg.width + WGB_TILE_W - 1) / WGB_TILE_W;
+        d.tiles_y = (tg.height + WGB_TILE_H - 1) / WGB_TILE_H;
+        band_rows(dev, d.tiles_y, d.band_ty0, d.band_ty1);
+        d.num_color = tg.num_color; d.has_depth = tg.has_depth;
+        for (uint32_t c = 0; c < tg.num_color; c++) d.color[c] = tg.color[c];
+        if (tg.has_depth) d.depth = tg.depth;
+        CUDA_CHECK(cudaEventRecord(dev->ev[0], dev->stream));
+        launch(dev, ks->clear, dim3(148 * 4), dim3(256), &d);
+        CUDA_CHECK(cudaEventRecord(dev->ev[2], dev->stream));
+        CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, dev->ev[0], dev->ev[2]);
+        dev->last_stats.total_ms += ms;
+    }
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+const char* wgb_last_error(void) { return g_last_error.c_str(); }
+const char* wgb_version(void) { return "wgpu-b200 1 sm_100a"; }
+void wgb_retain(wgb_object obj) { if (obj) reinterpret_cast<Object*>(obj)->rc.fetch_add(1); }
+void wgb_release(wgb_object obj) {
+    if (!obj) return;
+    Object* o = reinterpret_cast<Object*>(obj);
+    if (o->rc.fetch_sub(1) == 1) delete o;
+}
+void wgb_free(void* p) { free(p); }
+
+wgb_status wgb_create_instance(const wgb_instance_config*, wgb_instance* out) {
+    return guarded([&] { REQUIRE(out, "out is null"); *out = to_handle<wgb_instance>(new Instance()); });
+}
+wgb_status wgb_instance_request_adapter(wgb_instance instance, wgb_adapter* out) {
+    return guarded([&] {
+        REQUIRE(out, "out is null");
+        Instance* i = from_handle<Instance>(instance, "instance");
+        Adapter* a = new Adapter();
+        a->instance = Ref<Instance>(i);
+        *out = to_handle<wgb_adapter>(a);
+    });
+}
+wgb_status wgb_adapter_get_info(wgb_adapter adapter, wgb_adapter_info* out) {
+    return guarded([&] {
+        from_handle<Adapter>(adapter, "adapter");
+        REQUIRE(out, "out is null");
+        memset(out, 0, sizeof(*out));
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) { n = 0; cudaGetLastError(); }
+        out->cuda_device_count = (uint32_t)n;
+        out->device_type = 1;
+        if (n > 0) {
+            cudaDeviceProp p;
+            int cur = 0;
+            cudaGetDevice(&cur);
+            if (cudaGetDeviceProperties(&p, cur) == cudaSuccess) snprintf(out->name, sizeof(out->name), "wgpu-b200 (%s)", p.name);
+        }
+        if (!out->name[0]) snprintf(out->name, sizeof(out->name), "wgpu-b200 (no CUDA device)");
+    });
+}
+
+#define WGB_CUDA_DEVICE_COMPILE_ONLY (-2)
+wgb_status wgb_adapter_request_device(wgb_adapter adapter, const wgb_device_descriptor* desc, wgb_device* out_device, wgb_queue* out_queue) {
+    return guarded([&] {
+        from_handle<Adapter>(adapter, "adapter");
+        REQUIRE(out_device && out_queue, "out is null");
+        wgb_device_descriptor dd{-1, 0, 1};
+        if (desc) dd = *desc;
+        Ref<Device> dev;
+        dev.p = new Device();
+        if (dd.cuda_device == WGB_CUDA_DEVICE_COMPILE_ONLY) {
+            dev->compile_only = true;     // shader translation + NVRTC only; cannot allocate or draw
+        } else {
+            int n = 0;
+            cudaError_t e = cudaGetDeviceCount(&n);
+            if (e != cudaSuccess || n == 0) { cudaGetLastError(); fail(WGB_ERROR_DEVICE, "no CUDA device available (%s); this backend has no CPU fallback", cudaGetErrorString(e)); }
+            int ord = dd.cuda_device;
+            if (ord < 0) CUDA_CHECK(cudaGetDevice(&ord));
+            REQUIRE(ord < n, "CUDA device %d does not exist (%d devices)", ord, n);
+            dev->ordinal = ord;
+            CUDA_CHECK(cudaSetDevice(ord));
+            CUDA_CHECK(cudaFree(0));
+            cudaDeviceProp p;
+            CUDA_CHECK(cudaGetDeviceProperties(&p, ord));
+            if (p.major != 10) fail(WGB_ERROR_DEVICE, "device %d is sm_%d%d; this backend is built for sm_100a (B200) only", ord, p.major, p.minor);
+            load_driver_api();
+            CUDA_CHECK(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
+            for (auto& e2 : dev->ev) CUDA_CHECK(cudaEventCreate(&e2));
+            CUDA_CHECK(cudaMallocHost((void**)&dev->host_counters, sizeof(WgbCounters)));
+        }
+        dev->band_rank = dd.band_rank;
+        dev->band_count = dd.band_count ? dd.band_count : 1;
+        REQUIRE(dev->band_rank < dev->band_count, "band_rank %u >= band_count %u", dev->band_rank, dev->band_count);
+        Queue* q = new Queue();
+        q->device = dev;
+        *out_queue = to_handle<wgb_queue>(q);
+        dev->rc.fetch_add(1);
+        *out_device = to_handle<wgb_device>(dev.get());
+    });
+}
+
+wgb_status wgb_device_poll(wgb_device device, int32_t wait, uint64_t submission_index, uint64_t timeout_ns, int32_t* out_poll) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        std::lock_guard<std::recursive_mutex> lk(dev->mu);
+        int32_t result = WGB_POLL_OK;
+        if (!dev->compile_only) {
+            dev->make_current();
+            // retire completed submissions in order
+            auto retire = [&] {
+                while (!dev->inflight.empty() && cudaEventQuery(dev->inflight.front().done) == cudaSuccess) {
+                    cudaEventDestroy(dev->inflight.front().done);
+                    dev->inflight.pop_front();
+                }
+            };
+            retire();
+            if (wait) {                                                                 // device.rs:258-289
+                if (dev->inflight.empty()) result = WGB_POLL_QUEUE_EMPTY;
+                else {
+                    const auto t0 = std::chrono::steady_clock::now();
+                    for (;;) {
+                        bool done;
+                        if (submission_index == WGB_SUBMISSION_ANY) done = false;
+                        else {
+                            done = true;
+                            for (const auto& f : dev->inflight) if (f.index == submission_index) done = false;
+                        }
+                        if (done) break;
+                        if (dev->inflight.empty()) break;
+                        if (timeout_ns == 0 || timeout_ns == UINT64_MAX) {
+                            CUDA_CHECK(cudaEventSynchronize(dev->inflight.front().done));
+                        } else {
+                            const auto el = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+                            if ((uint64_t)el > timeout_ns) { result = WGB_POLL_TIMEOUT; break; }
+                        }
+                        const size_t before = dev->inflight.size();
+                        retire();
+                        if (submission_index == WGB_SUBMISSION_ANY && dev->inflight.size() < before) break;
+                    }
+                }
+            }
+        } else if (wait) result = WGB_POLL_QUEUE_EMPTY;
+        if (out_poll) *out_poll = result;
+        if (dev->deferred_status != WGB_OK) {
+            const wgb_status s = dev->deferred_status;
+            const std::string m = dev->deferred_error;
+            dev->deferred_status = WGB_OK;
+            dev->deferred_error.clear();
+            throw Error(s, m);
+        }
+    });
+}
+
+// ---- buffers ----
+wgb_status wgb_device_create_buffer(wgb_device device, const wgb_buffer_descriptor* desc, wgb_buffer* out) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        REQUIRE(desc && out, "null argument");
+        Ref<Buffer> b;
+        b.p = new Buffer();
+        b->device = Ref<Device>(dev);
+        b->size = desc->size;
+        b->usage = desc->usage;
+        if (!dev->compile_only) {
+            dev->make_current();
+            CUDA_CHECK(cudaMalloc(&b->dptr, std::max<uint64_t>(desc->size, 16)));
+            CUDA_CHECK(cudaMemsetAsync(b->dptr, 0, std::max<uint64_t>(desc->size, 16), dev->stream));   // Vec<u8> is zero-initialised (buffer.rs:31-35)
+        }
+        if (desc->mapped_at_creation) {
+            b->staging.assign(desc->size, 0);
+            b->mapped = true; b->map_mode = WGB_MAP_MODE_WRITE; b->map_offset = 0; b->map_size = desc->size;
+        }
+        b->rc.fetch_add(1);
+        *out = to_handle<wgb_buffer>(b.get());
+    });
+}
+wgb_status wgb_buffer_map_async(wgb_buffer buffer, uint32_t mode, uint64_t offset, uint64_t size, wgb_map_callback callback, void* userdata) {
+    wgb_status s = guarded([&] {
+        Buffer* b = from_handle<Buffer>(buffer, "buffer");
+        std::lock_guard<std::mutex> lk(b->mu);
+        REQUIRE(!b->mapped, "buffer is already mapped");
+        REQUIRE(mode == WGB_MAP_MODE_READ || mode == WGB_MAP_MODE_WRITE, "invalid map mode");
+        if (size == WGB_WHOLE_SIZE) size = b->size - std::min(offset, b->size);
+        REQUIRE(offset + size <= b->size, "map range out of bounds");
+        b->staging.assign(b->size, 0);
+        Device* dev = b->device.get();
+        if (!dev->compile_only) {
+            std::lock_guard<std::recursive_mutex> dl(dev->mu);
+            dev->make_current();
+            CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+            // both modes start from the buffer's contents (a write guard derefs to the live Vec<u8>)
+            if (b->size) CUDA_CHECK(cudaMemcpy(b->staging.data(), b->dptr, b->size, cudaMemcpyDeviceToHost));
+        }
+        b->mapped = true; b->map_mode = mode; b->map_offset = offset; b->map_size = size;
+    });
+    if (callback) callback(s, userdata);
+    return s;
+}
+wgb_status wgb_buffer_get_mapped_range(wgb_buffer buffer, uint64_t offset, uint64_t size, void** out_ptr) {
+    return guarded([&] {
+        Buffer* b = from_handle<Buffer>(buffer, "buffer");
+        REQUIRE(out_ptr, "out is null");
+        std::lock_guard<std::mutex> lk(b->mu);
+        REQUIRE(b->mapped, "buffer is not mapped");
+        if (size == WGB_WHOLE_SIZE) size = b->size - std::min(offset, b->size);
+        REQUIRE(offset + size <= b->size, "mapped range out of bounds");
+        *out_ptr = b->staging.data() + offset;
+    });
+}
+wgb_status wgb_buffer_unmap(wgb_buffer buffer) {
+    return guarded([&] {
+        Buffer* b = from_handle<Buffer>(buffer, "buffer");
+        std::lock_guard<std::mutex> lk(b->mu);
+        if (!b->mapped) return;
+        Device* dev = b->device.get();
+        if (b->map_mode == WGB_MAP_MODE_WRITE && b->size && !dev->compile_only) {
+            std::lock_guard<std::recursive_mutex> dl(dev->mu);
+            dev->make_current();
+            CUDA_CHECK(cudaMemcpyAsync(b->dptr, b->staging.data(), b->size, cudaMemcpyHostToDevice, dev->stream));
+            CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+        }
+        b->mapped = false;
+        std::vector<uint8_t>().swap(b->staging);
+    });
+}
+wgb_status wgb_queue_write_buffer(wgb_queue queue, wgb_buffer buffer, uint64_t offset, const void* data, uint64_t size) {
+    return guarded([&] {
+        Queue* q = from_handle<Queue>(queue, "queue");
+        Buffer* b = from_handle<Buffer>(buffer, "buffer");
+        REQUIRE(data || size == 0, "data is null");
+        REQUIRE(offset + size <= b->size, "write_buffer range out of bounds");
+        Device* dev = q->device.get();
+        if (dev->compile_only || size == 0) return;
+        std::lock_guard<std::recursive_mutex> dl(dev->mu);
+        dev->make_current();
+        // pageable source: the copy is staged before the call returns, so `data` may be reused
+        CUDA_CHECK(cudaMemcpyAsync((char*)b->dptr + offset, data, size, cudaMemcpyHostToDevice, dev->stream));
+    });
+}
+
+// ---- textures / samplers ----
+wgb_status wgb_device_create_texture(wgb_device device, const wgb_texture_descriptor* desc, wgb_texture* out) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        REQUIRE(desc && out, "null argument");
+        const uint32_t bpp = bytes_per_texel(desc->format);
+        if (bpp == 0) fail(WGB_ERROR_UNSUPPORTED, "Unsupported texture format: %u", desc->format);   // texture.rs:262-263
+        REQUIRE(desc->width > 0 && desc->height > 0, "texture extent is zero");
+        REQUIRE(desc->width <= 16384 && desc->height <= 16384, "texture extent exceeds 16384");
+        Ref<Texture> t;
+        t.p = new Texture();
+        t->device = Ref<Device>(dev);
+        t->desc = *desc;
+        if (t->desc.depth_or_array_layers == 0) t->desc.depth_or_array_layers = 1;
+        t->bpp = bpp;
+        t->size = (uint64_t)bpp * desc->width * desc->height * t->desc.depth_or_array_layers;
+        if (!dev->compile_only) {
+            dev->make_current();
+            CUDA_CHECK(cudaMalloc(&t->dptr, t->size));
+            CUDA_CHECK(cudaMemsetAsync(t->dptr, 0, t->size, dev->stream));
+        }
+        t->rc.fetch_add(1);
+        *out = to_handle<wgb_texture>(t.get());
+    });
+}
+wgb_status wgb_texture_create_view(wgb_texture texture, const wgb_texture_view_descriptor* desc, wgb_texture_view* out) {
+    return guarded([&] {
+        Texture* t = from_handle<Texture>(texture, "texture");
+        REQUIRE(out, "out is null");
+        TextureView* v = new TextureView();
+        v->texture = Ref<Texture>(t);
+        v->base_layer = desc ? desc->base_array_layer : 0;
+        if (v->base_layer >= t->desc.depth_or_array_layers) { delete v; fail(WGB_ERROR_VALIDATION, "base_array_layer out of range"); }
+        *out = to_handle<wgb_texture_view>(v);
+    });
+}
+wgb_status wgb_queue_write_texture(wgb_queue queue, wgb_texture texture, uint32_t x, uint32_t y, const void* data, uint64_t data_size,
+                                   uint32_t bytes_per_row, uint32_t width, uint32_t height) {
+    return guarded([&] {
+        Queue* q = from_handle<Queue>(queue, "queue");
+        Texture* t = from_handle<Texture>(texture, "texture");
+        REQUIRE(data, "data is null");
+        REQUIRE((uint64_t)x + width <= t->desc.width && (uint64_t)y + height <= t->desc.height, "write_texture rectangle out of bounds");
+        const uint64_t row = (uint64_t)width * t->bpp;
+        const uint64_t pitch = bytes_per_row ? bytes_per_row : row;
+        REQUIRE(pitch >= row, "bytes_per_row smaller than a row");
+        REQUIRE(height == 0 || (uint64_t)(height - 1) * pitch + row <= data_size, "write_texture source too small");
+        Device* dev = q->device.get();
+        if (dev->compile_only || width == 0 || height == 0) return;
+        std::lock_guard<std::recursive_mutex> dl(dev->mu);
+        dev->make_current();
+        char* dst = (char*)t->dptr + ((uint64_t)y * t->desc.width + x) * t->bpp;
+        CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)t->desc.width * t->bpp, data, pitch, row, height, cudaMemcpyHostToDevice, dev->stream));
+        CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+    });
+}
+wgb_status wgb_texture_read(wgb_texture texture, void* dst, uint64_t dst_size) {
+    return guarded([&] {
+        Texture* t = from_handle<Texture>(texture, "texture");
+        REQUIRE(dst && dst_size >= t->size, "destination too small: need %llu bytes", (unsigned long long)t->size);
+        Device* dev = t->device.get();
+        if (dev->compile_only) fail(WGB_ERROR_DEVICE, "a compile-only device has no texture storage");
+        std::lock_guard<std::recursive_mutex> dl(dev->mu);
+        dev->make_current();
+        CUDA_CHECK(cudaMemcpyAsync(dst, t->dptr, t->size, cudaMemcpyDeviceToHost, dev->stream));
+        CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+    });
+}
+wgb_status wgb_texture_device_pointer(wgb_texture texture, uint64_t* out_ptr, uint64_t* out_size) {
+    return guarded([&] {
+        Texture* t = from_handle<Texture>(texture, "texture");
+        if (out_ptr) *out_ptr = (uint64_t)(uintptr_t)t->dptr;
+        if (out_size) *out_size = t->size;
+    });
+}
+wgb_status wgb_device_create_sampler(wgb_device device, const wgb_sampler_descriptor* desc, wgb_sampler* out) {
+    return guarded([&] {
+        from_handle<Device>(device, "device");
+        REQUIRE(desc && out, "null argument");
+        if (desc->address_mode_u == WGB_ADDRESS_MODE_CLAMP_TO_BORDER || desc->address_mode_v == WGB_ADDRESS_MODE_CLAMP_TO_BORDER)
+            fail(WGB_ERROR_UNSUPPORTED, "ClampToBorder (binding.rs:161 todo!)");
+        REQUIRE(desc->address_mode_u <= 2 && desc->address_mode_v <= 2, "invalid address mode");
+        Sampler* s = new Sampler();
+        s->desc = *desc;      // filters are kept but sampling is always nearest, like the reference (binding.rs:93-149)
+        *out = to_handle<wgb_sampler>(s);
+    });
+}
+
+// ---- shaders ----
+wgb_status wgb_device_create_shader_module(wgb_device device, const wgb_shader_module_descriptor* desc, wgb_shader_module* out) {
+    return guarded([&] {
+        from_handle<Device>(device, "device");
+        REQUIRE(desc && out, "null argument");
+        REQUIRE(desc->wgsl || desc->emitted_count, "shader module needs WGSL source or emitted entry points");
+        std::unique_ptr<ShaderModule> m(new ShaderModule());
+        if (desc->wgsl) m->wgsl = desc->wgsl;
+        for (uint32_t i = 0; i < desc->emitted_count; i++) {
+            REQUIRE(desc->emitted[i].entry_point && desc->emitted[i].cuda_source, "emitted entry point is incomplete");
+            m->emitted.push_back({desc->emitted[i].stage, desc->emitted[i].entry_point, desc->emitted[i].cuda_source});
+        }
+        *out = to_handle<wgb_shader_module>(m.release());
+    });
+}
+wgb_status wgb_translate_wgsl(const char* wgsl, uint32_t stage, const char* entry_point, char** out_cuda) {
+    return guarded([&] {
+        REQUIRE(wgsl && entry_point && out_cuda, "null argument");
+        const std::string s = wgb_emit_wgsl(wgsl, stage, entry_point);
+        *out_cuda = (char*)malloc(s.size() + 1);
+        if (!*out_cuda) throw std::bad_alloc();
+        memcpy(*out_cuda, s.c_str(), s.size() + 1);
+    });
+}
+
+// ---- binding model ----
+wgb_status wgb_device_create_bind_group_layout(wgb_device device, const wgb_bind_group_layout_entry* entries, uint32_t count, wgb_bind_group_layout* out) {
+    return guarded([&] {
+        from_handle<Device>(device, "device");
+        REQUIRE(out && (entries || count == 0), "null argument");
+        BindGroupLayout* l = new BindGroupLayout();
+        l->entries.assign(entries, entries + count);
+        *out = to_handle<wgb_bind_group_layout>(l);
+    });
+}
+wgb_status wgb_device_create_pipeline_layout(wgb_device device, const wgb_bind_group_layout* layouts, uint32_t count, wgb_pipeline_layout* out) {
+    return guarded([&] {
+        from_handle<Device>(device, "device");
+        REQUIRE(out && (layouts || count == 0), "null argument");
+        std::unique_ptr<PipelineLayout> l(new PipelineLayout());
+        for (uint32_t i = 0; i < count; i++) l->layouts.push_back(Ref<BindGroupLayout>(from_handle<BindGroupLayout>(layouts[i], "bind group layout")));
+        *out = to_handle<wgb_pipeline_layout>(l.release());
+    });
+}
+wgb_status wgb_device_create_bind_group(wgb_device device, wgb_bind_group_layout layout, const wgb_bind_group_entry* entries, uint32_t count, wgb_bind_group* out) {
+    return guarded([&] {
+        from_handle<Device>(device, "device");
+        if (layout) from_handle<BindGroupLayout>(layout, "bind group layout");
+        REQUIRE(out && (entries || count == 0), "null argument");
+        std::unique_ptr<BindGroup> g(new BindGroup());
+        for (uint32_t i = 0; i < count; i++) {
+            BindGroup::Entry e;
+            e.binding = entries[i].binding;
+            e.kind = entries[i].kind;
+            if (e.kind == WGB_BINDING_BUFFER) {
+                Buffer* b = from_handle<Buffer>(entries[i].buffer, "buffer");
+                e.buffer = Ref<Buffer>(b);
+                e.offset = entries[i].offset;
+                e.size = entries[i].size == WGB_WHOLE_SIZE ? b->size - std::min(b->size, e.offset) : entries[i].size;
+            } else if (e.kind == WGB_BINDING_TEXTURE_VIEW) e.view = Ref<TextureView>(from_handle<TextureView>(entries[i].texture_view, "texture view"));
+            else if (e.kind == WGB_BINDING_SAMPLER) e.sampler = Ref<Sampler>(from_handle<Sampler>(entries[i].sampler, "sampler"));
+            else fail(WGB_ERROR_VALIDATION, "invalid binding kind %u", e.kind);
+            g->entries.push_back(e);
+        }
+        *out = to_handle<wgb_bind_group>(g.release());
+    });
+}
+
+// ---- render pipeline ----
+wgb_status wgb_device_create_render_pipeline(wgb_device device, const wgb_render_pipeline_descriptor* desc, wgb_render_pipeline* out) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        REQUIRE(desc && out, "null argument");
+        if (desc->polygon_mode != WGB_POLYGON_MODE_FILL) fail(WGB_ERROR_UNSUPPORTED, "PolygonMode::Line/Point (state.rs:438-478 panics)");
+        REQUIRE(desc->topology <= WGB_TOPOLOGY_TRIANGLE_STRIP, "invalid topology");
+        Ref<RenderPipeline> p;
+        p.p = new RenderPipeline();
+        p->device = Ref<Device>(dev);
+        ShaderModule* vm = from_handle<ShaderModule>(desc->vertex_module, "vertex shader module");
+        p->vs_text = vm->cuda_for(WGB_SHADER_STAGE_VERTEX, desc->vertex_entry_point ? desc->vertex_entry_point : "vs_main");
+        if (desc->fragment_module) {
+            ShaderModule* fm = from_handle<ShaderModule>(desc->fragment_module, "fragment shader module");
+            p->fs_text = fm->cuda_for(WGB_SHADER_STAGE_FRAGMENT, desc->fragment_entry_point ? desc->fragment_entry_point : "fs_main");
+            p->has_fragment = true;
+        }
+        REQUIRE(desc->vertex_buffer_count <= WGB_MAX_VERTEX_BUFFERS, "too many vertex buffers");
+        for (uint32_t b = 0; b < desc->vertex_buffer_count; b++) {
+            RenderPipeline::VB vb;
+            vb.stride = desc->vertex_buffers[b].array_stride;
+            vb.step_mode = desc->vertex_buffers[b].step_mode;
+            for (uint32_t a = 0; a < desc->vertex_buffers[b].attribute_count; a++) {
+                const wgb_vertex_attribute& at = desc->vertex_buffers[b].attributes[a];
+                REQUIRE(vertex_format_size(at.format) != 0, "unsupported vertex format %u", at.format);
+                REQUIRE(at.shader_location < 32, "shader_location too large");
+                vb.attrs.push_back(at);
+            }
+            p->vbs.push_back(vb);
+        }
+        p->topology = desc->topology; p->strip_index_format = desc->strip_index_format;
+        p->front_face = desc->front_face; p->cull_mode = desc->cull_mode;
+        p->has_depth_stencil = desc->has_depth_stencil != 0;
+        p->depth_format = desc->depth_format; p->depth_write = desc->depth_write_enabled; p->depth_compare = desc->depth_compare;
+        if (p->has_depth_stencil) REQUIRE(desc->depth_compare >= 1 && desc->depth_compare <= 8, "invalid depth compare");
+        REQUIRE(desc->target_count <= WGB_MAX_COLOR, "too many colour targets");
+        for (uint32_t t = 0; t < desc->target_count; t++) {
+            REQUIRE(is_color_format(desc->targets[t].format), "colour target %u has a non-colour format", t);
+            p->targets.push_back(desc->targets[t]);   // blend and write_mask are accepted and not applied (fragment.rs:480-485)
+        }
+        // compile the variant the descriptor implies now (device.rs:129-134 compiles at creation)
+        p->variant(p->has_depth_stencil, false);
+        p->rc.fetch_add(1);
+        *out = to_handle<wgb_render_pipeline>(p.get());
+    });
+}
+wgb_status wgb_render_pipeline_get_source(wgb_render_pipeline pipeline, char** out) {
+    return guarded([&] {
+        RenderPipeline* p = from_handle<RenderPipeline>(pipeline, "render pipeline");
+        REQUIRE(out, "out is null");
+        std::lock_guard<std::mutex> lk(p->mu);
+        REQUIRE(!p->variant_source.empty(), "pipeline has no compiled variant");
+        const std::string& s = p->variant_source.begin()->second;
+        *out = (char*)malloc(s.size() + 1);
+        if (!*out) throw std::bad_alloc();
+        memcpy(*out, s.c_str(), s.size() + 1);
+    });
+}
+
+// ---- command encoding ----
+wgb_status wgb_device_create_command_encoder(wgb_device device, wgb_command_encoder* out) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        REQUIRE(out, "out is null");
+        CommandEncoder* e = new CommandEncoder();
+        e->device = Ref<Device>(dev);
+        *out = to_handle<wgb_command_encoder>(e);
+    });
+}
+wgb_status wgb_command_encoder_begin_render_pass(wgb_command_encoder encoder, const wgb_render_pass_descriptor* desc, wgb_render_pass* out) {
+    return guarded([&] {
+        CommandEncoder* enc = from_handle<CommandEncoder>(encoder, "command encoder");
+        REQUIRE(desc && out, "null argument");
+        REQUIRE(!enc->finished, "command encoder is finished");
+        auto cmd = std::make_shared<PassCommand>();
+        for (uint32_t i = 0; i < desc->color_attachment_count; i++) {
+            const wgb_color_attachment& a = desc->color_attachments[i];
+            PassCommand::Color c;
+            if (a.view) c.view = Ref<TextureView>(from_handle<TextureView>(a.view, "texture view"));
+            c.load_op = a.load_op; c.store_op = a.store_op;
+            memcpy(c.clear, a.clear_value, sizeof(c.clear));
+            cmd->colors.push_back(c);
+        }
+        if (desc->depth_stencil_attachment) {
+            const wgb_depth_stencil_attachment& a = *desc->depth_stencil_attachment;
+            cmd->has_depth = true;
+            cmd->depth_view = Ref<TextureView>(from_handle<TextureView>(a.view, "texture view"));
+            cmd->has_depth_ops = a.has_depth_ops != 0;
+            cmd->depth_load_op = a.depth_load_op;
+            cmd->depth_clear = a.depth_clear_value;
+            cmd->has_stencil_ops = a.has_stencil_ops != 0;
+        }
+        RenderPass* p = new RenderPass();
+        p->encoder = Ref<CommandEncoder>(enc);
+        p->cmd = cmd;
+        *out = to_handle<wgb_render_pass>(p);
+    });
+}
+static SubCommand& record(wgb_render_pass pass, SubCommand::Kind k) {
+    RenderPass* p = from_handle<RenderPass>(pass, "render pass");
+    REQUIRE(!p->ended, "render pass has ended");
+    p->cmd->sub.emplace_back();
+    p->cmd->sub.back().kind = k;
+    return p->cmd->sub.back();
+}
+wgb_status wgb_render_pass_set_pipeline(wgb_render_pass pass, wgb_render_pipeline pipeline) {
+    return guarded([&] {
+        RenderPipeline* rp = from_handle<RenderPipeline>(pipeline, "render pipeline");
+        record(pass, SubCommand::SetPipeline).pipeline = Ref<RenderPipeline>(rp);
+    });
+}
+wgb_status wgb_render_pass_set_bind_group(wgb_render_pass pass, uint32_t index, wgb_bind_group group, const uint32_t*, uint32_t) {
+    return guarded([&] {
+        BindGroup* g = group ? from_handle<BindGroup>(group, "bind group") : nullptr;
+        SubCommand& s = record(pass, SubCommand::SetBindGroup);
+        s.index = index;
+        if (g) s.bind_group = Ref<BindGroup>(g);
+    });
+}
+wgb_status wgb_render_pass_set_index_buffer(wgb_render_pass pass, wgb_buffer buffer, uint32_t index_format, uint64_t offset, uint64_t size) {
+    return guarded([&] {
+        Buffer* b = from_handle<Buffer>(buffer, "buffer");
+        REQUIRE(index_format == WGB_INDEX_FORMAT_UINT16 || index_format == WGB_INDEX_FORMAT_UINT32, "invalid index format");
+        SubCommand& s = record(pass, SubCommand::SetIndexBuffer);
+        s.buffer = Ref<Buffer>(b); s.index_format = index_format; s.offset = offset; s.size = size;
+    });
+}
+wgb_status wgb_render_pass_set_vertex_buffer(wgb_render_pass pass, uint32_t slot, wgb_buffer buffer, uint64_t offset, uint64_t size) {
+    return guarded([&] {
+        Buffer* b = from_handle<Buffer>(buffer, "buffer");
+        SubCommand& s = record(pass, SubCommand::SetVertexBuffer);
+        s.buffer = Ref<Buffer>(b); s.index = slot; s.offset = offset; s.size = size;
+    });
+}
+wgb_status wgb_render_pass_set_viewport(wgb_render_pass pass, float x, float y, float width, float height, float min_depth, float max_depth) {
+    return guarded([&] {
+        SubCommand& s = record(pass, SubCommand::SetViewport);
+        s.vp[0] = x; s.vp[1] = y; s.vp[2] = width; s.vp[3] = height; s.vp[4] = min_depth; s.vp[5] = max_depth;
+    });
+}
+wgb_status wgb_render_pass_set_scissor_rect(wgb_render_pass pass, uint32_t x, uint32_t y, uint32_t width, uint32_t height) {
+    return guarded([&] {
+        SubCommand& s = record(pass, SubCommand::SetScissor);
+        s.sc[0] = x; s.sc[1] = y; s.sc[2] = width; s.sc[3] = height;
+    });
+}
+wgb_status wgb_render_pass_set_blend_constant(wgb_render_pass pass, const double*) {
+    return guarded([&] { record(pass, SubCommand::SetBlendConstant); });
+}
+wgb_status wgb_render_pass_set_stencil_reference(wgb_render_pass pass, uint32_t) {
+    return guarded([&] { record(pass, SubCommand::SetStencilReference); });
+}
+wgb_status wgb_render_pass_draw(wgb_render_pass pass, uint32_t first_vertex, uint32_t vertex_count, uint32_t first_instance, uint32_t instance_count) {
+    return guarded([&] {
+        SubCommand& s = record(pass, SubCommand::Draw);
+        s.first = first_vertex; s.count = vertex_count; s.first_instance = first_instance; s.instance_count = instance_count;
+    });
+}
+wgb_status wgb_render_pass_draw_indexed(wgb_render_pass pass, uint32_t first_index, uint32_t index_count, int32_t base_vertex,
+                                        uint32_t first_instance, uint32_t instance_count) {
+    return guarded([&] {
+        SubCommand& s = record(pass, SubCommand::DrawIndexed);
+        s.first = first_index; s.count = index_count; s.base_vertex = base_vertex; s.first_instance = first_instance; s.instance_count = instance_count;
+    });
+}
+wgb_status wgb_render_pass_end(wgb_render_pass pass) {
+    return guarded([&] { from_handle<RenderPass>(pass, "render pass")->end(); });
+}
+wgb_status wgb_command_encoder_finish(wgb_command_encoder encoder, wgb_command_buffer* out) {
+    return guarded([&] {
+        CommandEncoder* enc = from_handle<CommandEncoder>(encoder, "command encoder");
+        REQUIRE(out, "out is null");
+        std::lock_guard<std::mutex> lk(enc->mu);
+        REQUIRE(!enc->finished, "command encoder is already finished");
+        enc->finished = true;
+        CommandBuffer* cb = new CommandBuffer();
+        cb->device = enc->device;
+        cb->passes.swap(enc->passes);
+        *out = to_handle<wgb_command_buffer>(cb);
+    });
+}
+wgb_status wgb_queue_submit(wgb_queue queue, const wgb_command_buffer* command_buffers, uint32_t count, uint64_t* out_submission_index) {
+    return guarded([&] {
+        Queue* q = from_handle<Queue>(queue, "queue");
+        Device* dev = q->device.get();
+        REQUIRE(command_buffers || count == 0, "null argument");
+        std::lock_guard<std::recursive_mutex> lk(dev->mu);
+        if (dev->compile_only) fail(WGB_ERROR_DEVICE, "a compile-only device cannot execute submissions");
+        dev->make_current();
+        const uint64_t index = dev->next_submission++;                                  // device.rs:443-444
+        if (out_submission_index) *out_submission_index = index;
+        wgb_status st = WGB_OK;
+        std::string msg;
+        for (uint32_t i = 0; i < count && st == WGB_OK; i++) {
+            CommandBuffer* cb = from_handle<CommandBuffer>(command_buffers[i], "command buffer");
+            REQUIRE(!cb->submitted, "command buffer was already submitted");
+            REQUIRE(cb->device.get() == dev, "command buffer belongs to another device");
+            cb->submitted = true;
+            for (const auto& pass : cb->passes) {
+                // errors raised while a submission executes surface at poll, where the reference's
+                // engine-thread panic would be observed (device.rs:498-503)
+                try { execute_pass(dev, *pass); }
+                catch (const Error& e) { st = e.status; msg = e.what(); break; }
+            }
+            cb->passes.clear();
+        }
+        cudaEvent_t done;
+        CUDA_CHECK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventRecord(done, dev->stream));
+        dev->inflight.push_back({index, done});
+        if (st != WGB_OK && dev->deferred_status == WGB_OK) { dev->deferred_status = st; dev->deferred_error = msg; }
+    });
+}
+
+// ---- measurement ----
+wgb_status wgb_device_get_last_pass_stats(wgb_device device, wgb_pass_stats* out) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        REQUIRE(out, "out is null");
+        std::lock_guard<std::recursive_mutex> lk(dev->mu);
+        *out = dev->last_stats;
+    });
+}
+wgb_status wgb_device_set_coverage_capture(wgb_device device, int32_t enabled) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        std::lock_guard<std::recursive_mutex> lk(dev->mu);
+        dev->coverage_capture = enabled != 0;
+        dev->coverage_w = dev->coverage_h = 0;
+    });
+}
+wgb_status wgb_device_read_coverage(wgb_device device, uint32_t* dst, uint64_t pixel_count) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        std::lock_guard<std::recursive_mutex> lk(dev->mu);
+        REQUIRE(dst, "dst is null");
+        REQUIRE(dev->coverage_capture && dev->coverage.p, "coverage capture is not enabled or no pass has run");
+        REQUIRE(pixel_count == (uint64_t)dev->coverage_w * dev->coverage_h, "pixel_count does not match the last pass (%ux%u)", dev->coverage_w, dev->coverage_h);
+        dev->make_current();
+        CUDA_CHECK(cudaMemcpyAsync(dst, dev->coverage.p, pixel_count * 4, cudaMemcpyDeviceToHost, dev->stream));
+        CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+    });
+}
+wgb_status wgb_device_set_band(wgb_device device, uint32_t band_rank, uint32_t band_count) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        std::lock_guard<std::recursive_mutex> lk(dev->mu);
+        if (band_count == 0) band_count = 1;
+        REQUIRE(band_rank < band_count, "band_rank %u >= band_count %u", band_rank, band_count);
+        dev->band_rank = band_rank; dev->band_count = band_count;
+    });
+}
+wgb_status wgb_device_get_band_rows(wgb_device device, uint32_t height, uint32_t* out_row0, uint32_t* out_row1) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        std::lock_guard<std::recursive_mutex> lk(dev->mu);
+        uint32_t ty0, ty1;
+        band_rows(dev, (height + WGB_TILE_H - 1) / WGB_TILE_H, ty0, ty1);
+        if (out_row0) *out_row0 = std::min(ty0 * WGB_TILE_H, height);
+        if (out_row1) *out_row1 = std::min(ty1 * WGB_TILE_H, height);
+    });
+}
+wgb_status wgb_device_get_stream(wgb_device device, void** out_stream) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        REQUIRE(out_stream, "out is null");
+        *out_stream = (void*)dev->stream;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,342 @@
+// wgb_prelude.cuh -- device-side WGSL value types and operators used by emitted shader code.
+//
+// Arithmetic contract: wgpu-cpu's shader JIT emits one IEEE-754 binary32
+// operation per WGSL operator and never fuses a multiply with an add
+// (naga-cranelift/src/expression/binary.rs:420-449).  Every float operator below is
+// therefore spelled with the round-to-nearest intrinsics (__fmul_rn, __fadd_rn, ...),
+// which the compiler may not contract into FMAs, and the pipeline TU is additionally
+// compiled with --fmad=false, default --prec-div=true / --ftz=false.
+#pragma once
+#include "wgb_shared.h"
+
+typedef unsigned int u32;
+typedef int i32;
+typedef float f32;
+
+#define WGB_DEV __device__ __forceinline__
+
+WGB_DEV f32 wgb_add(f32 a, f32 b) { return __fadd_rn(a, b); }
+WGB_DEV f32 wgb_sub(f32 a, f32 b) { return __fsub_rn(a, b); }
+WGB_DEV f32 wgb_mul(f32 a, f32 b) { return __fmul_rn(a, b); }
+WGB_DEV f32 wgb_div(f32 a, f32 b) { return __fdiv_rn(a, b); }
+// float % : a - b*trunc(a/b) as four separate ops (binary.rs:435-449)
+WGB_DEV f32 wgb_rem(f32 a, f32 b) { return __fsub_rn(a, __fmul_rn(b, truncf(__fdiv_rn(a, b)))); }
+
+// ---------------------------------------------------------------------------------------
+// vectors
+// ---------------------------------------------------------------------------------------
+#define WGB_VEC_TYPES(T, S)                                                                         \
+    struct vec2##S {                                                                                \
+        T x, y;                                                                                     \
+        WGB_DEV vec2##S() : x(0), y(0) {}                                                           \
+        WGB_DEV vec2##S(T x_, T y_) : x(x_), y(y_) {}                                               \
+        WGB_DEV explicit vec2##S(T s) : x(s), y(s) {}                                               \
+        WGB_DEV T& operator[](int i) { return (&x)[i]; }                                            \
+        WGB_DEV const T& operator[](int i) const { return (&x)[i]; }                                \
+    };                                                                                              \
+    struct vec3##S {                                                                                \
+        T x, y, z;                                                                                  \
+        WGB_DEV vec3##S() : x(0), y(0), z(0) {}                                                     \
+        WGB_DEV vec3##S(T x_, T y_, T z_) : x(x_), y(y_), z(z_) {}                                  \
+        WGB_DEV explicit vec3##S(T s) : x(s), y(s), z(s) {}                                         \
+        WGB_DEV vec3##S(vec2##S a, T z_) : x(a.x), y(a.y), z(z_) {}                                 \
+        WGB_DEV vec3##S(T x_, vec2##S a) : x(x_), y(a.x), z(a.y) {}                                 \
+        WGB_DEV T& operator[](int i) { return (&x)[i]; }                                            \
+        WGB_DEV const T& operator[](int i) const { return (&x)[i]; }                                \
+    };                                                                                              \
+    struct vec4##S {                                                                                \
+        T x, y, z, w;                                                                               \
+        WGB_DEV vec4##S() : x(0), y(0), z(0), w(0) {}                                               \
+        WGB_DEV vec4##S(T x_, T y_, T z_, T w_) : x(x_), y(y_), z(z_), w(w_) {}                     \
+        WGB_DEV explicit vec4##S(T s) : x(s), y(s), z(s), w(s) {}                                   \
+        WGB_DEV vec4##S(vec2##S a, T z_, T w_) : x(a.x), y(a.y), z(z_), w(w_) {}                    \
+        WGB_DEV vec4##S(T x_, vec2##S a, T w_) : x(x_), y(a.x), z(a.y), w(w_) {}                    \
+        WGB_DEV vec4##S(T x_, T y_, vec2##S a) : x(x_), y(y_), z(a.x), w(a.y) {}                    \
+        WGB_DEV vec4##S(vec2##S a, vec2##S b) : x(a.x), y(a.y), z(b.x), w(b.y) {}                   \
+        WGB_DEV vec4##S(vec3##S a, T w_) : x(a.x), y(a.y), z(a.z), w(w_) {}                         \
+        WGB_DEV vec4##S(T x_, vec3##S a) : x(x_), y(a.x), z(a.y), w(a.z) {}                         \
+        WGB_DEV T& operator[](int i) { return (&x)[i]; }                                            \
+        WGB_DEV const T& operator[](int i) const { return (&x)[i]; }                                \
+    };
+
+WGB_VEC_TYPES(f32, f)
+WGB_VEC_TYPES(i32, i)
+WGB_VEC_TYPES(u32, u)
+WGB_VEC_TYPES(bool, b)
+
+// element-wise float operators; scalar (x) vector in both orders (binary.rs:210-268, 343-418)
+#define WGB_VEC_FLOAT_OP(OP, FN)                                                                                  \
+    WGB_DEV vec2f operator OP(vec2f a, vec2f b) { return vec2f(FN(a.x, b.x), FN(a.y, b.y)); }                      \
+    WGB_DEV vec3f operator OP(vec3f a, vec3f b) { return vec3f(FN(a.x, b.x), FN(a.y, b.y), FN(a.z, b.z)); }        \
+    WGB_DEV vec4f operator OP(vec4f a, vec4f b) { return vec4f(FN(a.x, b.x), FN(a.y, b.y), FN(a.z, b.z), FN(a.w, b.w)); } \
+    WGB_DEV vec2f operator OP(vec2f a, f32 s) { return vec2f(FN(a.x, s), FN(a.y, s)); }                            \
+    WGB_DEV vec3f operator OP(vec3f a, f32 s) { return vec3f(FN(a.x, s), FN(a.y, s), FN(a.z, s)); }                \
+    WGB_DEV vec4f operator OP(vec4f a, f32 s) { return vec4f(FN(a.x, s), FN(a.y, s), FN(a.z, s), FN(a.w, s)); }    \
+    WGB_DEV vec2f operator OP(f32 s, vec2f a) { return vec2f(FN(s, a.x), FN(s, a.y)); }                            \
+    WGB_DEV vec3f operator OP(f32 s, vec3f a) { return vec3f(FN(s, a.x), FN(s, a.y), FN(s, a.z)); }                \
+    WGB_DEV vec4f operator OP(f32 s, vec4f a) { return vec4f(FN(s, a.x), FN(s, a.y), FN(s, a.z), FN(s, a.w)); }
+WGB_VEC_FLOAT_OP(+, wgb_add)
+WGB_VEC_FLOAT_OP(-, wgb_sub)
+WGB_VEC_FLOAT_OP(*, wgb_mul)
+WGB_VEC_FLOAT_OP(/, wgb_div)
+WGB_DEV vec2f operator-(vec2f a) { return vec2f(-a.x, -a.y); }
+WGB_DEV vec3f operator-(vec3f a) { return vec3f(-a.x, -a.y, -a.z); }
+WGB_DEV vec4f operator-(vec4f a) { return vec4f(-a.x, -a.y, -a.z, -a.w); }
+
+#define WGB_VEC_INT_OP(S, T, OP)                                                                                  \
+    WGB_DEV vec2##S operator OP(vec2##S a, vec2##S b) { return vec2##S(a.x OP b.x, a.y OP b.y); }                  \
+    WGB_DEV vec3##S operator OP(vec3##S a, vec3##S b) { return vec3##S(a.x OP b.x, a.y OP b.y, a.z OP b.z); }      \
+    WGB_DEV vec4##S operator OP(vec4##S a, vec4##S b) { return vec4##S(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w); } \
+    WGB_DEV vec2##S operator OP(vec2##S a, T s) { return vec2##S(a.x OP s, a.y OP s); }                            \
+    WGB_DEV vec3##S operator OP(vec3##S a, T s) { return vec3##S(a.x OP s, a.y OP s, a.z OP s); }                  \
+    WGB_DEV vec4##S operator OP(vec4##S a, T s) { return vec4##S(a.x OP s, a.y OP s, a.z OP s, a.w OP s); }
+WGB_VEC_INT_OP(i, i32, +)
+WGB_VEC_INT_OP(i, i32, -)
+WGB_VEC_INT_OP(i, i32, *)
+WGB_VEC_INT_OP(u, u32, +)
+WGB_VEC_INT_OP(u, u32, -)
+WGB_VEC_INT_OP(u, u32, *)
+
+// ---------------------------------------------------------------------------------------
+// matrices (column-major, columns are vectors; types.rs:442-444)
+// ---------------------------------------------------------------------------------------
+struct mat2x2f { vec2f c[2]; WGB_DEV vec2f& operator[](int i) { return c[i]; } WGB_DEV const vec2f& operator[](int i) const { return c[i]; } };
+struct mat3x3f { vec3f c[3]; WGB_DEV vec3f& operator[](int i) { return c[i]; } WGB_DEV const vec3f& operator[](int i) const { return c[i]; } };
+struct mat4x4f {
+    vec4f c[4];
+    WGB_DEV mat4x4f() {}
+    WGB_DEV mat4x4f(vec4f c0, vec4f c1, vec4f c2, vec4f c3) { c[0] = c0; c[1] = c1; c[2] = c2; c[3] = c3; }
+    WGB_DEV vec4f& operator[](int i) { return c[i]; }
+    WGB_DEV const vec4f& operator[](int i) const { return c[i]; }
+};
+// matrix * vector: x_i = splat(v[i]) * M.col[i], accumulated left to right with separate
+// adds: ((v0*c0 + v1*c1) + v2*c2) + v3*c3   (binary.rs:297-323)
+WGB_DEV vec2f operator*(const mat2x2f& m, vec2f v) { return v.x * m.c[0] + v.y * m.c[1]; }
+WGB_DEV vec3f operator*(const mat3x3f& m, vec3f v) { return (v.x * m.c[0] + v.y * m.c[1]) + v.z * m.c[2]; }
+WGB_DEV vec4f operator*(const mat4x4f& m, vec4f v) { return ((v.x * m.c[0] + v.y * m.c[1]) + v.z * m.c[2]) + v.w * m.c[3]; }
+WGB_DEV mat4x4f operator*(const mat4x4f& m, f32 s) { return mat4x4f(m.c[0] * s, m.c[1] * s, m.c[2] * s, m.c[3] * s); }
+WGB_DEV mat4x4f operator*(f32 s, const mat4x4f& m) { return mat4x4f(s * m.c[0], s * m.c[1], s * m.c[2], s * m.c[3]); }
+// matrix * matrix is a todo!() in the reference (binary.rs:254); defined column by column with the same rule
+WGB_DEV mat4x4f operator*(const mat4x4f& a, const mat4x4f& b) { return mat4x4f(a * b.c[0], a * b.c[1], a * b.c[2], a * b.c[3]); }
+
+// ---------------------------------------------------------------------------------------
+// casts (expression/as.rs:60-184).  float -> int traps in the reference when out of
+// range; here it saturates (CUDA's cvt.rzi), which agrees wherever the reference runs.
+// ---------------------------------------------------------------------------------------
+WGB_DEV f32 wgb_to_f32(f32 v) { return v; }
+WGB_DEV f32 wgb_to_f32(i32 v) { return __int2float_rn(v); }
+WGB_DEV f32 wgb_to_f32(u32 v) { return __uint2float_rn(v); }
+WGB_DEV f32 wgb_to_f32(bool v) { return v ? 1.0f : 0.0f; }
+WGB_DEV i32 wgb_to_i32(f32 v) { return __float2int_rz(v); }
+WGB_DEV i32 wgb_to_i32(i32 v) { return v; }
+WGB_DEV i32 wgb_to_i32(u32 v) { return (i32)v; }
+WGB_DEV i32 wgb_to_i32(bool v) { return v ? 1 : 0; }
+WGB_DEV u32 wgb_to_u32(f32 v) { return __float2uint_rz(v); }
+WGB_DEV u32 wgb_to_u32(i32 v) { return (u32)v; }
+WGB_DEV u32 wgb_to_u32(u32 v) { return v; }
+WGB_DEV u32 wgb_to_u32(bool v) { return v ? 1u : 0u; }
+WGB_DEV bool wgb_to_bool(f32 v) { return v != 0.0f; }
+WGB_DEV bool wgb_to_bool(i32 v) { return v != 0; }
+WGB_DEV bool wgb_to_bool(u32 v) { return v != 0u; }
+WGB_DEV bool wgb_to_bool(bool v) { return v; }
+
+// integer division / remainder: the reference aborts on division by zero and on
+// i32::MIN / -1 (binary.rs:451-563); WGSL's defined results are used here instead
+WGB_DEV i32 wgb_idiv(i32 a, i32 b) { return (b == 0 || (a == (-2147483647 - 1) && b == -1)) ? a : a / b; }
+WGB_DEV u32 wgb_idiv(u32 a, u32 b) { return b == 0u ? a : a / b; }
+WGB_DEV i32 wgb_irem(i32 a, i32 b) { return (b == 0 || (a == (-2147483647 - 1) && b == -1)) ? 0 : a % b; }
+WGB_DEV u32 wgb_irem(u32 a, u32 b) { return b == 0u ? 0u : a % b; }
+
+// select(f, t, cond) (expression/select.rs:36-103: scalar condition)
+template <class T> WGB_DEV T wgb_select(T f, T t, bool cond) { return cond ? t : f; }
+
+// ---------------------------------------------------------------------------------------
+// resources
+// ---------------------------------------------------------------------------------------
+// uniform / storage loads: `offset` is the WGSL-layout byte offset computed by the emitter
+template <class T> WGB_DEV T wgb_load(const WgbDraw& d, int group, int binding, u32 offset);
+template <> WGB_DEV f32 wgb_load<f32>(const WgbDraw& d, int g, int b, u32 off) {
+    return __ldg(reinterpret_cast<const f32*>(d.res[g][b].ptr + off));
+}
+template <> WGB_DEV i32 wgb_load<i32>(const WgbDraw& d, int g, int b, u32 off) {
+    return __ldg(reinterpret_cast<const i32*>(d.res[g][b].ptr + off));
+}
+template <> WGB_DEV u32 wgb_load<u32>(const WgbDraw& d, int g, int b, u32 off) {
+    return __ldg(reinterpret_cast<const u32*>(d.res[g][b].ptr + off));
+}
+template <> WGB_DEV vec2f wgb_load<vec2f>(const WgbDraw& d, int g, int b, u32 off) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(d.res[g][b].ptr + off));
+    return vec2f(v.x, v.y);
+}
+template <> WGB_DEV vec3f wgb_load<vec3f>(const WgbDraw& d, int g, int b, u32 off) {
+    const f32* p = reinterpret_cast<const f32*>(d.res[g][b].ptr + off);
+    return vec3f(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+template <> WGB_DEV vec4f wgb_load<vec4f>(const WgbDraw& d, int g, int b, u32 off) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(d.res[g][b].ptr + off));
+    return vec4f(v.x, v.y, v.z, v.w);
+}
+template <> WGB_DEV mat4x4f wgb_load<mat4x4f>(const WgbDraw& d, int g, int b, u32 off) {
+    return mat4x4f(wgb_load<vec4f>(d, g, b, off), wgb_load<vec4f>(d, g, b, off + 16),
+                   wgb_load<vec4f>(d, g, b, off + 32), wgb_load<vec4f>(d, g, b, off + 48));
+}
+
+// texture formats / address modes (numeric values of include/wgpu_b200.h)
+#define WGB_FMT_RGBA8_UNORM 0
+#define WGB_FMT_RGBA8_UNORM_SRGB 1
+#define WGB_FMT_BGRA8_UNORM 2
+#define WGB_FMT_BGRA8_UNORM_SRGB 3
+#define WGB_FMT_R8_UNORM 4
+#define WGB_FMT_RG8_UNORM 5
+#define WGB_FMT_RGBA8_SNORM 6
+#define WGB_FMT_DEPTH32_FLOAT 7
+#define WGB_ADDR_CLAMP_TO_EDGE 0
+#define WGB_ADDR_REPEAT 1
+#define WGB_ADDR_MIRROR_REPEAT 2
+
+// f32::rem_euclid (Rust std): r = fmod(x, rhs); r < 0 ? r + |rhs| : r
+WGB_DEV f32 wgb_rem_euclid(f32 x, f32 rhs) {
+    const f32 r = fmodf(x, rhs);
+    return r < 0.0f ? __fadd_rn(r, fabsf(rhs)) : r;
+}
+// Rust `as u32` on f32: saturating, NaN -> 0 (== cvt.rzi.u32.f32)
+WGB_DEV u32 wgb_f32_as_u32(f32 v) { return __float2uint_rz(v); }
+
+// texel_coordinate (wgpu-cpu/src/render_pass/binding.rs:151-164)
+WGB_DEV u32 wgb_texel_coordinate(f32 x, u32 address_mode, u32 size) {
+    if (address_mode == WGB_ADDR_CLAMP_TO_EDGE) {
+        if (x < 0.0f) x = 0.0f;          // f32::clamp keeps NaN
+        if (x > 1.0f) x = 1.0f;
+    } else if (address_mode == WGB_ADDR_REPEAT) {
+        x = wgb_rem_euclid(x, 1.0f);
+    } else {
+        const f32 r = wgb_rem_euclid(x, 2.0f);
+        x = (r <= 1.0f) ? r : __fsub_rn(2.0f, r);
+    }
+    // f32::round: half away from zero
+    return wgb_f32_as_u32(roundf(__fmul_rn(x, __uint2float_rn(size - 1u))));
+}
+
+// textureSample: nearest, mip 0, 2-D (binding.rs:93-149), texel decode u8 as f32 / 255.0
+// without sRGB decode (texture.rs:170-188).  The texel is fetched through the bindless
+// texture object with unnormalised integer coordinates, so the hardware never rounds.
+WGB_DEV vec4f wgb_texture_sample(const WgbDraw& d, int tg, int tb, int sg, int sb, vec2f uv) {
+    const WgbResource& t = d.res[tg][tb];
+    const WgbResource& s = d.res[sg][sb];
+    const u32 tx = wgb_texel_coordinate(uv.x, s.a, t.a);
+    const u32 ty = wgb_texel_coordinate(uv.y, s.b, t.b);
+    const uchar4 p = tex2D<uchar4>((cudaTextureObject_t)t.tex, (float)tx, (float)ty);
+    return vec4f(__fdiv_rn((f32)p.x, 255.0f), __fdiv_rn((f32)p.y, 255.0f), __fdiv_rn((f32)p.z, 255.0f),
+                 __fdiv_rn((f32)p.w, 255.0f));
+}
+
+// ---------------------------------------------------------------------------------------
+// stage I/O glue types
+// ---------------------------------------------------------------------------------------
+struct WgbFragIn {
+    vec4f position;          // (vp.x, vp.y, ndc.z, 1/w)  raster.rs:155
+    bool front_facing;
+    u32 primitive_index;
+    u32 sample_index;
+    u32 sample_mask;
+};
+struct WgbFragOut {
+    vec4f color[WGB_MAX_COLOR];
+    f32 frag_depth;
+};
+
+// vertex attribute fetch; the WGB_ATTR<location>_* macros are generated by the host from
+// the pipeline's vertex buffer layouts (vertex.rs:60-85, 128-156, 195-199)
+template <class T> WGB_DEV T wgb_fetch_raw(const WgbDraw& d, int slot, u32 stride, u32 offset, bool per_instance,
+                                           u32 vertex_index, u32 instance_index, u32& oob);
+#define WGB_FETCH_ADDR()                                                                            \
+    const wgb_u64 start = (wgb_u64)(per_instance ? instance_index : vertex_index) * stride + offset; \
+    if (start + sizeof(T) > d.vb[slot].size) { oob = 1u; return T(); }                              \
+    const wgb_u64 addr = d.vb[slot].ptr + start;
+template <> WGB_DEV vec4f wgb_fetch_raw<vec4f>(const WgbDraw& d, int slot, u32 stride, u32 offset, bool per_instance,
+                                              u32 vertex_index, u32 instance_index, u32& oob) {
+    typedef vec4f T;
+    WGB_FETCH_ADDR()
+    if ((addr & 15u) == 0) {       // 128-bit vectorised fetch whenever the layout allows it
+        const float4 v = __ldg(reinterpret_cast<const float4*>(addr));
+        return vec4f(v.x, v.y, v.z, v.w);
+    }
+    if ((addr & 7u) == 0) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(addr));
+        const float2 b = __ldg(reinterpret_cast<const float2*>(addr + 8));
+        return vec4f(a.x, a.y, b.x, b.y);
+    }
+    const f32* p = reinterpret_cast<const f32*>(addr);
+    return vec4f(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
+template <> WGB_DEV vec3f wgb_fetch_raw<vec3f>(const WgbDraw& d, int slot, u32 stride, u32 offset, bool per_instance,
+                                              u32 vertex_index, u32 instance_index, u32& oob) {
+    typedef vec3f T;
+    WGB_FETCH_ADDR()
+    const f32* p = reinterpret_cast<const f32*>(addr);
+    return vec3f(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+template <> WGB_DEV vec2f wgb_fetch_raw<vec2f>(const WgbDraw& d, int slot, u32 stride, u32 offset, bool per_instance,
+                                              u32 vertex_index, u32 instance_index, u32& oob) {
+    typedef vec2f T;
+    WGB_FETCH_ADDR()
+    if ((addr & 7u) == 0) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(addr));
+        return vec2f(v.x, v.y);
+    }
+    const f32* p = reinterpret_cast<const f32*>(addr);
+    return vec2f(__ldg(p), __ldg(p + 1));
+}
+template <> WGB_DEV f32 wgb_fetch_raw<f32>(const WgbDraw& d, int slot, u32 stride, u32 offset, bool per_instance,
+                                          u32 vertex_index, u32 instance_index, u32& oob) {
+    typedef f32 T;
+    WGB_FETCH_ADDR()
+    return __ldg(reinterpret_cast<const f32*>(addr));
+}
+template <> WGB_DEV u32 wgb_fetch_raw<u32>(const WgbDraw& d, int slot, u32 stride, u32 offset, bool per_instance,
+                                          u32 vertex_index, u32 instance_index, u32& oob) {
+    typedef u32 T;
+    WGB_FETCH_ADDR()
+    return __ldg(reinterpret_cast<const u32*>(addr));
+}
+template <> WGB_DEV i32 wgb_fetch_raw<i32>(const WgbDraw& d, int slot, u32 stride, u32 offset, bool per_instance,
+                                          u32 vertex_index, u32 instance_index, u32& oob) {
+    typedef i32 T;
+    WGB_FETCH_ADDR()
+    return __ldg(reinterpret_cast<const i32*>(addr));
+}
+// WGB_FETCH(T, LOC): expands to the fetch for @location(LOC) of the bound pipeline layout
+#define WGB_FETCH(T, LOC)                                                                           \
+    wgb_fetch_raw<T>(wgb, WGB_ATTR##LOC##_SLOT, WGB_ATTR##LOC##_STRIDE, WGB_ATTR##LOC##_OFFSET,        \
+                     WGB_ATTR##LOC##_INSTANCE, vertex_index, instance_index, oob)
+
+// varyings travel between the stages as 32-bit slots (inter-stage layout of
+// naga-cranelift/src/bindings.rs:307-346 in units of 4 bytes)
+WGB_DEV u32 wgb_bits(f32 v) { return __float_as_uint(v); }
+WGB_DEV u32 wgb_bits(u32 v) { return v; }
+WGB_DEV u32 wgb_bits(i32 v) { return (u32)v; }
+WGB_DEV void wgb_put(u32* s, int o, f32 v) { s[o] = wgb_bits(v); }
+WGB_DEV void wgb_put(u32* s, int o, u32 v) { s[o] = v; }
+WGB_DEV void wgb_put(u32* s, int o, i32 v) { s[o] = (u32)v; }
+WGB_DEV void wgb_put(u32* s, int o, vec2f v) { s[o] = wgb_bits(v.x); s[o + 1] = wgb_bits(v.y); }
+WGB_DEV void wgb_put(u32* s, int o, vec3f v) { s[o] = wgb_bits(v.x); s[o + 1] = wgb_bits(v.y); s[o + 2] = wgb_bits(v.z); }
+WGB_DEV void wgb_put(u32* s, int o, vec4f v) { s[o] = wgb_bits(v.x); s[o + 1] = wgb_bits(v.y); s[o + 2] = wgb_bits(v.z); s[o + 3] = wgb_bits(v.w); }
+WGB_DEV void wgb_put(u32* s, int o, vec2u v) { s[o] = v.x; s[o + 1] = v.y; }
+WGB_DEV void wgb_put(u32* s, int o, vec3u v) { s[o] = v.x; s[o + 1] = v.y; s[o + 2] = v.z; }
+WGB_DEV void wgb_put(u32* s, int o, vec4u v) { s[o] = v.x; s[o + 1] = v.y; s[o + 2] = v.z; s[o + 3] = v.w; }
+WGB_DEV void wgb_put(u32* s, int o, vec2i v) { s[o] = (u32)v.x; s[o + 1] = (u32)v.y; }
+WGB_DEV void wgb_put(u32* s, int o, vec3i v) { s[o] = (u32)v.x; s[o + 1] = (u32)v.y; s[o + 2] = (u32)v.z; }
+WGB_DEV void wgb_put(u32* s, int o, vec4i v) { s[o] = (u32)v.x; s[o + 1] = (u32)v.y; s[o + 2] = (u32)v.z; s[o + 3] = (u32)v.w; }
+template <class T> WGB_DEV T wgb_get(const u32* s, int o);
+template <> WGB_DEV f32 wgb_get<f32>(const u32* s, int o) { return __uint_as_float(s[o]); }
+template <> WGB_DEV u32 wgb_get<u32>(const u32* s, int o) { return s[o]; }
+template <> WGB_DEV i32 wgb_get<i32>(const u32* s, int o) { return (i32)s[o]; }
+template <> WGB_DEV vec2f wgb_get<vec2f>(const u32* s, int o) { return vec2f(__uint_as_float(s[o]), __uint_as_float(s[o + 1])); }
+template <> WGB_DEV vec3f wgb_get<vec3f>(const u32* s, int o) { return vec3f(__uint_as_float(s[o]), __uint_as_float(s[o + 1]), __uint_as_float(s[o + 2])); }
+template <> WGB_DEV vec4f wgb_get<vec4f>(const u32* s, int o) { return vec4f(__uint_as_float(s[o]), __uint_as_float(s[o + 1]), __uint_as_float(s[o + 2]), __uint_as_float(s[o + 3])); }
+template <> WGB_DEV vec2u wgb_get<vec2u>(const u32* s, int o) { return vec2u(s[o], s[o + 1]); }
+template <> WGB_DEV vec3u wgb_get<vec3u>(const u32* s, int o) { return vec3u(s[o], s[o + 1], s[o + 2]); }
+template <> WGB_DEV vec4u wgb_get<vec4u>(const u32* s, int o) { return vec4u(s[o], s[o + 1], s[o + 2], s[o + 3]); }
+template <> WGB_DEV vec2i wgb_get<vec2i>(const u32* s, int o) { return vec2i((i32)s[o], (i32)s[o + 1]); }
+template <> WGB_DEV vec3i wgb_get<vec3i>(const u32* s, int o) { return vec3i((i32)s[o], (i32)s[o + 1], (i32)s[o + 2]); }
+template <> WGB_DEV vec4i wgb_get<vec4i>(const u32* s, int o) { return vec4i((i32)s[o], (i32)s[o + 1], (i32)s[o + 2], (i32)s[o + 3]); }

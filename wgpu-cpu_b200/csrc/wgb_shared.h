@@ -1,0 +1,148 @@
+// wgb_shared.h -- plain-old-data shared by the host runtime (wgb_api.cpp) and the device
+// code compiled per pipeline with NVRTC (wgb_prelude.cuh / wgb_raster.cuh).
+#pragma once
+
+#ifdef __CUDACC_RTC__
+typedef unsigned char wgb_u8;
+typedef unsigned short wgb_u16;
+typedef unsigned int wgb_u32;
+typedef int wgb_i32;
+typedef unsigned long long wgb_u64;
+#else
+#include <stdint.h>
+typedef uint8_t wgb_u8;
+typedef uint16_t wgb_u16;
+typedef uint32_t wgb_u32;
+typedef int32_t wgb_i32;
+typedef uint64_t wgb_u64;
+#endif
+
+#define WGB_MAX_GROUPS 4
+#define WGB_MAX_BINDINGS 4
+#define WGB_MAX_VERTEX_BUFFERS 8
+#define WGB_MAX_COLOR 4
+
+// screen tile processed by one CTA of the tile kernel
+#ifndef WGB_TILE_W
+#define WGB_TILE_W 32
+#endif
+#ifndef WGB_TILE_H
+#define WGB_TILE_H 32
+#endif
+// a primitive whose tile bounding box holds more than this many tiles goes to the
+// "big" list that every tile scans instead of into per-tile bins; this bounds the bin
+// storage at WGB_SMALL_MAX_TILES entries per primitive
+#define WGB_SMALL_MAX_TILES 4
+// upper bound on sub-triangles the six-plane clipper can emit for one triangle
+// (wgpu-cpu/src/render_pass/clipper.rs:737-739 "2**6")
+#define WGB_MAX_CLIP_TRIS 64
+
+// resource kinds in a bind slot
+#define WGB_RES_NONE 0
+#define WGB_RES_BUFFER 1
+#define WGB_RES_TEXTURE 2
+#define WGB_RES_SAMPLER 3
+
+struct WgbResource {            // 32 bytes
+    wgb_u64 ptr;                // buffer base (already offset) / texture linear base
+    wgb_u64 tex;                // CUtexObject (bindless) for textures
+    wgb_u32 a;                  // buffer: size in bytes; texture: width;  sampler: address_mode_u
+    wgb_u32 b;                  //                         texture: height; sampler: address_mode_v
+    wgb_u32 c;                  //                         texture: format
+    wgb_u32 kind;
+};
+
+struct WgbAttachment {
+    wgb_u64 ptr;                // linear, row-major, no padding (texture.rs:250-302)
+    wgb_u32 format;
+    wgb_u32 load_clear;         // 1: LoadOp::Clear still pending for this pass (first draw), 0: load stored texels
+    wgb_u32 clear_texel;        // encoded clear colour (colour) / f32 bits (depth)
+    wgb_u32 bytes_per_texel;
+};
+
+struct WgbVertexBuffer {
+    wgb_u64 ptr;
+    wgb_u64 size;
+};
+
+// counters + status written by the geometry kernels, read by the tile kernel and the host
+struct WgbCounters {             // 64 bytes
+    wgb_u32 num_slow;           // primitives that need the clipper
+    wgb_u32 num_clip_records;   // sub-triangle records reserved by the clip kernel
+    wgb_u32 num_big;            // entries in the big list
+    wgb_u32 num_small_pairs;    // total (entry, tile) pairs in the bins (after the scan)
+    wgb_u32 status;             // WGB_STATUS_* bits
+    wgb_u32 pad0;
+    wgb_u64 fragments;          // rasterised fragments (what the reference runs its fragment stage on)
+    wgb_u64 shaded;             // fragment-shader invocations for surviving fragments
+    wgb_u32 pad[6];
+};
+#define WGB_STATUS_CLIP_OVERFLOW 1u
+#define WGB_STATUS_INDEX_OOB 2u
+#define WGB_STATUS_VERTEX_OOB 4u
+#define WGB_STATUS_W_ZERO 8u
+#define WGB_STATUS_BIG_OVERFLOW 16u
+
+// one record per primitive emitted by the clipper (slow path only)
+struct WgbClipRecord {          // 100 bytes
+    float frag[3][4];           // to_raster'd CLIPPED vertices: (vp.x, vp.y, ndc.z, 1/w)
+    float bary[3][3];           // triangles: clip barycentrics w.r.t. the UNCLIPPED vertices; lines: [0][0..1] = alphas
+    wgb_u32 prim;               // primitive sequence number within the batch
+    wgb_u32 sub;                // index in the clipper's output queue
+    wgb_u32 front_facing;
+    wgb_u32 box;                // tile box, same encoding as prim_box
+};
+
+struct WgbBigEntry {            // 16 bytes
+    wgb_u16 tx0, ty0, tx1, ty1; // inclusive tile bounding box
+    wgb_u32 entry;              // bin entry encoding (see below)
+    wgb_u32 pad;
+};
+// bin entry encoding: bit 31 = 1 -> clip record index in the low bits, 0 -> primitive sequence number
+#define WGB_ENTRY_CLIP 0x80000000u
+
+// parameters of one draw batch; passed by value as a __grid_constant__ kernel argument
+struct WgbDraw {
+    // framebuffer
+    wgb_u32 fb_width, fb_height;
+    wgb_u32 tiles_x, tiles_y;            // whole framebuffer in tiles
+    wgb_u32 band_ty0, band_ty1;          // this rank's tile-row band [ty0, ty1) (sort-first partition)
+    // raster state (state.rs:604-628, raster.rs:129-143)
+    float vp_tx, vp_ty, vp_sx, vp_sy;    // ToRaster translation / scaling
+    wgb_u32 sc_x0, sc_y0, sc_x1, sc_y1;  // scissor_bb
+    // draw call (state.rs:225-236)
+    wgb_u32 indexed;                     // 0 direct, 1 u16, 2 u32
+    wgb_u32 first;                       // first index / first vertex
+    wgb_u32 count;                       // indices / vertices per instance
+    wgb_i32 base_vertex;
+    wgb_u32 first_instance, instance_count;
+    wgb_u32 prims_per_instance;          // assembled primitives per instance
+    wgb_u32 prim_base;                   // first primitive sequence number of this batch
+    wgb_u32 num_prims;                   // primitives in this batch
+    wgb_u32 stats;                       // 1: maintain fragment counters + coverage buffer
+    wgb_u64 index_ptr;
+    wgb_u64 index_size;
+    wgb_u64 strip_map;                   // separated strips: u32 x 3 vertex slots per primitive, else 0
+    WgbVertexBuffer vb[WGB_MAX_VERTEX_BUFFERS];
+    WgbResource res[WGB_MAX_GROUPS][WGB_MAX_BINDINGS];
+    // attachments
+    wgb_u32 num_color;
+    wgb_u32 has_depth;
+    WgbAttachment color[WGB_MAX_COLOR];
+    WgbAttachment depth;
+    // work buffers
+    wgb_u64 counters;                    // WgbCounters*
+    wgb_u64 prim_box;                    // u32 per primitive: kind | packed tile box / clip record base
+    wgb_u64 slow_list;                   // u32 per slow primitive
+    wgb_u64 clip_records;                // WgbClipRecord*
+    wgb_u32 clip_capacity;
+    wgb_u32 pad1;
+    wgb_u64 big_list;                    // WgbBigEntry*
+    wgb_u32 big_capacity;
+    wgb_u32 pad0;
+    wgb_u64 tile_count;                  // u32 per tile in the band
+    wgb_u64 tile_offset;                 // u32 per tile (+1)
+    wgb_u64 tile_cursor;                 // u32 per tile
+    wgb_u64 bins;                        // u32 entries
+    wgb_u64 coverage;                    // optional u32 per pixel (stats)
+};

@@ -1,0 +1,132 @@
+"""Render a `scenes.Scene` through the wgpu-style host API, the way hello_mesh.rs drives wgpu
+(wgpu-cpu/examples/hello_mesh.rs:111-157, 174-224, 263-339): create resources, one command
+encoder, one render pass, submit, poll(Wait), read the attachments back."""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import api, shaders
+from .scenes import Scene
+
+
+@dataclass
+class Frame:
+    color: np.ndarray
+    depth: Optional[np.ndarray]
+    coverage: Optional[np.ndarray]
+    stats: dict
+
+
+class SceneRenderer:
+    """Holds the device-resident resources of one scene so that frames can be re-submitted."""
+
+    def __init__(self, device: api.Device, queue: api.Queue, scene: Scene, use_emitted: bool = False):
+        self.device, self.queue, self.scene = device, queue, scene
+        s = scene
+        if use_emitted:
+            module = device.create_shader_module(None, [
+                (api.STAGE_VERTEX, "vs_main", shaders.emitted(s.shader, "vs")),
+                (api.STAGE_FRAGMENT, "fs_main", shaders.emitted(s.shader, "fs"))])
+        else:
+            module = device.create_shader_module(shaders.wgsl(s.shader))
+        self.module = module
+        self.vertex_buffers = [device.create_buffer_init(vb, api.BUFFER_USAGE["VERTEX"]) for vb in s.vertex_buffers]
+        self.index_buffer = None
+        if s.index_data is not None:
+            self.index_buffer = device.create_buffer_init(s.index_data, api.BUFFER_USAGE["INDEX"])
+            self.index_format = "uint16" if s.index_data.dtype == np.uint16 else "uint32"
+        self.resources = {}
+        groups = {}
+        for (g, b), res in sorted(s.bindings.items()):
+            if res[0] == "buffer":
+                buf = device.create_buffer_init(res[1], api.BUFFER_USAGE["UNIFORM"] | api.BUFFER_USAGE["COPY_DST"])
+                self.resources[(g, b)] = buf
+                groups.setdefault(g, []).append({"binding": b, "buffer": buf})
+            elif res[0] == "texture":
+                img = res[1]
+                tex = device.create_texture_with_data(queue, img.shape[1], img.shape[0], res[2], img)
+                view = tex.create_view()
+                self.resources[(g, b)] = (tex, view)
+                groups.setdefault(g, []).append({"binding": b, "texture_view": view})
+            elif res[0] == "sampler":
+                smp = device.create_sampler(address_mode_u=res[1], address_mode_v=res[2], address_mode_w=res[1])
+                self.resources[(g, b)] = smp
+                groups.setdefault(g, []).append({"binding": b, "sampler": smp})
+        self.bind_groups = {g: device.create_bind_group(None, entries) for g, entries in groups.items()}
+        depth_state = None
+        if s.depth_compare is not None:
+            depth_state = {"format": "depth32float", "depth_write_enabled": s.depth_write, "depth_compare": s.depth_compare}
+        self.pipeline = device.create_render_pipeline(
+            vertex_module=module, fragment_module=module,
+            vertex_buffers=[{"array_stride": l.stride, "step_mode": l.step_mode,
+                             "attributes": [(a.format, a.offset, a.location) for a in l.attributes]} for l in s.vertex_layouts],
+            topology=s.topology, strip_index_format=s.strip_index_format, front_face=s.front_face, cull_mode=s.cull_mode,
+            depth_stencil=depth_state, targets=[s.color_format])
+        self.target = device.create_texture(s.width, s.height, s.color_format)
+        self.target_view = self.target.create_view()
+        self.depth_texture = self.depth_view = None
+        if s.has_depth:
+            self.depth_texture = device.create_texture(s.width, s.height, "depth32float")
+            self.depth_view = self.depth_texture.create_view()
+        if s.initial_color is not None:
+            queue.write_texture(self.target, s.initial_color)
+        if s.initial_depth is not None and self.depth_texture is not None:
+            queue.write_texture(self.depth_texture, np.ascontiguousarray(s.initial_depth, dtype=np.float32))
+
+    def encode(self) -> api.CommandBuffer:
+        s = self.scene
+        enc = self.device.create_command_encoder()
+        color = {"view": self.target_view, "load": ("clear", s.clear_color) if s.clear_color is not None else "load"}
+        depth = None
+        if s.has_depth:
+            depth = {"view": self.depth_view, "depth_load": ("clear", s.clear_depth) if s.clear_depth is not None else "load",
+                     "depth_store": "discard"}
+        with enc.begin_render_pass([color], depth) as rp:
+            rp.set_pipeline(self.pipeline)
+            for g, bg in self.bind_groups.items():
+                rp.set_bind_group(g, bg)
+            if self.index_buffer is not None:
+                rp.set_index_buffer(self.index_buffer, self.index_format)
+            for i, vb in enumerate(self.vertex_buffers):
+                rp.set_vertex_buffer(i, vb)
+            if s.viewport is not None:
+                rp.set_viewport(*s.viewport)
+            if s.scissor is not None:
+                rp.set_scissor_rect(*s.scissor)
+            for d in s.draws:
+                if d.indexed:
+                    rp.draw_indexed(range(d.first, d.first + d.count), d.base_vertex,
+                                    range(d.first_instance, d.first_instance + d.instance_count))
+                else:
+                    rp.draw(range(d.first, d.first + d.count), range(d.first_instance, d.first_instance + d.instance_count))
+        return enc.finish()
+
+    def submit(self) -> int:
+        idx = self.queue.submit([self.encode()])
+        return idx
+
+    def render(self) -> dict:
+        idx = self.submit()
+        self.device.poll(True, idx)
+        return self.device.last_pass_stats()
+
+    def read(self, want_coverage: bool = False) -> Frame:
+        s = self.scene
+        color = self.target.read()
+        depth = self.depth_texture.read() if self.depth_texture is not None else None
+        cov = self.device.read_coverage(s.width, s.height) if want_coverage else None
+        return Frame(color, depth, cov, self.device.last_pass_stats())
+
+
+def render_scene(device: api.Device, queue: api.Queue, scene: Scene, want_coverage: bool = True,
+                 use_emitted: bool = False) -> Frame:
+    device.set_coverage_capture(want_coverage)
+    r = SceneRenderer(device, queue, scene, use_emitted=use_emitted)
+    r.render()
+    f = r.read(want_coverage)
+    device.set_coverage_capture(False)
+    return f

@@ -1,0 +1,23 @@
+"""Shader registry: WGSL sources of the BASELINE configs / parity tests and, next to them, the
+CUDA C++ the WGSL->CUDA emitter produces for their entry points (`shaders/emitted/*.cuh`, kept as
+golden emitter output)."""
+from __future__ import annotations
+
+import os
+
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shaders")
+NAMES = ("colored_triangle", "hello_mesh", "hello_texture", "procedural", "features", "frag_depth")
+ALIASES = {"hello_shader": "colored_triangle"}
+
+
+def wgsl(name: str) -> str:
+    name = ALIASES.get(name, name)
+    with open(os.path.join(_DIR, name + ".wgsl")) as f:
+        return f.read()
+
+
+def emitted(name: str, stage: str) -> str:
+    """Golden emitter output for `vs_main` ("vs") / `fs_main` ("fs") of shader `name`."""
+    name = ALIASES.get(name, name)
+    with open(os.path.join(_DIR, "emitted", f"{name}.{stage}.cuh")) as f:
+        return f.read()

@@ -1,0 +1,24 @@
+// wgsl2cuda: colored_triangle.wgsl  stage=fragment  entry=fs_main
+namespace wgb_fragment {
+struct VertexInput { u32 vertex_index; };
+struct VertexOutput { vec4f position; vec4f color; };
+WGB_DEV vec4f fs_main(const WgbDraw& wgb, VertexOutput input) {
+    return input.color;
+}
+}  // namespace wgb_fragment
+#define WGB_FS_COLOR_MASK 1
+#define WGB_FS_WRITES_FRAG_DEPTH 0
+#define WGB_FS_MAY_DISCARD 0
+#define WGB_FS_EARLY_DEPTH 0
+WGB_DEV constexpr int wgb_fs_interp(int slot) {
+    return (slot >= WGB_VS_LOC0_SLOT && slot < WGB_VS_LOC0_SLOT + 4) ? 1 : 0;
+}
+WGB_DEV bool wgb_fs_entry(const WgbDraw& wgb, const WgbFragIn& fi, const u32* vary, WgbFragOut& out) {
+    wgb_fragment::VertexOutput a0;
+    a0.position = fi.position;
+    a0.color = wgb_get<vec4f>(vary, WGB_VS_LOC0_SLOT);
+    bool killed = false;
+    const vec4f r = wgb_fragment::fs_main(wgb, a0);
+    out.color[0] = r;
+    return !killed;
+}

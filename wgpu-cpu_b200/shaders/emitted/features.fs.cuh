@@ -1,0 +1,36 @@
+// wgsl2cuda: features.wgsl  stage=fragment  entry=fs_main
+namespace wgb_fragment {
+struct VertexInput { u32 vertex_index; u32 instance_index; vec4f vertex_position; vec4f vertex_color; };
+struct VertexOutput { vec4f position; vec4f color; u32 tag; };
+struct FragmentInput { vec4f position; bool front_facing; vec4f color; u32 tag; };
+WGB_DEV vec4f fs_main(const WgbDraw& wgb, bool& wgb_killed, FragmentInput input) {
+    const u32 px = wgb_to_u32(input.position.x);
+    const u32 py = wgb_to_u32(input.position.y);
+    if ((wgb_irem((wgb_idiv(px, 4u) + wgb_idiv(py, 4u)), 3u) == 0u)) {
+        wgb_killed = true;
+        return vec4f();
+    }
+    const f32 t = wgb_div(wgb_to_f32(wgb_irem(input.tag, 7u)), 7.0f);
+    const f32 facing = wgb_to_f32(input.front_facing);
+    return vec4f(input.color.x, wgb_mul(input.color.y, t), wgb_mul(input.color.z, facing), 1.0f);
+}
+}  // namespace wgb_fragment
+#define WGB_FS_COLOR_MASK 1
+#define WGB_FS_WRITES_FRAG_DEPTH 0
+#define WGB_FS_MAY_DISCARD 1
+#define WGB_FS_EARLY_DEPTH 0
+WGB_DEV constexpr int wgb_fs_interp(int slot) {
+    return (slot >= WGB_VS_LOC0_SLOT && slot < WGB_VS_LOC0_SLOT + 4) ? 1 : (slot >= WGB_VS_LOC1_SLOT && slot < WGB_VS_LOC1_SLOT + 1) ? 0 : 0;
+}
+WGB_DEV bool wgb_fs_entry(const WgbDraw& wgb, const WgbFragIn& fi, const u32* vary, WgbFragOut& out) {
+    wgb_fragment::FragmentInput a0;
+    a0.position = fi.position;
+    a0.front_facing = fi.front_facing;
+    a0.color = wgb_get<vec4f>(vary, WGB_VS_LOC0_SLOT);
+    a0.tag = wgb_get<u32>(vary, WGB_VS_LOC1_SLOT);
+    bool killed = false;
+    const vec4f r = wgb_fragment::fs_main(wgb, killed, a0);
+    if (killed) return false;
+    out.color[0] = r;
+    return !killed;
+}
