@@ -127,10 +127,12 @@ static void vs_features(const VsIn& in, VsOut& out, const Resources& res, int* e
     store_u32(out.inter + 16, in.vertex_index + in.instance_index * 1000u);
 }
 static void fs_features(const FsIn& in, FsOut& out, const Resources&, int*) {
-    /* as.rs: f32 -> u32 truncates (the reference traps when out of range; fragment
-     * positions are non-negative and small) */
-    const uint32_t px = (uint32_t)in.position.x;
-    const uint32_t py = (uint32_t)in.position.y;
+    /* as.rs: f32 -> u32 truncates and traps when out of range, so the shader bounds the
+     * (possibly extrapolated) position with selects first */
+    const float lx = in.position.x < 0.0f ? 0.0f : in.position.x;
+    const float ly = in.position.y < 0.0f ? 0.0f : in.position.y;
+    const uint32_t px = (uint32_t)(lx > 4096.0f ? 4096.0f : lx);
+    const uint32_t py = (uint32_t)(ly > 4096.0f ? 4096.0f : ly);
     if ((px / 4u + py / 4u) % 3u == 0u) { out.killed = true; return; }
     const Vec4 color = load_vec4(in.inter + 0);
     const uint32_t tag = load_u32(in.inter + 16);

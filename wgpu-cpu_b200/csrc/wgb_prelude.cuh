@@ -219,13 +219,13 @@ WGB_DEV u32 wgb_texel_coordinate(f32 x, u32 address_mode, u32 size) {
 
 // textureSample: nearest, mip 0, 2-D (binding.rs:93-149), texel decode u8 as f32 / 255.0
 // without sRGB decode (texture.rs:170-188).  The texel is fetched through the bindless
-// texture object with unnormalised integer coordinates, so the hardware never rounds.
+// texture object by integer element index, so the hardware never rounds or filters.
 WGB_DEV vec4f wgb_texture_sample(const WgbDraw& d, int tg, int tb, int sg, int sb, vec2f uv) {
     const WgbResource& t = d.res[tg][tb];
     const WgbResource& s = d.res[sg][sb];
     const u32 tx = wgb_texel_coordinate(uv.x, s.a, t.a);
     const u32 ty = wgb_texel_coordinate(uv.y, s.b, t.b);
-    const uchar4 p = tex2D<uchar4>((cudaTextureObject_t)t.tex, (float)tx, (float)ty);
+    const uchar4 p = tex1Dfetch<uchar4>((cudaTextureObject_t)t.tex, (int)(ty * t.a + tx));
     return vec4f(__fdiv_rn((f32)p.x, 255.0f), __fdiv_rn((f32)p.y, 255.0f), __fdiv_rn((f32)p.z, 255.0f),
                  __fdiv_rn((f32)p.w, 255.0f));
 }

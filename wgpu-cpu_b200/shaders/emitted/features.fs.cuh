@@ -4,8 +4,10 @@ struct VertexInput { u32 vertex_index; u32 instance_index; vec4f vertex_position
 struct VertexOutput { vec4f position; vec4f color; u32 tag; };
 struct FragmentInput { vec4f position; bool front_facing; vec4f color; u32 tag; };
 WGB_DEV vec4f fs_main(const WgbDraw& wgb, bool& wgb_killed, FragmentInput input) {
-    const u32 px = wgb_to_u32(input.position.x);
-    const u32 py = wgb_to_u32(input.position.y);
+    const f32 lx = wgb_select(input.position.x, 0.0f, (input.position.x < 0.0f));
+    const f32 ly = wgb_select(input.position.y, 0.0f, (input.position.y < 0.0f));
+    const u32 px = wgb_to_u32(wgb_select(lx, 4096.0f, (lx > 4096.0f)));
+    const u32 py = wgb_to_u32(wgb_select(ly, 4096.0f, (ly > 4096.0f)));
     if ((wgb_irem((wgb_idiv(px, 4u) + wgb_idiv(py, 4u)), 3u) == 0u)) {
         wgb_killed = true;
         return vec4f();

@@ -71,8 +71,12 @@ struct FragmentInput {
 
 @fragment
 fn fs_main(input: FragmentInput) -> @location(0) vec4f {
-    let px = u32(input.position.x);
-    let py = u32(input.position.y);
+    // the interpolated position is extrapolated for fragments outside their triangle (the
+    // reference's scan-line coverage has no inside test), so bound it before the trapping cast
+    let lx = select(input.position.x, 0.0, input.position.x < 0.0);
+    let ly = select(input.position.y, 0.0, input.position.y < 0.0);
+    let px = u32(select(lx, 4096.0, lx > 4096.0));
+    let py = u32(select(ly, 4096.0, ly > 4096.0));
     if ((px / 4u + py / 4u) % 3u == 0u) {
         discard;
     }
