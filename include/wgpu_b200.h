@@ -299,6 +299,10 @@ WGB_API wgb_status wgb_device_read_coverage(wgb_device device, uint32_t* dst, ui
 WGB_API wgb_status wgb_device_set_band(wgb_device device, uint32_t band_rank, uint32_t band_count);
 /* first and one-past-last pixel row of the band for a framebuffer of `height` rows */
 WGB_API wgb_status wgb_device_get_band_rows(wgb_device device, uint32_t height, uint32_t* out_row0, uint32_t* out_row1);
+/* CUDA-event timer on the device's stream: begin records an event, end records a second one,
+ * waits for it and returns the device time between the two in milliseconds */
+WGB_API wgb_status wgb_device_timer_begin(wgb_device device);
+WGB_API wgb_status wgb_device_timer_end(wgb_device device, float* out_ms);
 /* the CUDA stream submissions run on (cudaStream_t), for interop with collectives */
 WGB_API wgb_status wgb_device_get_stream(wgb_device device, void** out_stream);
 

@@ -579,6 +579,14 @@ class Device(_Handle):
         _check(_lib.wgb_device_get_band_rows(self._h, height, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def timer_begin(self):
+        _check(_lib.wgb_device_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        _check(_lib.wgb_device_timer_end(self._h, C.byref(ms)))
+        return ms.value
+
     def stream(self) -> int:
         p = C.c_void_p()
         _check(_lib.wgb_device_get_stream(self._h, C.byref(p)))

@@ -296,6 +296,7 @@ struct Device : Object {
     bool coverage_capture = false;
     uint32_t coverage_w = 0, coverage_h = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t timer_ev[2] = {nullptr, nullptr};
     wgb_pass_stats last_stats{};
     std::map<std::string, std::shared_ptr<KernelSet>> kernel_cache;   // by translation-unit text
 
@@ -310,6 +311,7 @@ struct Device : Object {
         for (DevBuf* b : bufs) b->release();
         if (host_counters) cudaFreeHost(host_counters);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& e : timer_ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -920,7 +922,7 @@ wgb_status wgb_adapter_get_info(wgb_adapter adapter, wgb_adapter_info* out) {
             cudaDeviceProp p;
             int cur = 0;
             cudaGetDevice(&cur);
-            if (cudaGetDeviceProperties(&p, cur) == cudaSuccess) snprintf(out->name, sizeof(out->name), "wgpu-b200 (%s)", p.name);
+            if (cudaGetDeviceProperties(&p, cur) == cudaSuccess) snprintf(out->name, sizeof(out->name), "wgpu-b200 (%.100s)", p.name);
         }
         if (!out->name[0]) snprintf(out->name, sizeof(out->name), "wgpu-b200 (no CUDA device)");
     });
@@ -953,6 +955,7 @@ wgb_status wgb_adapter_request_device(wgb_adapter adapter, const wgb_device_desc
             load_driver_api();
             CUDA_CHECK(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
             for (auto& e2 : dev->ev) CUDA_CHECK(cudaEventCreate(&e2));
+            for (auto& e2 : dev->timer_ev) CUDA_CHECK(cudaEventCreate(&e2));
             CUDA_CHECK(cudaMallocHost((void**)&dev->host_counters, sizeof(WgbCounters)));
         }
         dev->band_rank = dd.band_rank;
@@ -1521,6 +1524,27 @@ wgb_status wgb_device_get_band_rows(wgb_device device, uint32_t height, uint32_t
         band_rows(dev, (height + WGB_TILE_H - 1) / WGB_TILE_H, ty0, ty1);
         if (out_row0) *out_row0 = std::min(ty0 * WGB_TILE_H, height);
         if (out_row1) *out_row1 = std::min(ty1 * WGB_TILE_H, height);
+    });
+}
+wgb_status wgb_device_timer_begin(wgb_device device) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        std::lock_guard<std::recursive_mutex> lk(dev->mu);
+        if (dev->compile_only) fail(WGB_ERROR_DEVICE, "a compile-only device has no stream");
+        dev->make_current();
+        CUDA_CHECK(cudaEventRecord(dev->timer_ev[0], dev->stream));
+    });
+}
+wgb_status wgb_device_timer_end(wgb_device device, float* out_ms) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        REQUIRE(out_ms, "out is null");
+        std::lock_guard<std::recursive_mutex> lk(dev->mu);
+        if (dev->compile_only) fail(WGB_ERROR_DEVICE, "a compile-only device has no stream");
+        dev->make_current();
+        CUDA_CHECK(cudaEventRecord(dev->timer_ev[1], dev->stream));
+        CUDA_CHECK(cudaEventSynchronize(dev->timer_ev[1]));
+        CUDA_CHECK(cudaEventElapsedTime(out_ms, dev->timer_ev[0], dev->timer_ev[1]));
     });
 }
 wgb_status wgb_device_get_stream(wgb_device device, void** out_stream) {
