@@ -10,6 +10,7 @@ WGB_DEV vec4f fs_main(const WgbDraw& wgb, VertexOutput input) {
 #define WGB_FS_WRITES_FRAG_DEPTH 0
 #define WGB_FS_MAY_DISCARD 0
 #define WGB_FS_EARLY_DEPTH 0
+#define WGB_FS_USES_FRONT_FACING 0
 WGB_DEV constexpr int wgb_fs_interp(int slot) {
     return (slot >= WGB_VS_LOC0_SLOT && slot < WGB_VS_LOC0_SLOT + 4) ? 1 : 0;
 }
