@@ -176,7 +176,7 @@ def main():
     scene = make(S)
     W, H = scene.width, scene.height
     dev, queue = api.instance().request_adapter().request_device(local_rank, band_rank=rank, band_count=world)
-    r = SceneRenderer(dev, queue, scene, use_emitted=os.environ.get("WGB_USE_EMITTED", "1") == "1")
+    r = SceneRenderer(dev, queue, scene, use_emitted=os.environ.get("WGB_USE_EMITTED", "0") == "1")
     warm = max(args.warmup, 3)
 
     # presenter gather: every rank's colour band -> rank 0

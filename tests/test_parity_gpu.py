@@ -18,7 +18,7 @@ def gpu():
     return dev, queue
 
 
-def _compare(scene, gpu, use_emitted=True):
+def _compare(scene, gpu, use_emitted=False):
     from oracle import pyoracle
     from wgpu_cpu_b200.render import render_scene
     dev, queue = gpu
@@ -54,7 +54,7 @@ def test_colored_triangle_golden_identities(gpu):
     """tests/reference/*.png are LFS pointers; their oids still pin A == D and B == C == clear."""
     from wgpu_cpu_b200.render import render_scene
     dev, queue = gpu
-    img = {v: render_scene(dev, queue, S.colored_triangle(v), use_emitted=True).color
+    img = {v: render_scene(dev, queue, S.colored_triangle(v), use_emitted=False).color
            for v in ["default", "cull_front", "draw_backwards", "draw_backwards_no_cull"]}
     assert np.array_equal(img["default"], img["draw_backwards_no_cull"])
     assert np.array_equal(img["cull_front"], img["draw_backwards"])

@@ -100,8 +100,20 @@ WGB_VEC_INT_OP(u, u32, *)
 // ---------------------------------------------------------------------------------------
 // matrices (column-major, columns are vectors; types.rs:442-444)
 // ---------------------------------------------------------------------------------------
-struct mat2x2f { vec2f c[2]; WGB_DEV vec2f& operator[](int i) { return c[i]; } WGB_DEV const vec2f& operator[](int i) const { return c[i]; } };
-struct mat3x3f { vec3f c[3]; WGB_DEV vec3f& operator[](int i) { return c[i]; } WGB_DEV const vec3f& operator[](int i) const { return c[i]; } };
+struct mat2x2f {
+    vec2f c[2];
+    WGB_DEV mat2x2f() {}
+    WGB_DEV mat2x2f(vec2f c0, vec2f c1) { c[0] = c0; c[1] = c1; }
+    WGB_DEV vec2f& operator[](int i) { return c[i]; }
+    WGB_DEV const vec2f& operator[](int i) const { return c[i]; }
+};
+struct mat3x3f {
+    vec3f c[3];
+    WGB_DEV mat3x3f() {}
+    WGB_DEV mat3x3f(vec3f c0, vec3f c1, vec3f c2) { c[0] = c0; c[1] = c1; c[2] = c2; }
+    WGB_DEV vec3f& operator[](int i) { return c[i]; }
+    WGB_DEV const vec3f& operator[](int i) const { return c[i]; }
+};
 struct mat4x4f {
     vec4f c[4];
     WGB_DEV mat4x4f() {}
@@ -118,6 +130,26 @@ WGB_DEV mat4x4f operator*(const mat4x4f& m, f32 s) { return mat4x4f(m.c[0] * s, 
 WGB_DEV mat4x4f operator*(f32 s, const mat4x4f& m) { return mat4x4f(s * m.c[0], s * m.c[1], s * m.c[2], s * m.c[3]); }
 // matrix * matrix is a todo!() in the reference (binary.rs:254); defined column by column with the same rule
 WGB_DEV mat4x4f operator*(const mat4x4f& a, const mat4x4f& b) { return mat4x4f(a * b.c[0], a * b.c[1], a * b.c[2], a * b.c[3]); }
+WGB_DEV mat3x3f operator*(const mat3x3f& a, const mat3x3f& b) { return mat3x3f(a * b.c[0], a * b.c[1], a * b.c[2]); }
+WGB_DEV mat2x2f operator*(const mat2x2f& a, const mat2x2f& b) { return mat2x2f(a * b.c[0], a * b.c[1]); }
+WGB_DEV mat3x3f operator*(const mat3x3f& m, f32 s) { return mat3x3f(m.c[0] * s, m.c[1] * s, m.c[2] * s); }
+WGB_DEV mat3x3f operator*(f32 s, const mat3x3f& m) { return mat3x3f(s * m.c[0], s * m.c[1], s * m.c[2]); }
+WGB_DEV mat2x2f operator*(const mat2x2f& m, f32 s) { return mat2x2f(m.c[0] * s, m.c[1] * s); }
+WGB_DEV mat2x2f operator*(f32 s, const mat2x2f& m) { return mat2x2f(s * m.c[0], s * m.c[1]); }
+WGB_DEV mat4x4f operator+(const mat4x4f& a, const mat4x4f& b) { return mat4x4f(a.c[0] + b.c[0], a.c[1] + b.c[1], a.c[2] + b.c[2], a.c[3] + b.c[3]); }
+WGB_DEV mat4x4f operator-(const mat4x4f& a, const mat4x4f& b) { return mat4x4f(a.c[0] - b.c[0], a.c[1] - b.c[1], a.c[2] - b.c[2], a.c[3] - b.c[3]); }
+WGB_DEV mat3x3f operator+(const mat3x3f& a, const mat3x3f& b) { return mat3x3f(a.c[0] + b.c[0], a.c[1] + b.c[1], a.c[2] + b.c[2]); }
+WGB_DEV mat3x3f operator-(const mat3x3f& a, const mat3x3f& b) { return mat3x3f(a.c[0] - b.c[0], a.c[1] - b.c[1], a.c[2] - b.c[2]); }
+WGB_DEV mat2x2f operator+(const mat2x2f& a, const mat2x2f& b) { return mat2x2f(a.c[0] + b.c[0], a.c[1] + b.c[1]); }
+WGB_DEV mat2x2f operator-(const mat2x2f& a, const mat2x2f& b) { return mat2x2f(a.c[0] - b.c[0], a.c[1] - b.c[1]); }
+WGB_DEV mat4x4f wgb_transpose(const mat4x4f& m) {
+    return mat4x4f(vec4f(m.c[0].x, m.c[1].x, m.c[2].x, m.c[3].x), vec4f(m.c[0].y, m.c[1].y, m.c[2].y, m.c[3].y),
+                   vec4f(m.c[0].z, m.c[1].z, m.c[2].z, m.c[3].z), vec4f(m.c[0].w, m.c[1].w, m.c[2].w, m.c[3].w));
+}
+WGB_DEV mat3x3f wgb_transpose(const mat3x3f& m) {
+    return mat3x3f(vec3f(m.c[0].x, m.c[1].x, m.c[2].x), vec3f(m.c[0].y, m.c[1].y, m.c[2].y), vec3f(m.c[0].z, m.c[1].z, m.c[2].z));
+}
+WGB_DEV mat2x2f wgb_transpose(const mat2x2f& m) { return mat2x2f(vec2f(m.c[0].x, m.c[1].x), vec2f(m.c[0].y, m.c[1].y)); }
 
 // ---------------------------------------------------------------------------------------
 // casts (expression/as.rs:60-184).  float -> int traps in the reference when out of
@@ -147,8 +179,193 @@ WGB_DEV u32 wgb_idiv(u32 a, u32 b) { return b == 0u ? a : a / b; }
 WGB_DEV i32 wgb_irem(i32 a, i32 b) { return (b == 0 || (a == (-2147483647 - 1) && b == -1)) ? 0 : a % b; }
 WGB_DEV u32 wgb_irem(u32 a, u32 b) { return b == 0u ? 0u : a % b; }
 
-// select(f, t, cond) (expression/select.rs:36-103: scalar condition)
+// component-wise lifting of scalar functions to vectors (and vector (x) scalar)
+#define WGB_LIFT1(FN, S)                                                                            \
+    WGB_DEV vec2##S FN(vec2##S a) { return vec2##S(FN(a.x), FN(a.y)); }                               \
+    WGB_DEV vec3##S FN(vec3##S a) { return vec3##S(FN(a.x), FN(a.y), FN(a.z)); }                      \
+    WGB_DEV vec4##S FN(vec4##S a) { return vec4##S(FN(a.x), FN(a.y), FN(a.z), FN(a.w)); }
+#define WGB_LIFT2(FN, S, T)                                                                         \
+    WGB_DEV vec2##S FN(vec2##S a, vec2##S b) { return vec2##S(FN(a.x, b.x), FN(a.y, b.y)); }          \
+    WGB_DEV vec3##S FN(vec3##S a, vec3##S b) { return vec3##S(FN(a.x, b.x), FN(a.y, b.y), FN(a.z, b.z)); } \
+    WGB_DEV vec4##S FN(vec4##S a, vec4##S b) { return vec4##S(FN(a.x, b.x), FN(a.y, b.y), FN(a.z, b.z), FN(a.w, b.w)); } \
+    WGB_DEV vec2##S FN(vec2##S a, T b) { return vec2##S(FN(a.x, b), FN(a.y, b)); }                    \
+    WGB_DEV vec3##S FN(vec3##S a, T b) { return vec3##S(FN(a.x, b), FN(a.y, b), FN(a.z, b)); }        \
+    WGB_DEV vec4##S FN(vec4##S a, T b) { return vec4##S(FN(a.x, b), FN(a.y, b), FN(a.z, b), FN(a.w, b)); } \
+    WGB_DEV vec2##S FN(T a, vec2##S b) { return vec2##S(FN(a, b.x), FN(a, b.y)); }                    \
+    WGB_DEV vec3##S FN(T a, vec3##S b) { return vec3##S(FN(a, b.x), FN(a, b.y), FN(a, b.z)); }        \
+    WGB_DEV vec4##S FN(T a, vec4##S b) { return vec4##S(FN(a, b.x), FN(a, b.y), FN(a, b.z), FN(a, b.w)); }
+WGB_LIFT2(wgb_idiv, i, i32)
+WGB_LIFT2(wgb_idiv, u, u32)
+WGB_LIFT2(wgb_irem, i, i32)
+WGB_LIFT2(wgb_irem, u, u32)
+WGB_LIFT2(wgb_rem, f, f32)
+WGB_DEV vec2i operator-(vec2i a) { return vec2i(-a.x, -a.y); }
+WGB_DEV vec3i operator-(vec3i a) { return vec3i(-a.x, -a.y, -a.z); }
+WGB_DEV vec4i operator-(vec4i a) { return vec4i(-a.x, -a.y, -a.z, -a.w); }
+
+// vector comparisons -> vecNb (expression/binary.rs:172-209 is scalar-only in the reference)
+#define WGB_VEC_CMP(NAME, OP, S)                                                                    \
+    WGB_DEV vec2b NAME(vec2##S a, vec2##S b) { return vec2b(a.x OP b.x, a.y OP b.y); }                \
+    WGB_DEV vec3b NAME(vec3##S a, vec3##S b) { return vec3b(a.x OP b.x, a.y OP b.y, a.z OP b.z); }    \
+    WGB_DEV vec4b NAME(vec4##S a, vec4##S b) { return vec4b(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w); }
+#define WGB_VEC_CMP_ALL(S) WGB_VEC_CMP(wgb_eq, ==, S) WGB_VEC_CMP(wgb_ne, !=, S) WGB_VEC_CMP(wgb_lt, <, S) \
+    WGB_VEC_CMP(wgb_gt, >, S) WGB_VEC_CMP(wgb_le, <=, S) WGB_VEC_CMP(wgb_ge, >=, S)
+WGB_VEC_CMP_ALL(f)
+WGB_VEC_CMP_ALL(i)
+WGB_VEC_CMP_ALL(u)
+WGB_VEC_CMP(wgb_eq, ==, b)
+WGB_VEC_CMP(wgb_ne, !=, b)
+WGB_DEV vec2b wgb_not(vec2b a) { return vec2b(!a.x, !a.y); }
+WGB_DEV vec3b wgb_not(vec3b a) { return vec3b(!a.x, !a.y, !a.z); }
+WGB_DEV vec4b wgb_not(vec4b a) { return vec4b(!a.x, !a.y, !a.z, !a.w); }
+WGB_DEV bool wgb_all(bool a) { return a; }
+WGB_DEV bool wgb_all(vec2b a) { return a.x && a.y; }
+WGB_DEV bool wgb_all(vec3b a) { return a.x && a.y && a.z; }
+WGB_DEV bool wgb_all(vec4b a) { return a.x && a.y && a.z && a.w; }
+WGB_DEV bool wgb_any(bool a) { return a; }
+WGB_DEV bool wgb_any(vec2b a) { return a.x || a.y; }
+WGB_DEV bool wgb_any(vec3b a) { return a.x || a.y || a.z; }
+WGB_DEV bool wgb_any(vec4b a) { return a.x || a.y || a.z || a.w; }
+#define WGB_INT_BITOPS(S, T)                                                                        \
+    WGB_DEV T wgb_and(T a, T b) { return a & b; } WGB_DEV T wgb_or(T a, T b) { return a | b; } WGB_DEV T wgb_xor(T a, T b) { return a ^ b; } \
+    WGB_DEV T wgb_bitnot(T a) { return ~a; }                                                         \
+    WGB_DEV T wgb_shl(T a, u32 b) { return a << (b & 31u); } WGB_DEV T wgb_shr(T a, u32 b) { return a >> (b & 31u); } \
+    WGB_LIFT2(wgb_and, S, T) WGB_LIFT2(wgb_or, S, T) WGB_LIFT2(wgb_xor, S, T) WGB_LIFT1(wgb_bitnot, S) \
+    WGB_DEV vec2##S wgb_shl(vec2##S a, vec2u b) { return vec2##S(wgb_shl(a.x, b.x), wgb_shl(a.y, b.y)); } \
+    WGB_DEV vec3##S wgb_shl(vec3##S a, vec3u b) { return vec3##S(wgb_shl(a.x, b.x), wgb_shl(a.y, b.y), wgb_shl(a.z, b.z)); } \
+    WGB_DEV vec4##S wgb_shl(vec4##S a, vec4u b) { return vec4##S(wgb_shl(a.x, b.x), wgb_shl(a.y, b.y), wgb_shl(a.z, b.z), wgb_shl(a.w, b.w)); } \
+    WGB_DEV vec2##S wgb_shr(vec2##S a, vec2u b) { return vec2##S(wgb_shr(a.x, b.x), wgb_shr(a.y, b.y)); } \
+    WGB_DEV vec3##S wgb_shr(vec3##S a, vec3u b) { return vec3##S(wgb_shr(a.x, b.x), wgb_shr(a.y, b.y), wgb_shr(a.z, b.z)); } \
+    WGB_DEV vec4##S wgb_shr(vec4##S a, vec4u b) { return vec4##S(wgb_shr(a.x, b.x), wgb_shr(a.y, b.y), wgb_shr(a.z, b.z), wgb_shr(a.w, b.w)); }
+WGB_INT_BITOPS(i, i32)
+WGB_INT_BITOPS(u, u32)
+
+// select(f, t, cond) (expression/select.rs:36-103: scalar condition; vector conditions select per component)
 template <class T> WGB_DEV T wgb_select(T f, T t, bool cond) { return cond ? t : f; }
+#define WGB_VEC_SELECT(S)                                                                           \
+    WGB_DEV vec2##S wgb_select(vec2##S f, vec2##S t, vec2b c) { return vec2##S(c.x ? t.x : f.x, c.y ? t.y : f.y); } \
+    WGB_DEV vec3##S wgb_select(vec3##S f, vec3##S t, vec3b c) { return vec3##S(c.x ? t.x : f.x, c.y ? t.y : f.y, c.z ? t.z : f.z); } \
+    WGB_DEV vec4##S wgb_select(vec4##S f, vec4##S t, vec4b c) { return vec4##S(c.x ? t.x : f.x, c.y ? t.y : f.y, c.z ? t.z : f.z, c.w ? t.w : f.w); }
+WGB_VEC_SELECT(f)
+WGB_VEC_SELECT(i)
+WGB_VEC_SELECT(u)
+WGB_VEC_SELECT(b)
+
+template <class To, class From> WGB_DEV To wgb_bitcast(From v) { static_assert(sizeof(To) == sizeof(From), "bitcast size"); To r; memcpy(&r, &v, sizeof(To)); return r; }
+
+// fixed-size arrays by value
+template <class T, int N> struct wgb_array {
+    T v[N];
+    WGB_DEV T& operator[](u32 i) { return v[i]; }
+    WGB_DEV const T& operator[](u32 i) const { return v[i]; }
+};
+
+// ---------------------------------------------------------------------------------------
+// math builtins.  The reference leaves every one of them as todo!() (expression/math.rs:23,29),
+// so there is no reference arithmetic to match; they are IEEE single precision, unfused.
+// ---------------------------------------------------------------------------------------
+WGB_DEV f32 wgb_abs(f32 a) { return fabsf(a); }
+WGB_DEV i32 wgb_abs(i32 a) { return a < 0 ? -a : a; }
+WGB_DEV u32 wgb_abs(u32 a) { return a; }
+WGB_DEV f32 wgb_min(f32 a, f32 b) { return fminf(a, b); }
+WGB_DEV i32 wgb_min(i32 a, i32 b) { return a < b ? a : b; }
+WGB_DEV u32 wgb_min(u32 a, u32 b) { return a < b ? a : b; }
+WGB_DEV f32 wgb_max(f32 a, f32 b) { return fmaxf(a, b); }
+WGB_DEV i32 wgb_max(i32 a, i32 b) { return a > b ? a : b; }
+WGB_DEV u32 wgb_max(u32 a, u32 b) { return a > b ? a : b; }
+WGB_DEV f32 wgb_floor(f32 a) { return floorf(a); }
+WGB_DEV f32 wgb_ceil(f32 a) { return ceilf(a); }
+WGB_DEV f32 wgb_round(f32 a) { return rintf(a); }          // WGSL round: ties to even
+WGB_DEV f32 wgb_trunc(f32 a) { return truncf(a); }
+WGB_DEV f32 wgb_fract(f32 a) { return __fsub_rn(a, floorf(a)); }
+WGB_DEV f32 wgb_sqrt(f32 a) { return __fsqrt_rn(a); }
+WGB_DEV f32 wgb_inverseSqrt(f32 a) { return __fdiv_rn(1.0f, __fsqrt_rn(a)); }
+WGB_DEV f32 wgb_sin(f32 a) { return sinf(a); }
+WGB_DEV f32 wgb_cos(f32 a) { return cosf(a); }
+WGB_DEV f32 wgb_tan(f32 a) { return tanf(a); }
+WGB_DEV f32 wgb_asin(f32 a) { return asinf(a); }
+WGB_DEV f32 wgb_acos(f32 a) { return acosf(a); }
+WGB_DEV f32 wgb_atan(f32 a) { return atanf(a); }
+WGB_DEV f32 wgb_atan2(f32 a, f32 b) { return atan2f(a, b); }
+WGB_DEV f32 wgb_sinh(f32 a) { return sinhf(a); }
+WGB_DEV f32 wgb_cosh(f32 a) { return coshf(a); }
+WGB_DEV f32 wgb_tanh(f32 a) { return tanhf(a); }
+WGB_DEV f32 wgb_exp(f32 a) { return expf(a); }
+WGB_DEV f32 wgb_exp2(f32 a) { return exp2f(a); }
+WGB_DEV f32 wgb_log(f32 a) { return logf(a); }
+WGB_DEV f32 wgb_log2(f32 a) { return log2f(a); }
+WGB_DEV f32 wgb_pow(f32 a, f32 b) { return powf(a, b); }
+WGB_DEV f32 wgb_sign(f32 a) { return a > 0.0f ? 1.0f : (a < 0.0f ? -1.0f : 0.0f); }
+WGB_DEV i32 wgb_sign(i32 a) { return a > 0 ? 1 : (a < 0 ? -1 : 0); }
+WGB_DEV f32 wgb_step(f32 edge, f32 x) { return x >= edge ? 1.0f : 0.0f; }
+WGB_DEV f32 wgb_saturate(f32 a) { return fminf(fmaxf(a, 0.0f), 1.0f); }
+WGB_DEV f32 wgb_degrees(f32 a) { return __fmul_rn(a, 57.295779513082322865f); }
+WGB_DEV f32 wgb_radians(f32 a) { return __fmul_rn(a, 0.017453292519943295474f); }
+WGB_DEV f32 wgb_clamp(f32 x, f32 lo, f32 hi) { return fminf(fmaxf(x, lo), hi); }
+WGB_DEV i32 wgb_clamp(i32 x, i32 lo, i32 hi) { return wgb_min(wgb_max(x, lo), hi); }
+WGB_DEV u32 wgb_clamp(u32 x, u32 lo, u32 hi) { return wgb_min(wgb_max(x, lo), hi); }
+WGB_DEV f32 wgb_mix(f32 a, f32 b, f32 t) { return __fadd_rn(__fmul_rn(a, __fsub_rn(1.0f, t)), __fmul_rn(b, t)); }
+WGB_DEV f32 wgb_fma(f32 a, f32 b, f32 c) { return __fmaf_rn(a, b, c); }
+WGB_DEV f32 wgb_smoothstep(f32 lo, f32 hi, f32 x) {
+    const f32 t = wgb_saturate(__fdiv_rn(__fsub_rn(x, lo), __fsub_rn(hi, lo)));
+    return __fmul_rn(__fmul_rn(t, t), __fsub_rn(3.0f, __fmul_rn(2.0f, t)));
+}
+#define WGB_LIFT1F(FN) WGB_LIFT1(FN, f)
+WGB_LIFT1F(wgb_abs) WGB_LIFT1F(wgb_floor) WGB_LIFT1F(wgb_ceil) WGB_LIFT1F(wgb_round) WGB_LIFT1F(wgb_trunc) WGB_LIFT1F(wgb_fract)
+WGB_LIFT1F(wgb_sqrt) WGB_LIFT1F(wgb_inverseSqrt) WGB_LIFT1F(wgb_sin) WGB_LIFT1F(wgb_cos) WGB_LIFT1F(wgb_tan) WGB_LIFT1F(wgb_asin)
+WGB_LIFT1F(wgb_acos) WGB_LIFT1F(wgb_atan) WGB_LIFT1F(wgb_sinh) WGB_LIFT1F(wgb_cosh) WGB_LIFT1F(wgb_tanh) WGB_LIFT1F(wgb_exp)
+WGB_LIFT1F(wgb_exp2) WGB_LIFT1F(wgb_log) WGB_LIFT1F(wgb_log2) WGB_LIFT1F(wgb_sign) WGB_LIFT1F(wgb_saturate) WGB_LIFT1F(wgb_degrees)
+WGB_LIFT1F(wgb_radians)
+WGB_LIFT1(wgb_abs, i) WGB_LIFT1(wgb_sign, i)
+WGB_LIFT2(wgb_min, f, f32) WGB_LIFT2(wgb_max, f, f32) WGB_LIFT2(wgb_atan2, f, f32) WGB_LIFT2(wgb_pow, f, f32) WGB_LIFT2(wgb_step, f, f32)
+WGB_LIFT2(wgb_min, i, i32) WGB_LIFT2(wgb_max, i, i32) WGB_LIFT2(wgb_min, u, u32) WGB_LIFT2(wgb_max, u, u32)
+#define WGB_LIFT3(FN, S, T)                                                                         \
+    WGB_DEV vec2##S FN(vec2##S a, vec2##S b, vec2##S c) { return vec2##S(FN(a.x, b.x, c.x), FN(a.y, b.y, c.y)); } \
+    WGB_DEV vec3##S FN(vec3##S a, vec3##S b, vec3##S c) { return vec3##S(FN(a.x, b.x, c.x), FN(a.y, b.y, c.y), FN(a.z, b.z, c.z)); } \
+    WGB_DEV vec4##S FN(vec4##S a, vec4##S b, vec4##S c) { return vec4##S(FN(a.x, b.x, c.x), FN(a.y, b.y, c.y), FN(a.z, b.z, c.z), FN(a.w, b.w, c.w)); } \
+    WGB_DEV vec2##S FN(vec2##S a, T b, T c) { return vec2##S(FN(a.x, b, c), FN(a.y, b, c)); }        \
+    WGB_DEV vec3##S FN(vec3##S a, T b, T c) { return vec3##S(FN(a.x, b, c), FN(a.y, b, c), FN(a.z, b, c)); } \
+    WGB_DEV vec4##S FN(vec4##S a, T b, T c) { return vec4##S(FN(a.x, b, c), FN(a.y, b, c), FN(a.z, b, c), FN(a.w, b, c)); }
+WGB_LIFT3(wgb_clamp, f, f32) WGB_LIFT3(wgb_clamp, i, i32) WGB_LIFT3(wgb_clamp, u, u32) WGB_LIFT3(wgb_fma, f, f32)
+WGB_DEV vec2f wgb_mix(vec2f a, vec2f b, vec2f t) { return vec2f(wgb_mix(a.x, b.x, t.x), wgb_mix(a.y, b.y, t.y)); }
+WGB_DEV vec3f wgb_mix(vec3f a, vec3f b, vec3f t) { return vec3f(wgb_mix(a.x, b.x, t.x), wgb_mix(a.y, b.y, t.y), wgb_mix(a.z, b.z, t.z)); }
+WGB_DEV vec4f wgb_mix(vec4f a, vec4f b, vec4f t) { return vec4f(wgb_mix(a.x, b.x, t.x), wgb_mix(a.y, b.y, t.y), wgb_mix(a.z, b.z, t.z), wgb_mix(a.w, b.w, t.w)); }
+WGB_DEV vec2f wgb_mix(vec2f a, vec2f b, f32 t) { return wgb_mix(a, b, vec2f(t)); }
+WGB_DEV vec3f wgb_mix(vec3f a, vec3f b, f32 t) { return wgb_mix(a, b, vec3f(t)); }
+WGB_DEV vec4f wgb_mix(vec4f a, vec4f b, f32 t) { return wgb_mix(a, b, vec4f(t)); }
+WGB_DEV vec2f wgb_smoothstep(vec2f a, vec2f b, vec2f x) { return vec2f(wgb_smoothstep(a.x, b.x, x.x), wgb_smoothstep(a.y, b.y, x.y)); }
+WGB_DEV vec3f wgb_smoothstep(vec3f a, vec3f b, vec3f x) { return vec3f(wgb_smoothstep(a.x, b.x, x.x), wgb_smoothstep(a.y, b.y, x.y), wgb_smoothstep(a.z, b.z, x.z)); }
+WGB_DEV vec4f wgb_smoothstep(vec4f a, vec4f b, vec4f x) { return vec4f(wgb_smoothstep(a.x, b.x, x.x), wgb_smoothstep(a.y, b.y, x.y), wgb_smoothstep(a.z, b.z, x.z), wgb_smoothstep(a.w, b.w, x.w)); }
+WGB_DEV vec2f wgb_smoothstep(f32 a, f32 b, vec2f x) { return wgb_smoothstep(vec2f(a), vec2f(b), x); }
+WGB_DEV vec3f wgb_smoothstep(f32 a, f32 b, vec3f x) { return wgb_smoothstep(vec3f(a), vec3f(b), x); }
+WGB_DEV vec4f wgb_smoothstep(f32 a, f32 b, vec4f x) { return wgb_smoothstep(vec4f(a), vec4f(b), x); }
+WGB_DEV f32 wgb_dot(vec2f a, vec2f b) { return __fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+WGB_DEV f32 wgb_dot(vec3f a, vec3f b) { return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z)); }
+WGB_DEV f32 wgb_dot(vec4f a, vec4f b) { return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z)), __fmul_rn(a.w, b.w)); }
+WGB_DEV i32 wgb_dot(vec2i a, vec2i b) { return a.x * b.x + a.y * b.y; }
+WGB_DEV i32 wgb_dot(vec3i a, vec3i b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+WGB_DEV i32 wgb_dot(vec4i a, vec4i b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+WGB_DEV u32 wgb_dot(vec2u a, vec2u b) { return a.x * b.x + a.y * b.y; }
+WGB_DEV u32 wgb_dot(vec3u a, vec3u b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+WGB_DEV u32 wgb_dot(vec4u a, vec4u b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+WGB_DEV vec3f wgb_cross(vec3f a, vec3f b) {
+    return vec3f(__fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(a.z, b.y)), __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(a.x, b.z)),
+                 __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
+WGB_DEV f32 wgb_length(f32 a) { return fabsf(a); }
+WGB_DEV f32 wgb_length(vec2f a) { return __fsqrt_rn(wgb_dot(a, a)); }
+WGB_DEV f32 wgb_length(vec3f a) { return __fsqrt_rn(wgb_dot(a, a)); }
+WGB_DEV f32 wgb_length(vec4f a) { return __fsqrt_rn(wgb_dot(a, a)); }
+WGB_DEV f32 wgb_distance(f32 a, f32 b) { return fabsf(__fsub_rn(a, b)); }
+WGB_DEV f32 wgb_distance(vec2f a, vec2f b) { return wgb_length(a - b); }
+WGB_DEV f32 wgb_distance(vec3f a, vec3f b) { return wgb_length(a - b); }
+WGB_DEV f32 wgb_distance(vec4f a, vec4f b) { return wgb_length(a - b); }
+WGB_DEV vec2f wgb_normalize(vec2f a) { return a / wgb_length(a); }
+WGB_DEV vec3f wgb_normalize(vec3f a) { return a / wgb_length(a); }
+WGB_DEV vec4f wgb_normalize(vec4f a) { return a / wgb_length(a); }
+WGB_DEV vec2f wgb_reflect(vec2f e, vec2f n) { return e - n * __fmul_rn(2.0f, wgb_dot(n, e)); }
+WGB_DEV vec3f wgb_reflect(vec3f e, vec3f n) { return e - n * __fmul_rn(2.0f, wgb_dot(n, e)); }
+WGB_DEV vec4f wgb_reflect(vec4f e, vec4f n) { return e - n * __fmul_rn(2.0f, wgb_dot(n, e)); }
 
 // ---------------------------------------------------------------------------------------
 // resources
@@ -175,6 +392,19 @@ template <> WGB_DEV vec3f wgb_load<vec3f>(const WgbDraw& d, int g, int b, u32 of
 template <> WGB_DEV vec4f wgb_load<vec4f>(const WgbDraw& d, int g, int b, u32 off) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(d.res[g][b].ptr + off));
     return vec4f(v.x, v.y, v.z, v.w);
+}
+template <> WGB_DEV vec2i wgb_load<vec2i>(const WgbDraw& d, int g, int b, u32 off) { return vec2i(wgb_load<i32>(d, g, b, off), wgb_load<i32>(d, g, b, off + 4)); }
+template <> WGB_DEV vec3i wgb_load<vec3i>(const WgbDraw& d, int g, int b, u32 off) { return vec3i(wgb_load<i32>(d, g, b, off), wgb_load<i32>(d, g, b, off + 4), wgb_load<i32>(d, g, b, off + 8)); }
+template <> WGB_DEV vec4i wgb_load<vec4i>(const WgbDraw& d, int g, int b, u32 off) { return vec4i(wgb_load<i32>(d, g, b, off), wgb_load<i32>(d, g, b, off + 4), wgb_load<i32>(d, g, b, off + 8), wgb_load<i32>(d, g, b, off + 12)); }
+template <> WGB_DEV vec2u wgb_load<vec2u>(const WgbDraw& d, int g, int b, u32 off) { return vec2u(wgb_load<u32>(d, g, b, off), wgb_load<u32>(d, g, b, off + 4)); }
+template <> WGB_DEV vec3u wgb_load<vec3u>(const WgbDraw& d, int g, int b, u32 off) { return vec3u(wgb_load<u32>(d, g, b, off), wgb_load<u32>(d, g, b, off + 4), wgb_load<u32>(d, g, b, off + 8)); }
+template <> WGB_DEV vec4u wgb_load<vec4u>(const WgbDraw& d, int g, int b, u32 off) { return vec4u(wgb_load<u32>(d, g, b, off), wgb_load<u32>(d, g, b, off + 4), wgb_load<u32>(d, g, b, off + 8), wgb_load<u32>(d, g, b, off + 12)); }
+// matrix columns are 16-byte aligned for 3 and 4 rows, 8-byte aligned for 2 rows (WGSL layout)
+template <> WGB_DEV mat3x3f wgb_load<mat3x3f>(const WgbDraw& d, int g, int b, u32 off) {
+    return mat3x3f(wgb_load<vec3f>(d, g, b, off), wgb_load<vec3f>(d, g, b, off + 16), wgb_load<vec3f>(d, g, b, off + 32));
+}
+template <> WGB_DEV mat2x2f wgb_load<mat2x2f>(const WgbDraw& d, int g, int b, u32 off) {
+    return mat2x2f(wgb_load<vec2f>(d, g, b, off), wgb_load<vec2f>(d, g, b, off + 8));
 }
 template <> WGB_DEV mat4x4f wgb_load<mat4x4f>(const WgbDraw& d, int g, int b, u32 off) {
     return mat4x4f(wgb_load<vec4f>(d, g, b, off), wgb_load<vec4f>(d, g, b, off + 16),
@@ -228,6 +458,16 @@ WGB_DEV vec4f wgb_texture_sample(const WgbDraw& d, int tg, int tb, int sg, int s
     const uchar4 p = tex1Dfetch<uchar4>((cudaTextureObject_t)t.tex, (int)(ty * t.a + tx));
     return vec4f(__fdiv_rn((f32)p.x, 255.0f), __fdiv_rn((f32)p.y, 255.0f), __fdiv_rn((f32)p.z, 255.0f),
                  __fdiv_rn((f32)p.w, 255.0f));
+}
+
+WGB_DEV vec2u wgb_texture_dimensions(const WgbDraw& d, int tg, int tb) { return vec2u(d.res[tg][tb].a, d.res[tg][tb].b); }
+// textureLoad (ImageLoad is a todo!() in the reference, expression/image.rs:107): out-of-range texels read as zero
+template <class V> WGB_DEV vec4f wgb_texture_load(const WgbDraw& d, int tg, int tb, V c) {
+    const WgbResource& t = d.res[tg][tb];
+    const u32 x = (u32)c.x, y = (u32)c.y;
+    if (x >= t.a || y >= t.b) return vec4f();
+    const uchar4 p = tex1Dfetch<uchar4>((cudaTextureObject_t)t.tex, (int)(y * t.a + x));
+    return vec4f(__fdiv_rn((f32)p.x, 255.0f), __fdiv_rn((f32)p.y, 255.0f), __fdiv_rn((f32)p.z, 255.0f), __fdiv_rn((f32)p.w, 255.0f));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -305,6 +545,18 @@ template <> WGB_DEV i32 wgb_fetch_raw<i32>(const WgbDraw& d, int slot, u32 strid
     WGB_FETCH_ADDR()
     return __ldg(reinterpret_cast<const i32*>(addr));
 }
+#define WGB_FETCH_VEC(VT, ST, N)                                                                    \
+    template <> WGB_DEV VT wgb_fetch_raw<VT>(const WgbDraw& d, int slot, u32 stride, u32 offset, bool per_instance, \
+                                             u32 vertex_index, u32 instance_index, u32& oob) {        \
+        typedef VT T;                                                                               \
+        WGB_FETCH_ADDR()                                                                            \
+        const ST* p = reinterpret_cast<const ST*>(addr);                                            \
+        VT r;                                                                                       \
+        for (int i = 0; i < N; i++) r[i] = __ldg(p + i);                                            \
+        return r;                                                                                   \
+    }
+WGB_FETCH_VEC(vec2u, u32, 2) WGB_FETCH_VEC(vec3u, u32, 3) WGB_FETCH_VEC(vec4u, u32, 4)
+WGB_FETCH_VEC(vec2i, i32, 2) WGB_FETCH_VEC(vec3i, i32, 3) WGB_FETCH_VEC(vec4i, i32, 4)
 // WGB_FETCH(T, LOC): expands to the fetch for @location(LOC) of the bound pipeline layout
 #define WGB_FETCH(T, LOC)                                                                           \
     wgb_fetch_raw<T>(wgb, WGB_ATTR##LOC##_SLOT, WGB_ATTR##LOC##_STRIDE, WGB_ATTR##LOC##_OFFSET,        \

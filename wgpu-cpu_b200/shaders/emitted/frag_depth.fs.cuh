@@ -1,9 +1,14 @@
-// wgsl2cuda: frag_depth.wgsl  stage=fragment  entry=fs_main
+// wgsl2cuda: stage=fragment entry=fs_main
 namespace wgb_fragment {
 struct VertexInput { vec4f vertex_position; vec4f vertex_color; };
 struct VertexOutput { vec4f position; vec4f color; };
+struct Camera { mat4x4f matrix; };
 struct FragmentOutput { f32 depth; vec4f color; };
-WGB_DEV FragmentOutput fs_main(const WgbDraw& wgb, VertexOutput input) {
+struct WgbInvocation {
+    bool killed = false;
+};
+WGB_DEV FragmentOutput fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, VertexOutput input);
+WGB_DEV FragmentOutput fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, VertexOutput input) {
     const f32 depth = wgb_sub(1.0f, wgb_mul(input.position.z, input.color.x));
     return FragmentOutput{depth, input.color};
 }
@@ -17,12 +22,13 @@ WGB_DEV constexpr int wgb_fs_interp(int slot) {
     return (slot >= WGB_VS_LOC0_SLOT && slot < WGB_VS_LOC0_SLOT + 4) ? 1 : 0;
 }
 WGB_DEV bool wgb_fs_entry(const WgbDraw& wgb, const WgbFragIn& fi, const u32* vary, WgbFragOut& out) {
+    wgb_fragment::WgbInvocation wgb_inv;
     wgb_fragment::VertexOutput a0;
     a0.position = fi.position;
     a0.color = wgb_get<vec4f>(vary, WGB_VS_LOC0_SLOT);
-    bool killed = false;
-    const wgb_fragment::FragmentOutput r = wgb_fragment::fs_main(wgb, a0);
+    const wgb_fragment::FragmentOutput r = wgb_fragment::fs_main(wgb, wgb_inv, a0);
+    if (wgb_inv.killed) return false;
     out.frag_depth = r.depth;
     out.color[0] = r.color;
-    return !killed;
+    return true;
 }

@@ -1,8 +1,13 @@
-// wgsl2cuda: hello_texture.wgsl  stage=fragment  entry=fs_main
+// wgsl2cuda: stage=fragment entry=fs_main
 namespace wgb_fragment {
 struct VertexInput { u32 vertex_index; vec4f vertex_position; vec2f uv; };
 struct VertexOutput { vec4f position; vec2f uv; };
-WGB_DEV vec4f fs_main(const WgbDraw& wgb, VertexOutput input) {
+struct Camera { mat4x4f matrix; };
+struct WgbInvocation {
+    bool killed = false;
+};
+WGB_DEV vec4f fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, VertexOutput input);
+WGB_DEV vec4f fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, VertexOutput input) {
     vec4f color = wgb_texture_sample(wgb, 1, 0, 1, 1, input.uv);
     return color;
 }
@@ -16,11 +21,12 @@ WGB_DEV constexpr int wgb_fs_interp(int slot) {
     return (slot >= WGB_VS_LOC0_SLOT && slot < WGB_VS_LOC0_SLOT + 2) ? 1 : 0;
 }
 WGB_DEV bool wgb_fs_entry(const WgbDraw& wgb, const WgbFragIn& fi, const u32* vary, WgbFragOut& out) {
+    wgb_fragment::WgbInvocation wgb_inv;
     wgb_fragment::VertexOutput a0;
     a0.position = fi.position;
     a0.uv = wgb_get<vec2f>(vary, WGB_VS_LOC0_SLOT);
-    bool killed = false;
-    const vec4f r = wgb_fragment::fs_main(wgb, a0);
+    const vec4f r = wgb_fragment::fs_main(wgb, wgb_inv, a0);
+    if (wgb_inv.killed) return false;
     out.color[0] = r;
-    return !killed;
+    return true;
 }
