@@ -180,23 +180,19 @@ def main():
     warm = max(args.warmup, 3)
 
     # presenter gather: every rank's colour band -> rank 0
+    from wgpu_cpu_b200 import multigpu
     row0, row1 = dev.band_rows(H)
+    assert (row0, row1) == multigpu.band_rows(H, rank, world)
     frame_t = None
     if world > 1:
         ptr, nbytes = r.target.device_pointer()
-        frame_t = _tensor_from_ptr(torch, ptr, nbytes, local_rank).view(H, W, 4)
-        rows = [_band_rows(H, k, world) for k in range(world)]
+        frame_t = multigpu.tensor_from_device_pointer(ptr, nbytes, local_rank).view(H, W, 4)
 
     def gather():
         if world == 1:
             return
-        torch.cuda.synchronize()
-        if rank == 0:
-            reqs = [dist.irecv(frame_t[a:b], src=k) for k, (a, b) in enumerate(rows) if k != 0 and b > a]
-            for q in reqs:
-                q.wait()
-        elif row1 > row0:
-            dist.send(frame_t[row0:row1], dst=0)
+        # the render pass has completed on the backend's stream (poll(Wait)); NCCL runs on torch's stream
+        multigpu.gather_bands(frame_t, rank, world, dst=0)
         torch.cuda.synchronize()
 
     def barrier():
@@ -322,23 +318,6 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
-
-def _band_rows(height: int, rank: int, count: int, tile_h: int = 32):
-    tiles = (height + tile_h - 1) // tile_h
-    q, rem = divmod(tiles, count)
-    t0 = rank * q + min(rank, rem)
-    t1 = t0 + q + (1 if rank < rem else 0)
-    return min(t0 * tile_h, height), min(t1 * tile_h, height)
-
-
-def _tensor_from_ptr(torch, ptr: int, nbytes: int, device_index: int):
-    """Zero-copy torch view of the texture's device memory (for torch.distributed / NCCL)."""
-    class _Holder:
-        pass
-    h = _Holder()
-    h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
-    return torch.as_tensor(h, device=torch.device("cuda", device_index))
 
 
 if __name__ == "__main__":

@@ -1,0 +1,141 @@
+"""The C-ABI library loads, exports every symbol include/wgpu_b200.h declares, and its host-side logic
+(object lifetime, validation, error reporting, recording) behaves -- all without a GPU, using the
+compile-only device (translation + NVRTC, no execution).  No compute call is made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from wgpu_cpu_b200 import api, shaders
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "wgpu_b200.h")).read()
+    return sorted(set(re.findall(r"WGB_API\s+[\w\s\*]+?\b(wgb_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = api.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 50
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, f"missing exports: {missing}"
+    assert lib.wgb_version().decode().endswith("sm_100a")
+
+
+def test_no_device_means_an_error_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    adapter = api.instance().request_adapter()
+    assert adapter.get_info()["cuda_device_count"] == 0
+    with pytest.raises(api.WgpuError) as e:
+        adapter.request_device()
+    assert "no CPU fallback" in str(e.value)
+
+
+@pytest.fixture(scope="module")
+def offline():
+    dev, queue = api.instance().request_adapter().request_device(api.CUDA_DEVICE_COMPILE_ONLY)
+    return dev, queue
+
+
+def test_buffer_map_write_read_roundtrip(offline):
+    dev, _ = offline
+    b = dev.create_buffer(64, api.BUFFER_USAGE["VERTEX"], mapped_at_creation=True)
+    view = b.get_mapped_range()
+    assert view.shape == (64,) and not view.any()          # zero-initialised like Vec<u8> (buffer.rs:31-35)
+    view[:] = np.arange(64, dtype=np.uint8)
+    assert b.get_mapped_range(16, 8).tolist() == list(range(16, 24))
+    b.unmap()
+    with pytest.raises(api.WgpuError):
+        b.get_mapped_range()                               # not mapped any more
+    with pytest.raises(api.WgpuError):
+        dev.create_buffer(16, mapped_at_creation=True).get_mapped_range(8, 16)   # out of range
+
+
+def test_pipeline_creation_compiles_wgsl_with_nvrtc(offline):
+    dev, _ = offline
+    m = dev.create_shader_module(shaders.wgsl("hello_mesh"))
+    p = dev.create_render_pipeline(
+        vertex_module=m, fragment_module=m, front_face="cw", cull_mode="back", depth_stencil={"depth_compare": "less"},
+        vertex_buffers=[{"array_stride": 32, "attributes": [("float32x4", 0, 0), ("float32x4", 16, 1)]}], targets=["rgba8unorm-srgb"])
+    src = p.get_source()
+    assert "#define WGB_RESOLVE 1" in src and "#define WGB_CULL 2" in src and "#define WGB_FRONT_FACE_CW 1" in src
+    assert "#define WGB_ATTR1_OFFSET 16u" in src and '#include "wgb_raster.cuh"' in src
+
+
+def test_shader_errors_surface_at_pipeline_creation(offline):
+    dev, _ = offline
+    m = dev.create_shader_module("@vertex fn vs_main() -> @builtin(position) vec4f { return vec4f(q); }")
+    with pytest.raises(api.WgpuError) as e:
+        dev.create_render_pipeline(vertex_module=m, targets=[])
+    assert "unknown identifier 'q'" in str(e.value)
+    # a missing vertex attribute is a compile error of the generated translation unit
+    m = dev.create_shader_module(shaders.wgsl("hello_mesh"))
+    with pytest.raises(api.WgpuError) as e:
+        dev.create_render_pipeline(vertex_module=m, fragment_module=m, targets=["rgba8unorm"])
+    assert e.value.status == 5 and "WGB_ATTR" in str(e.value)
+
+
+def test_unsupported_state_is_reported(offline):
+    dev, _ = offline
+    m = dev.create_shader_module(shaders.wgsl("colored_triangle"))
+    with pytest.raises(api.WgpuError) as e:      # state.rs:438-478 panics for PolygonMode::Line
+        dev.create_render_pipeline(vertex_module=m, fragment_module=m, targets=["rgba8unorm"], polygon_mode=1)
+    assert e.value.status == 2
+    with pytest.raises(api.WgpuError) as e:      # order-dependent per fragment
+        dev.create_render_pipeline(vertex_module=m, fragment_module=m, targets=["rgba8unorm"],
+                                   depth_stencil={"depth_compare": "not-equal", "depth_write_enabled": True})
+    assert e.value.status == 2 and "NotEqual" in str(e.value)
+    with pytest.raises(api.WgpuError):           # binding.rs:161 todo!()
+        dev.create_sampler(address_mode_u="clamp-to-border")
+    with pytest.raises(api.WgpuError):
+        dev.create_texture(0, 4, "rgba8unorm")
+
+
+def test_recording_and_submit_on_compile_only_device(offline):
+    dev, queue = offline
+    m = dev.create_shader_module(shaders.wgsl("colored_triangle"))
+    p = dev.create_render_pipeline(vertex_module=m, fragment_module=m, targets=["rgba8unorm"])
+    tex = dev.create_texture(8, 8, "rgba8unorm")
+    enc = dev.create_command_encoder()
+    rp = enc.begin_render_pass([{"view": tex.create_view(), "load": ("clear", (0, 0, 0, 1))}])
+    rp.set_pipeline(p)
+    rp.set_viewport(0, 0, 8, 8)
+    rp.set_scissor_rect(0, 0, 8, 8)
+    rp.set_blend_constant((0, 0, 0, 0))
+    rp.set_stencil_reference(1)
+    rp.draw(range(0, 3))
+    rp.end()
+    rp.end()                                     # end() is idempotent (also called from Drop, mod.rs:325-329)
+    with pytest.raises(api.WgpuError):
+        rp.draw(range(0, 3))                     # recording after end
+    cb = enc.finish()
+    with pytest.raises(api.WgpuError):
+        enc.finish()
+    with pytest.raises(api.WgpuError) as e:      # there is no CPU path to execute it on
+        queue.submit([cb])
+    assert "compile-only" in str(e.value)
+    assert dev.poll(True) == 1                   # QueueEmpty (device.rs:266-268)
+
+
+def test_band_rows_match_python(offline):
+    from wgpu_cpu_b200.multigpu import band_rows
+    dev, _ = offline
+    for h in (1, 31, 32, 33, 2160, 4320, 1080):
+        for n in (1, 2, 3, 4, 8):
+            covered = []
+            for r in range(n):
+                dev.set_band(r, n)
+                assert dev.band_rows(h) == band_rows(h, r, n)
+                covered.append(dev.band_rows(h))
+            assert covered[0][0] == 0 and covered[-1][1] == h
+            assert all(covered[i][1] == covered[i + 1][0] for i in range(n - 1))
+    dev.set_band(0, 1)
+    with pytest.raises(api.WgpuError):
+        dev.set_band(2, 2)

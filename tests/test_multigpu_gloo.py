@@ -1,0 +1,54 @@
+"""The N > 1 path on CPU: world_size-2 gloo process group, each rank owning one band of the frame
+(wgpu_cpu_b200.multigpu), gathered to rank 0 with the same send/recv code bench.py runs over NCCL."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from wgpu_cpu_b200.multigpu import band_rows, gather_bands
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, height, width, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        frame = torch.zeros(height, width, 4, dtype=torch.uint8)
+        a, b = band_rows(height, rank, world)
+        # stand-in for the tile stage: every rank writes only its own band
+        frame[a:b] = torch.arange(a, b, dtype=torch.uint8).view(-1, 1, 1) + (rank + 1) * 40
+        gather_bands(frame, rank, world, dst=0)
+        dist.barrier()
+        if rank == 0:
+            np.save(out, frame.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_band_gather_world_size_2(tmp_path):
+    height, width, world = 200, 16, 2
+    out = str(tmp_path / "frame.npy")
+    mp.spawn(_worker, args=(world, _free_port(), height, width, out), nprocs=world, join=True)
+    frame = np.load(out)
+    for r in range(world):
+        a, b = band_rows(height, r, world)
+        expect = (np.arange(a, b, dtype=np.uint8) + (r + 1) * 40).reshape(-1, 1, 1)
+        assert (frame[a:b] == expect).all(), f"band of rank {r} is wrong"
+
+
+def test_bands_tile_the_frame():
+    for h in (2160, 1080, 4320, 50):
+        for n in (1, 2, 4, 8):
+            rows = [band_rows(h, r, n) for r in range(n)]
+            assert rows[0][0] == 0 and rows[-1][1] == h
+            assert all(rows[i][1] == rows[i + 1][0] for i in range(n - 1))
+            assert all(a % 32 == 0 or a == h for a, _ in rows)

@@ -1,0 +1,97 @@
+"""WGSL -> CUDA C++ emitter, host side (no GPU): golden emitter output for the built-in shaders,
+translation of every snippet case, and the errors raised for WGSL the backend does not run."""
+import pytest
+
+from tests.wgsl_cases import CASES, module_for
+from wgpu_cpu_b200 import api, shaders
+
+
+@pytest.mark.parametrize("name", shaders.NAMES)
+@pytest.mark.parametrize("stage,entry,tag", [(api.STAGE_VERTEX, "vs_main", "vs"), (api.STAGE_FRAGMENT, "fs_main", "fs")])
+def test_golden_emitter_output(name, stage, entry, tag):
+    assert api.translate_wgsl(shaders.wgsl(name), stage, entry) == shaders.emitted(name, tag)
+
+
+def test_arithmetic_contract_in_emitted_text():
+    """One IEEE operation per operator, never a*b+c: scalar float operators become wgb_* calls, and the
+    camera transform is the prelude's column-accumulating operator* (binary.rs:297-323)."""
+    vs = shaders.emitted("hello_mesh", "vs")
+    assert "wgb_load<mat4x4f>(wgb, 0, 0, 0u) * input.vertex_position" in vs
+    fs = shaders.emitted("procedural", "fs")
+    assert "wgb_add(wgb_sub(wgb_mul(zx, zx), wgb_mul(zy, zy)), cx)" in fs
+    assert "wgb_add(wgb_mul(wgb_mul(2.0f, zx), zy), cy)" in fs
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_snippets_translate(case):
+    src = module_for(case)
+    assert "wgb_vs_entry" in api.translate_wgsl(src, api.STAGE_VERTEX, "vs_main")
+    fs = api.translate_wgsl(src, api.STAGE_FRAGMENT, "fs_main")
+    assert "#define WGB_FS_WRITES_FRAG_DEPTH 1" in fs and "#define WGB_FS_COLOR_MASK 1" in fs
+
+
+def _fs(body, decls="", ret="@location(0) vec4f"):
+    return f"{decls}\n@fragment fn fs_main(@builtin(position) p: vec4f) -> {ret} {{ {body} }}"
+
+
+def test_inter_stage_layout_and_interpolation():
+    src = """
+struct VOut { @builtin(position) p: vec4f, @location(2) @interpolate(flat) id: u32, @location(0) uv: vec2f,
+              @location(1) @interpolate(linear) n: vec3f, }
+@vertex fn vs_main(@location(0) a: vec4f) -> VOut { return VOut(a, 1u, vec2f(0.0), vec3f(1.0)); }
+@fragment fn fs_main(v: VOut) -> @location(0) vec4f { return vec4f(v.uv, f32(v.id), v.n.x); }
+"""
+    vs = api.translate_wgsl(src, api.STAGE_VERTEX, "vs_main")
+    # locations packed in declaration order with naga's alignments (bindings.rs:307-346): u32 @0, vec2 @2 (8-byte), vec3 @4 (16-byte)
+    assert "#define WGB_VS_LOC2_SLOT 0" in vs and "#define WGB_VS_LOC0_SLOT 2" in vs and "#define WGB_VS_LOC1_SLOT 4" in vs
+    assert "#define WGB_VS_VARYING_SLOTS 7" in vs
+    fs = api.translate_wgsl(src, api.STAGE_FRAGMENT, "fs_main")
+    assert "WGB_VS_LOC2_SLOT + 1) ? 0" in fs      # flat
+    assert "WGB_VS_LOC0_SLOT + 2) ? 2" in fs      # default = perspective
+    assert "WGB_VS_LOC1_SLOT + 3) ? 1" in fs      # linear
+
+
+def test_frag_depth_after_location_is_ignored():
+    """fragment.rs:457-488: the late depth test runs at the first @location output, so a frag_depth
+    declared after it never reaches the test."""
+    src = _fs("return O(vec4f(1.0), 0.25);", "struct O { @location(0) c: vec4f, @builtin(frag_depth) d: f32, }", "O")
+    assert "#define WGB_FS_WRITES_FRAG_DEPTH 0" in api.translate_wgsl(src, api.STAGE_FRAGMENT, "fs_main")
+
+
+def test_discard_propagates_through_calls():
+    src = _fs("maybe(p.x); return vec4f(1.0);", "fn maybe(x: f32) { if (x > 3.0) { discard; } }")
+    fs = api.translate_wgsl(src, api.STAGE_FRAGMENT, "fs_main")
+    assert "#define WGB_FS_MAY_DISCARD 1" in fs and "if (wgb_inv.killed) return vec4f();" in fs
+
+
+def test_uniform_layout_offsets():
+    src = """
+struct Light { dir: vec3f, power: f32, color: vec3f, }
+struct U { m: mat4x4f, lights: array<Light, 2>, k: vec2f, }
+@group(0) @binding(1) var<uniform> u: U;
+@fragment fn fs_main(@builtin(position) p: vec4f) -> @location(0) vec4f {
+    let i = u32(p.x);
+    return vec4f(u.lights[1].color, u.lights[i].power + u.k.y);
+}"""
+    fs = api.translate_wgsl(src, api.STAGE_FRAGMENT, "fs_main")
+    assert "wgb_load<vec3f>(wgb, 0, 1, 112u)" in fs          # 64 + 32*1 + 16
+    assert "wgb_load<f32>(wgb, 0, 1, 76u + min((u32)(i), 1u) * 32u)" in fs
+    assert "wgb_load<f32>(wgb, 0, 1, 132u)" in fs            # k at 128, .y
+
+
+@pytest.mark.parametrize("src,fragment", [
+    (_fs("return vec4f(1.0);", "override k: f32 = 1.0;"), "override"),
+    (_fs("return vec4f(f16(1.0));"), "f16"),
+    ("@compute @workgroup_size(1) fn fs_main() {}", "not a fragment entry point"),
+    (_fs("return textureSample(t, s, p.xy, vec2i(1, 1));", "@group(0) @binding(0) var t: texture_2d<f32>;\n@group(0) @binding(1) var s: sampler;"), "offset"),
+    (_fs("b = 1.0; return vec4f(1.0);", "@group(0) @binding(0) var<storage, read_write> b: f32;"), "read-only"),
+    (_fs("return vec4f(q);"), "unknown identifier"),
+    (_fs("let a: u32 = 1.5; return vec4f(1.0);"), "cannot convert"),
+    (_fs("return vec4f(1.0) * mat4x4f();"), "vector * matrix"),
+    (_fs("return vec4f(1.0);", "var<workgroup> w: f32;"), "workgroup"),
+    (_fs("return vec4f(1.0);", "", "@location(0) vec3f"), "vec4<f32>"),
+])
+def test_unsupported_wgsl_is_rejected_with_a_message(src, fragment):
+    with pytest.raises(api.WgpuError) as e:
+        api.translate_wgsl(src, api.STAGE_FRAGMENT, "fs_main")
+    assert fragment in str(e.value)

@@ -1,0 +1,131 @@
+"""WGSL snippets with known results, restating the reference's shader-compiler tests
+(naga-cranelift/src/tests.rs:200-1401: the snippet, the expression evaluated, the expected value)
+plus cases for what the reference leaves todo!() (swizzles, splats, math builtins).
+
+Each case: (name, module-scope declarations, body statements, result expression of type f32, expected)."""
+
+CASES = [
+    # tests.rs:200-210 init_variable / store_variable
+    ("init_variable", "", "var a: u32 = 123;", "f32(a)", 123.0),
+    ("store_variable", "", "var a: u32; a = 123;", "f32(a)", 123.0),
+    # tests.rs:212-235 casts
+    ("cast_bool_u32", "", "var i: bool = true; var o: u32 = u32(i);", "f32(o)", 1.0),
+    ("cast_bool_i32", "", "var i: bool = false; var o: i32 = i32(i);", "f32(o)", 0.0),
+    ("cast_bool_f32", "", "var i: bool = true; var o: f32 = f32(i);", "o", 1.0),
+    ("cast_u32_f32", "", "var i: u32 = 5; var o: f32 = f32(i);", "o", 5.0),
+    ("cast_i32_f32", "", "var i: i32 = -3; var o: f32 = f32(i);", "o", -3.0),
+    ("cast_f32_i32_trunc", "", "var i: f32 = -3.75; var o: i32 = i32(i);", "f32(o)", -3.0),
+    # tests.rs:237-275 binops_scalars
+    ("i32_add", "", "var l: i32 = 1; var r: i32 = 1;", "f32(l + r)", 2.0),
+    ("i32_sub", "", "var l: i32 = 1; var r: i32 = 2;", "f32(l - r)", -1.0),
+    ("i32_mul", "", "var l: i32 = 2; var r: i32 = -3;", "f32(l * r)", -6.0),
+    ("i32_div", "", "var l: i32 = 3; var r: i32 = 2;", "f32(l / r)", 1.0),
+    ("i32_rem", "", "var l: i32 = 3; var r: i32 = 2;", "f32(l % r)", 1.0),
+    ("i32_div_neg", "", "var l: i32 = -7; var r: i32 = 2;", "f32(l / r)", -3.0),
+    ("f32_add", "", "var l: f32 = 1; var r: f32 = 1;", "l + r", 2.0),
+    ("f32_mul", "", "var l: f32 = 2; var r: f32 = -3;", "l * r", -6.0),
+    ("f32_div", "", "var l: f32 = 3; var r: f32 = 2;", "l / r", 1.5),
+    ("f32_rem", "", "var l: f32 = 3; var r: f32 = 2;", "l % r", 1.0),
+    ("f32_rem_neg", "", "var l: f32 = -5.5; var r: f32 = 2;", "l % r", -1.5),
+    # tests.rs:277-304 comparisons
+    ("cmp_eq", "", "var l: i32 = 2; var r: i32 = 2;", "f32(l == r)", 1.0),
+    ("cmp_ne", "", "var l: i32 = 1; var r: i32 = 2;", "f32(l != r)", 1.0),
+    ("cmp_lt_neg", "", "var l: i32 = -1; var r: i32 = 1;", "f32(l < r)", 1.0),
+    ("cmp_ge", "", "var l: i32 = 3; var r: i32 = 2;", "f32(l >= r)", 1.0),
+    # tests.rs:306-347 unops
+    ("neg_i32", "", "var i: i32 = 123;", "f32(-i)", -123.0),
+    ("neg_f32", "", "var i: f32 = -123.0;", "-i", 123.0),
+    ("not_bool", "", "var i: bool = true;", "f32(!i)", 0.0),
+    ("bitnot_u32", "", "var i: u32 = 123;", "f32((~i) & 0xffffu)", float((~123) & 0xffff)),
+    # tests.rs:349-375 if / return
+    ("if_taken", "", "var a: u32 = 1; if (a == 1) { a = 7; } else { a = 9; }", "f32(a)", 7.0),
+    ("if_not_taken", "", "var a: u32 = 2; if (a == 1) { a = 7; } else { a = 9; }", "f32(a)", 9.0),
+    # tests.rs:377-398 calls
+    ("call", "fn add(a: i32, b: i32) -> i32 { return a + b; }", "let x = add(3, 4);", "f32(x)", 7.0),
+    ("call_nested", "fn sq(a: f32) -> f32 { return a * a; }\nfn quad(a: f32) -> f32 { return sq(sq(a)); }", "let x = quad(3.0);", "x", 81.0),
+    # tests.rs:438-478 constants
+    ("const_global", "const K: u32 = 42u;", "", "f32(K)", 42.0),
+    ("const_expr", "const K = 6 * 7;", "", "f32(K)", 42.0),
+    ("const_vec", "const V = vec3f(1.0, 2.0, 3.0);", "", "V.y + V.z", 5.0),
+    # tests.rs:480-502 for loop: 6! = 720
+    ("for_factorial", "", "var acc: u32 = 1; for (var i: u32 = 1; i <= 6; i++) { acc *= i; }", "f32(acc)", 720.0),
+    ("while_loop", "", "var n: i32 = 0; var i: i32 = 0; while (i < 10) { i += 3; n += 1; }", "f32(n)", 4.0),
+    ("loop_break_if", "", "var i: i32 = 0; loop { i += 1; continuing { break if i >= 5; } }", "f32(i)", 5.0),
+    ("loop_continue", "", "var i: i32 = 0; var s: i32 = 0; loop { if (i >= 6) { break; } i += 1; if (i % 2 == 0) { continue; } s += i; }", "f32(s)", 9.0),
+    # tests.rs:504-648 switch
+    ("switch_case", "", "var a: i32 = 2; var r: i32 = 0; switch (a) { case 1: { r = 10; } case 2: { r = 20; } default: { r = 30; } }", "f32(r)", 20.0),
+    ("switch_default", "", "var a: i32 = 5; var r: i32 = 0; switch (a) { case 1: { r = 10; } case 2, 3: { r = 20; } default: { r = 30; } }", "f32(r)", 30.0),
+    ("switch_multi", "", "var a: u32 = 3u; var r: i32 = 0; switch (a) { case 1u: { r = 10; } case 2u, 3u: { r = 20; } default: { r = 30; } }", "f32(r)", 20.0),
+    ("switch_in_loop", "", "var r: i32 = 0; for (var i: i32 = 0; i < 4; i++) { switch (i) { case 1: { continue; } case 2: { break; } default: { r += 10; } } r += 1; }", "f32(r)", 23.0),
+    # tests.rs:650-669 globals
+    ("private_global", "var<private> g: u32 = 5u;\nfn bump() { g = g + 1u; }", "bump(); bump();", "f32(g)", 7.0),
+    # tests.rs:671-758, 1155-1196 access
+    ("vec_access", "", "var v = vec4f(1.0, 2.0, 3.0, 4.0); v.z = 9.0;", "v.x + v.z + v[3]", 14.0),
+    ("struct_access", "struct S { a: f32, b: vec2f, }", "var s = S(1.0, vec2f(2.0, 3.0)); s.b.y = 5.0;", "s.a + s.b.x + s.b.y", 8.0),
+    ("mat_column", "", "var m = mat4x4f(vec4f(1,1,1,1), vec4f(0,2,0,2), vec4f(3,2,1,0), vec4f(1,2,3,4));", "m[2].x + m[3][3]", 7.0),
+    ("dynamic_vec_index", "", "var v = vec4f(1.0, 2.0, 3.0, 4.0); var i: u32 = 2u;", "v[i]", 3.0),
+    # tests.rs:927-1110 arrays
+    ("array_const_index", "", "var a = array<f32, 4>(1.0, 2.0, 3.0, 4.0);", "a[1] + a[3]", 6.0),
+    ("array_dynamic", "", "var a = array<i32, 5>(5, 4, 3, 2, 1); var s: i32 = 0; for (var i = 0; i < 5; i++) { s += a[i] * i; }", "f32(s)", 20.0),
+    ("array_store", "", "var a: array<u32, 3>; a[1] = 7u; a[2] = a[1] + 1u;", "f32(a[0] + a[1] + a[2])", 15.0),
+    # tests.rs:1112-1153 select
+    ("select_true", "", "var c: bool = true;", "select(1.0, 2.0, c)", 2.0),
+    ("select_false", "", "var c: bool = false;", "select(1.0, 2.0, c)", 1.0),
+    # tests.rs:1287-1315 matrix_vector_product = [14, 19, 16, 21]
+    ("mat_vec_x", "", "var l = mat4x4f(vec4f(1,1,1,1), vec4f(0,2,0,2), vec4f(3,2,1,0), vec4f(1,2,3,4)); var r = vec4f(1,2,3,4); let o = l * r;", "o.x", 14.0),
+    ("mat_vec_y", "", "var l = mat4x4f(vec4f(1,1,1,1), vec4f(0,2,0,2), vec4f(3,2,1,0), vec4f(1,2,3,4)); var r = vec4f(1,2,3,4); let o = l * r;", "o.y", 19.0),
+    ("mat_vec_z", "", "var l = mat4x4f(vec4f(1,1,1,1), vec4f(0,2,0,2), vec4f(3,2,1,0), vec4f(1,2,3,4)); var r = vec4f(1,2,3,4); let o = l * r;", "o.z", 16.0),
+    ("mat_vec_w", "", "var l = mat4x4f(vec4f(1,1,1,1), vec4f(0,2,0,2), vec4f(3,2,1,0), vec4f(1,2,3,4)); var r = vec4f(1,2,3,4); let o = l * r;", "o.w", 21.0),
+    # tests.rs:1317-1345 matrix_scalar_product, :1347-1370 vector_scalar_product
+    ("mat_scalar", "", "var m = mat4x4f(vec4f(1,1,1,1), vec4f(0,2,0,2), vec4f(3,2,1,0), vec4f(1,2,3,4)); let o = m * 2.0;", "o[3].w + o[1].y", 12.0),
+    ("vec_scalar", "", "var v = vec4f(1,2,3,4); let o = v * 3.0;", "o.x + o.w", 15.0),
+    ("scalar_vec", "", "var v = vec3f(1,2,3); let o = 2.0 * v;", "o.y + o.z", 10.0),
+    ("vec_vec", "", "var a = vec3f(1,2,3); var b = vec3f(4,5,6); let o = a * b + a;", "o.x + o.y + o.z", 38.0),
+    # tests.rs:1372-1401 private matrix init
+    ("private_matrix", "var<private> pm: mat4x4f = mat4x4f(vec4f(1,0,0,0), vec4f(0,2,0,0), vec4f(0,0,3,0), vec4f(0,0,0,4));", "", "pm[1].y + pm[3].w", 6.0),
+    # ---- beyond the reference's JIT (todo!() there): swizzle, splat, math, vector compare, mat*mat ----
+    ("swizzle", "", "var v = vec4f(1.0, 2.0, 3.0, 4.0); let s = v.zyx; let t = v.xy;", "s.x * 100.0 + s.z * 10.0 + t.y", 312.0),
+    ("swizzle_rgba", "", "var v = vec4f(1.0, 2.0, 3.0, 4.0); let s = v.bgr;", "s.x + s.z * 10.0", 13.0),
+    ("splat", "", "let v = vec3f(2.5); let u = vec2<u32>(3u);", "v.x + v.z + f32(u.y)", 8.0),
+    ("math_minmax", "", "var a: f32 = 3.0; var b: f32 = -2.0;", "min(a, b) + max(a, b) * 10.0 + abs(b)", 30.0),
+    ("math_clamp_mix", "", "var a: f32 = 0.25;", "mix(10.0, 20.0, a) + clamp(5.0, 0.0, 1.0)", 13.5),
+    ("math_dot_cross", "", "var a = vec3f(1,0,0); var b = vec3f(0,1,0); let c = cross(a, b);", "dot(c, vec3f(1,2,3)) + length(vec2f(3,4))", 8.0),
+    ("math_floor_fract", "", "var a: f32 = 2.75;", "floor(a) + fract(a) * 4.0 + sqrt(16.0)", 9.0),
+    ("vec_compare", "", "var a = vec3f(1,5,3); var b = vec3f(2,4,3); let c = a < b; let d = select(a, b, c);", "f32(any(c)) + f32(all(c)) * 10.0 + d.x + d.y + d.z", 11.0),
+    ("mat_mat", "", "var a = mat2x2f(vec2f(1,2), vec2f(3,4)); var b = mat2x2f(vec2f(0,1), vec2f(1,0)); let c = a * b;", "c[0].x * 1000.0 + c[0].y * 100.0 + c[1].x * 10.0 + c[1].y", 3412.0),
+    ("bit_ops", "", "var a: u32 = 0xF0u; var b: u32 = 0x3Cu;", "f32((a & b) | ((a ^ b) << 8u) | (a >> 4u))", float((0xF0 & 0x3C) | ((0xF0 ^ 0x3C) << 8) | (0xF0 >> 4))),
+    ("abstract_mix", "", "var v: u32 = 7; let w = v % 3 + 2 * 3;", "f32(w)", 7.0),
+    ("int_div_zero_defined", "", "var a: i32 = 9; var z: i32 = 0;", "f32(a / z) + f32(a % z)", 9.0),
+    ("bitcast", "", "var a: f32 = 1.0;", "f32(bitcast<u32>(a) >> 23u)", 127.0),
+    ("let_shadowing", "", "let a = 1.0; var b = a; { let a = 5.0; b = b + a; }", "a + b", 7.0),
+    ("compound_assign", "", "var a: f32 = 8.0; a /= 2.0; a -= 1.0; a *= 3.0; var i: i32 = 5; i %= 3; i <<= 2u;", "a + f32(i)", 17.0),
+]
+
+
+def module_for(case) -> str:
+    name, decls, body, expr, expected = case
+    return f"""
+{decls}
+
+struct FragmentOutput {{
+    @builtin(frag_depth) depth: f32,
+    @location(0) color: vec4f,
+}}
+
+@vertex
+fn vs_main(@builtin(vertex_index) vertex_index: u32) -> @builtin(position) vec4f {{
+    let x = f32(i32(vertex_index & 1u) * 4 - 1);
+    let y = f32(i32(vertex_index >> 1u) * 4 - 1);
+    return vec4f(x, y, 0.5, 1.0);
+}}
+
+fn compute() -> f32 {{
+    {body}
+    return {expr};
+}}
+
+@fragment
+fn fs_main() -> FragmentOutput {{
+    return FragmentOutput(compute(), vec4f(1.0, 0.0, 0.0, 1.0));
+}}
+"""

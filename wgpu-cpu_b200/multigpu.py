@@ -1,0 +1,51 @@
+"""Sort-first multi-GPU partition: the framebuffer is split into `count` contiguous bands of
+whole tile rows, one per rank; every rank holds the full scene, runs the geometry stage for all primitives
+and the tile stage for its band only (per-pixel primitive order is preserved inside a band, so the result is
+bit-identical to one GPU), and the colour bands are gathered to the presenting rank over NCCL/NVLink.
+
+One process per GPU; torch.distributed supplies the process group (NCCL on GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+TILE_H = 32  # WGB_TILE_H
+
+
+def band_rows(height: int, rank: int, count: int, tile_h: int = TILE_H):
+    """First and one-past-last pixel row of band `rank` (must equal wgb_device_get_band_rows)."""
+    tiles = (height + tile_h - 1) // tile_h
+    q, rem = divmod(tiles, max(count, 1))
+    t0 = rank * q + min(rank, rem)
+    t1 = t0 + q + (1 if rank < rem else 0)
+    return min(t0 * tile_h, height), min(t1 * tile_h, height)
+
+
+def gather_bands(frame, rank: int, world: int, dst: int = 0):
+    """Gather every rank's band of `frame` (a [H, W, C] tensor that aliases the colour target) into rank
+    `dst`'s copy.  Point-to-point send/recv of the band rows only: 4*W*H*(N-1)/N bytes per frame in total."""
+    import torch.distributed as dist
+    if world == 1:
+        return
+    height = frame.shape[0]
+    if rank == dst:
+        reqs = []
+        for k in range(world):
+            a, b = band_rows(height, k, world)
+            if k != dst and b > a:
+                reqs.append(dist.irecv(frame[a:b], src=k))
+        for r in reqs:
+            r.wait()
+    else:
+        a, b = band_rows(height, rank, world)
+        if b > a:
+            dist.send(frame[a:b].contiguous(), dst=dst)
+
+
+def tensor_from_device_pointer(ptr: int, nbytes: int, device_index: int):
+    """Zero-copy torch uint8 view of device memory owned by the backend (a texture's texel storage)."""
+    import torch
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+    return torch.as_tensor(h, device=torch.device("cuda", device_index))
