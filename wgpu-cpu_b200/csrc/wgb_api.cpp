@@ -290,7 +290,7 @@ struct Device : Object {
     wgb_status deferred_status = WGB_OK;   // error raised while executing a submission
     std::string deferred_error;
     // work buffers, grown on demand and reused across passes
-    DevBuf counters, prim_box, slow_list, clip_records, big_list, tile_count, tile_offset, tile_cursor, bins, coverage, strip_map, strip_count;
+    DevBuf counters, prim_box, setup_cache, slow_list, clip_records, big_list, tile_count, tile_offset, tile_cursor, bins, coverage, strip_map, strip_count;
     WgbCounters* host_counters = nullptr;   // pinned
     uint32_t clip_capacity = 0, big_capacity = 0;
     bool coverage_capture = false;
@@ -307,7 +307,7 @@ struct Device : Object {
         if (stream) cudaStreamSynchronize(stream);
         for (auto& f : inflight) cudaEventDestroy(f.done);
         for (auto& kv : kernel_cache) if (kv.second->module && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->module);
-        DevBuf* bufs[] = {&counters, &prim_box, &slow_list, &clip_records, &big_list, &tile_count, &tile_offset, &tile_cursor, &bins, &coverage, &strip_map, &strip_count};
+        DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &slow_list, &clip_records, &big_list, &tile_count, &tile_offset, &tile_cursor, &bins, &coverage, &strip_map, &strip_count};
         for (DevBuf* b : bufs) b->release();
         if (host_counters) cudaFreeHost(host_counters);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -706,6 +706,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             dev->clip_capacity = clip_cap; dev->big_capacity = big_cap;
             dev->counters.ensure(sizeof(WgbCounters));
             dev->prim_box.ensure((size_t)np * 4);
+            dev->setup_cache.ensure((size_t)np * 48);
             dev->slow_list.ensure((size_t)np * 4);
             dev->clip_records.ensure((size_t)clip_cap * sizeof(WgbClipRecord));
             dev->big_list.ensure((size_t)big_cap * sizeof(WgbBigEntry));
@@ -714,6 +715,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             dev->tile_cursor.ensure((size_t)(band_tiles + 1) * 4);
             dev->bins.ensure(((size_t)np + clip_cap) * WGB_SMALL_MAX_TILES * 4);
             d.counters = dev->counters.addr(); d.prim_box = dev->prim_box.addr(); d.slow_list = dev->slow_list.addr();
+            d.setup_cache = dev->setup_cache.addr();
             d.clip_records = dev->clip_records.addr(); d.clip_capacity = clip_cap;
             d.big_list = dev->big_list.addr(); d.big_capacity = big_cap;
             d.tile_count = dev->tile_count.addr(); d.tile_offset = dev->tile_offset.addr(); d.tile_cursor = dev->tile_cursor.addr();

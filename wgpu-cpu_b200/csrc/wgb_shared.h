@@ -133,6 +133,7 @@ struct WgbDraw {
     // work buffers
     wgb_u64 counters;                    // WgbCounters*
     wgb_u64 prim_box;                    // u32 per primitive: kind | packed tile box / clip record base
+    wgb_u64 setup_cache;                 // float4 x 3 per primitive: to_raster'd vertices (vp.x, vp.y, ndc.z, 1/w) of unclipped primitives
     wgb_u64 slow_list;                   // u32 per slow primitive
     wgb_u64 clip_records;                // WgbClipRecord*
     wgb_u32 clip_capacity;
