@@ -149,6 +149,9 @@ def main():
     ap.add_argument("--config", default="c3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--present", default="peer", choices=["peer", "nccl"],
+                    help="N>1: how colour bands reach rank 0: tile kernels store into rank 0's target over NVLink peer memory "
+                         "(fused, default) or a separate NCCL gather")
     args = ap.parse_args()
 
     from wgpu_cpu_b200 import scenes as S
@@ -176,20 +179,30 @@ def main():
     scene = make(S)
     W, H = scene.width, scene.height
     dev, queue = api.instance().request_adapter().request_device(local_rank, band_rank=rank, band_count=world)
-    r = SceneRenderer(dev, queue, scene, use_emitted=os.environ.get("WGB_USE_EMITTED", "0") == "1")
+    from wgpu_cpu_b200 import multigpu
+    use_emitted = os.environ.get("WGB_USE_EMITTED", "0") == "1"
+    target = None
+    if world > 1 and args.present == "peer":
+        own = dev.create_texture(W, H, scene.color_format) if rank == 0 else None
+        target = multigpu.share_presenter_target(dev, own, rank, world, W, H, scene.color_format, dst=0)
+    r = SceneRenderer(dev, queue, scene, use_emitted=use_emitted, target=target)
     warm = max(args.warmup, 3)
 
-    # presenter gather: every rank's colour band -> rank 0
-    from wgpu_cpu_b200 import multigpu
+    # presenter: every rank's colour band -> rank 0
     row0, row1 = dev.band_rows(H)
     assert (row0, row1) == multigpu.band_rows(H, rank, world)
     frame_t = None
-    if world > 1:
+    if world > 1 and args.present == "nccl":
         ptr, nbytes = r.target.device_pointer()
         frame_t = multigpu.tensor_from_device_pointer(ptr, nbytes, local_rank).view(H, W, 4)
 
     def gather():
         if world == 1:
+            return
+        if args.present == "peer":
+            # the tile kernels already stored every band into rank 0's target over NVLink; the render pass has
+            # completed on each rank's stream (poll(Wait)), so a barrier makes the frame visible to the presenter
+            dist.barrier()
             return
         # the render pass has completed on the backend's stream (poll(Wait)); NCCL runs on torch's stream
         multigpu.gather_bands(frame_t, rank, world, dst=0)
@@ -304,7 +317,9 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "width": W, "height": H, "triangles": prims,
                    "l2": "inputs (280 MB vertex+index) and attachments (66 MB) exceed the 126 MB L2 at C3; no explicit flush",
-                   "parallelism": f"sort-first x{world}" if world > 1 else "single GPU",
+                   "parallelism": (f"sort-first x{world}, bands presented to rank 0 by " +
+                                   ("NVLink peer stores from the tile kernel" if args.present == "peer" else "NCCL send/recv"))
+                   if world > 1 else "single GPU",
                    "shaders": "WGSL translated to CUDA C++ and compiled with NVRTC for sm_100a"},
         "fragments_mpix_s": last["fragments"] * args.steps / dt / 1e6,
         "shaded_mpix_s": last["shaded"] * args.steps / dt / 1e6,

@@ -165,6 +165,14 @@ WGB_API wgb_status wgb_queue_write_texture(wgb_queue queue, wgb_texture texture,
 /* Read-back of a texture's texels, row-major and tightly packed: what wgpu_cpu::dump_texture /
  * image::rgba_texture_image observe (lib.rs:111-173).  Waits for earlier submissions. */
 WGB_API wgb_status wgb_texture_read(wgb_texture texture, void* dst, uint64_t dst_size);
+/* Peer-memory presenter (one process per GPU on an NVLink box): the presenting rank exports its colour target,
+ * every other rank imports it and uses the imported texture as ITS colour attachment, so that its tile kernel
+ * stores the finished tiles of its band straight into the presenter's memory over NVLink -- compute and the
+ * band exchange are one kernel, there is no gather step.  `handle` is a cudaIpcMemHandle_t (64 bytes). */
+#define WGB_IPC_HANDLE_SIZE 64
+WGB_API wgb_status wgb_texture_export_ipc(wgb_texture texture, uint8_t handle[WGB_IPC_HANDLE_SIZE]);
+WGB_API wgb_status wgb_device_import_texture_ipc(wgb_device device, const uint8_t handle[WGB_IPC_HANDLE_SIZE],
+                                                 const wgb_texture_descriptor* desc, wgb_texture* out);
 /* device address of the texel storage (linear, row-major), for collectives over NVLink */
 WGB_API wgb_status wgb_texture_device_pointer(wgb_texture texture, uint64_t* out_ptr, uint64_t* out_size);
 /* DeviceInterface::create_sampler (device.rs:177-180), Sampler (sampler.rs:4-27) */

@@ -254,6 +254,12 @@ class Texture(_Handle):
             return out.view(np.float32).reshape(self.layers, self.height, self.width)[0]
         return out[0]
 
+    def export_ipc(self) -> bytes:
+        """cudaIpcMemHandle_t of the texel storage (peer-memory presenter, see wgpu_b200.h)."""
+        h = (C.c_uint8 * 64)()
+        _check(_lib.wgb_texture_export_ipc(self._h, h))
+        return bytes(h)
+
     def device_pointer(self):
         p, n = C.c_uint64(), C.c_uint64()
         _check(_lib.wgb_texture_device_pointer(self._h, C.byref(p), C.byref(n)))
@@ -445,6 +451,16 @@ class Device(_Handle):
         """wgpu::util::DeviceExt::create_texture_with_data -> Queue::write_texture (hello_texture.rs:184-201)."""
         t = self.create_texture(width, height, format)
         queue.write_texture(t, data)
+        return t
+
+    def import_texture_ipc(self, handle: bytes, width: int, height: int, format: str, layers: int = 1) -> Texture:
+        """Map a texture another process exported with Texture.export_ipc (its device must be an NVLink peer)."""
+        desc = _TextureDescriptor(width, height, layers, 1, 1, TEXTURE_FORMAT[format], 0)
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 64)(*handle)
+        _check(_lib.wgb_device_import_texture_ipc(self._h, buf, C.byref(desc), C.byref(h)))
+        t = Texture(h)
+        t.width, t.height, t.layers, t.format = width, height, layers, format
         return t
 
     def create_sampler(self, address_mode_u="clamp-to-edge", address_mode_v="clamp-to-edge", address_mode_w="clamp-to-edge",

@@ -336,13 +336,14 @@ struct Texture : Object {
     uint32_t bpp = 0;
     uint64_t size = 0;
     void* dptr = nullptr;
+    bool imported = false;          // dptr maps another process's allocation (cudaIpcOpenMemHandle)
     cudaTextureObject_t texobj = 0;
     std::mutex mu;
     ~Texture() override {
         if (device->compile_only) return;
         cudaSetDevice(device->ordinal);
         if (texobj) cudaDestroyTextureObject(texobj);
-        if (dptr) cudaFree(dptr);
+        if (dptr) { if (imported) cudaIpcCloseMemHandle(dptr); else cudaFree(dptr); }
     }
     // bindless texture object over the linear texel storage (element fetch, no filtering)
     cudaTextureObject_t texture_object() {
@@ -1177,6 +1178,43 @@ wgb_status wgb_texture_read(wgb_texture texture, void* dst, uint64_t dst_size) {
         dev->make_current();
         CUDA_CHECK(cudaMemcpyAsync(dst, t->dptr, t->size, cudaMemcpyDeviceToHost, dev->stream));
         CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+    });
+}
+wgb_status wgb_texture_export_ipc(wgb_texture texture, uint8_t handle[WGB_IPC_HANDLE_SIZE]) {
+    return guarded([&] {
+        Texture* t = from_handle<Texture>(texture, "texture");
+        REQUIRE(handle, "handle is null");
+        static_assert(sizeof(cudaIpcMemHandle_t) == WGB_IPC_HANDLE_SIZE, "IPC handle size");
+        if (t->device->compile_only) fail(WGB_ERROR_DEVICE, "a compile-only device has no texture storage");
+        REQUIRE(!t->imported, "an imported texture cannot be exported again");
+        t->device->make_current();
+        cudaIpcMemHandle_t h;
+        CUDA_CHECK(cudaIpcGetMemHandle(&h, t->dptr));
+        memcpy(handle, &h, sizeof(h));
+    });
+}
+wgb_status wgb_device_import_texture_ipc(wgb_device device, const uint8_t handle[WGB_IPC_HANDLE_SIZE],
+                                         const wgb_texture_descriptor* desc, wgb_texture* out) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        REQUIRE(handle && desc && out, "null argument");
+        if (dev->compile_only) fail(WGB_ERROR_DEVICE, "a compile-only device cannot map peer memory");
+        const uint32_t bpp = bytes_per_texel(desc->format);
+        if (bpp == 0) fail(WGB_ERROR_UNSUPPORTED, "Unsupported texture format: %u", desc->format);
+        Ref<Texture> t;
+        t.p = new Texture();
+        t->device = Ref<Device>(dev);
+        t->desc = *desc;
+        if (t->desc.depth_or_array_layers == 0) t->desc.depth_or_array_layers = 1;
+        t->bpp = bpp;
+        t->size = (uint64_t)bpp * desc->width * desc->height * t->desc.depth_or_array_layers;
+        dev->make_current();
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, sizeof(h));
+        CUDA_CHECK(cudaIpcOpenMemHandle(&t->dptr, h, cudaIpcMemLazyEnablePeerAccess));
+        t->imported = true;
+        t->rc.fetch_add(1);
+        *out = to_handle<wgb_texture>(t.get());
     });
 }
 wgb_status wgb_texture_device_pointer(wgb_texture texture, uint64_t* out_ptr, uint64_t* out_size) {

@@ -39,6 +39,18 @@ def gather_bands(frame, rank: int, world: int, dst: int = 0):
             dist.send(frame[a:b].contiguous(), dst=dst)
 
 
+def share_presenter_target(device, texture, rank: int, world: int, width: int, height: int, fmt: str, dst: int = 0):
+    """Peer-memory presenter: rank `dst` exports its colour target over CUDA IPC, every other rank maps it and
+    returns the mapped texture to use as its own colour attachment.  After this the tile kernels of all ranks
+    store their bands directly into rank `dst`'s memory over NVLink; a barrier replaces the gather."""
+    import torch.distributed as dist
+    handles = [texture.export_ipc() if rank == dst else None]
+    dist.broadcast_object_list(handles, src=dst)
+    if rank == dst:
+        return texture
+    return device.import_texture_ipc(handles[0], width, height, fmt)
+
+
 def tensor_from_device_pointer(ptr: int, nbytes: int, device_index: int):
     """Zero-copy torch uint8 view of device memory owned by the backend (a texture's texel storage)."""
     import torch

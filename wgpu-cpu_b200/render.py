@@ -24,7 +24,10 @@ class Frame:
 class SceneRenderer:
     """Holds the device-resident resources of one scene so that frames can be re-submitted."""
 
-    def __init__(self, device: api.Device, queue: api.Queue, scene: Scene, use_emitted: bool = False):
+    def __init__(self, device: api.Device, queue: api.Queue, scene: Scene, use_emitted: bool = False,
+                 target: Optional[api.Texture] = None):
+        """`target`: render into this texture instead of creating one (e.g. the presenter's colour target
+        imported over CUDA IPC, so that the tile kernel stores its band straight into peer memory)."""
         self.device, self.queue, self.scene = device, queue, scene
         s = scene
         if use_emitted:
@@ -66,7 +69,7 @@ class SceneRenderer:
                              "attributes": [(a.format, a.offset, a.location) for a in l.attributes]} for l in s.vertex_layouts],
             topology=s.topology, strip_index_format=s.strip_index_format, front_face=s.front_face, cull_mode=s.cull_mode,
             depth_stencil=depth_state, targets=[s.color_format])
-        self.target = device.create_texture(s.width, s.height, s.color_format)
+        self.target = target if target is not None else device.create_texture(s.width, s.height, s.color_format)
         self.target_view = self.target.create_view()
         self.depth_texture = self.depth_view = None
         if s.has_depth:
