@@ -275,6 +275,24 @@ WGB_API wgb_status wgb_render_pass_draw_indexed(wgb_render_pass pass, uint32_t f
                                                 int32_t base_vertex, uint32_t first_instance, uint32_t instance_count);
 /* RenderPassInterface::end (render_pass/mod.rs:309-329): pushes Command::RenderPass into the encoder */
 WGB_API wgb_status wgb_render_pass_end(wgb_render_pass pass);
+/* Encoder copies and clears: CommandEncoderInterface::copy_buffer_to_buffer / copy_buffer_to_texture /
+ * copy_texture_to_buffer / copy_texture_to_texture / clear_buffer / clear_texture (command.rs:37-115).  All six are
+ * `todo!()` in the reference (its tests read the texture's Vec<u8> directly, lib.rs:111-173); they are implemented
+ * here with WebGPU semantics because every standard wgpu app observes results through copy_texture_to_buffer +
+ * map_async.  They execute in order with the render passes of the same command buffer.
+ * Texel copies address mip 0; `bytes_per_row` is the buffer's row pitch (0 = tightly packed). */
+typedef struct { wgb_texture texture; uint32_t x, y, layer; } wgb_texel_copy_texture_info;
+typedef struct { wgb_buffer buffer; uint64_t offset; uint32_t bytes_per_row, rows_per_image; } wgb_texel_copy_buffer_info;
+WGB_API wgb_status wgb_command_encoder_copy_buffer_to_buffer(wgb_command_encoder encoder, wgb_buffer source, uint64_t source_offset,
+                                                             wgb_buffer destination, uint64_t destination_offset, uint64_t size);
+WGB_API wgb_status wgb_command_encoder_copy_buffer_to_texture(wgb_command_encoder encoder, const wgb_texel_copy_buffer_info* source,
+                                                              const wgb_texel_copy_texture_info* destination, uint32_t width, uint32_t height);
+WGB_API wgb_status wgb_command_encoder_copy_texture_to_buffer(wgb_command_encoder encoder, const wgb_texel_copy_texture_info* source,
+                                                              const wgb_texel_copy_buffer_info* destination, uint32_t width, uint32_t height);
+WGB_API wgb_status wgb_command_encoder_copy_texture_to_texture(wgb_command_encoder encoder, const wgb_texel_copy_texture_info* source,
+                                                               const wgb_texel_copy_texture_info* destination, uint32_t width, uint32_t height);
+WGB_API wgb_status wgb_command_encoder_clear_buffer(wgb_command_encoder encoder, wgb_buffer buffer, uint64_t offset, uint64_t size);
+WGB_API wgb_status wgb_command_encoder_clear_texture(wgb_command_encoder encoder, wgb_texture texture);
 /* CommandEncoderInterface::finish (command.rs:89-98) */
 WGB_API wgb_status wgb_command_encoder_finish(wgb_command_encoder encoder, wgb_command_buffer* out);
 /* QueueInterface::submit (device.rs:436-462): monotonically increasing submission index */

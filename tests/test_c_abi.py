@@ -139,3 +139,24 @@ def test_band_rows_match_python(offline):
     dev.set_band(0, 1)
     with pytest.raises(api.WgpuError):
         dev.set_band(2, 2)
+
+
+def test_encoder_copy_validation(offline):
+    dev, _ = offline
+    buf = dev.create_buffer(1024)
+    tex = dev.create_texture(16, 16, "rgba8unorm")
+    enc = dev.create_command_encoder()
+    enc.copy_texture_to_buffer(tex, buf)                       # 16*16*4 = 1024 bytes: fits exactly
+    enc.copy_buffer_to_buffer(buf, 0, buf, 512, 512)
+    enc.clear_buffer(buf, 16, 32)
+    with pytest.raises(api.WgpuError):
+        enc.copy_texture_to_buffer(tex, buf, bytes_per_row=256)  # 15*256 + 64 > 1024
+    with pytest.raises(api.WgpuError):
+        enc.copy_texture_to_buffer(tex, buf, size=(17, 1))
+    with pytest.raises(api.WgpuError):
+        enc.copy_buffer_to_buffer(buf, 1000, buf, 0, 100)
+    with pytest.raises(api.WgpuError):
+        enc.copy_texture_to_buffer(tex, buf, bytes_per_row=32)   # pitch smaller than a row
+    enc.finish()
+    with pytest.raises(api.WgpuError):
+        enc.clear_buffer(buf)                                    # encoder already finished

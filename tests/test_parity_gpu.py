@@ -164,3 +164,60 @@ def test_sort_first_bands_reassemble_the_single_gpu_frame(gpu, bands):
     assert np.array_equal(color, ref.color)
     assert np.array_equal(depth.view(np.uint32), ref.depth.view(np.uint32))
     assert frags == ref.stats["fragments_shaded"]
+
+
+def test_readback_through_copy_texture_to_buffer(gpu):
+    """the standard wgpu read-back (copy_texture_to_buffer with a 256-byte row pitch, then
+    map_async(Read)) returns the same texels as the direct texture read the reference's tests use."""
+    from wgpu_cpu_b200 import api
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    scene = S.hello_mesh(200, 120)
+    r = SceneRenderer(dev, queue, scene)
+    pitch = (scene.width * 4 + 255) // 256 * 256
+    staging = dev.create_buffer(pitch * scene.height, api.BUFFER_USAGE["MAP_READ"] | api.BUFFER_USAGE["COPY_DST"])
+    enc = dev.create_command_encoder()
+    enc.clear_buffer(staging)
+    cb_render = r.encode()
+    enc.copy_texture_to_buffer(r.target, staging, bytes_per_row=pitch)
+    idx = queue.submit([cb_render, enc.finish()])
+    dev.poll(True, idx)
+    staging.map_async("read")
+    rows = staging.get_mapped_range().reshape(scene.height, pitch)[:, :scene.width * 4].reshape(scene.height, scene.width, 4).copy()
+    staging.unmap()
+    assert np.array_equal(rows, r.target.read())
+    assert rows[..., :3].any()
+
+
+def test_encoder_copies_roundtrip(gpu):
+    from wgpu_cpu_b200 import api
+    dev, queue = gpu
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 255, (48, 64, 4), dtype=np.uint8)
+    src = dev.create_buffer_init(img, api.BUFFER_USAGE["COPY_SRC"])
+    a = dev.create_texture(64, 48, "rgba8unorm")
+    b = dev.create_texture(80, 60, "rgba8unorm")
+    out = dev.create_buffer(64 * 48 * 4, api.BUFFER_USAGE["COPY_DST"] | api.BUFFER_USAGE["MAP_READ"])
+    out2 = dev.create_buffer(64 * 48 * 4, api.BUFFER_USAGE["COPY_DST"] | api.BUFFER_USAGE["MAP_READ"])
+    enc = dev.create_command_encoder()
+    enc.copy_buffer_to_texture(src, a)
+    enc.copy_texture_to_texture(a, b, size=(32, 20), src_origin=(8, 4), dst_origin=(40, 30))
+    enc.copy_texture_to_buffer(a, out)
+    enc.copy_buffer_to_buffer(out, 256, out2, 512, 1024)
+    idx = queue.submit([enc.finish()])
+    dev.poll(True, idx)
+    assert np.array_equal(a.read(), img)
+    tb = b.read()
+    assert np.array_equal(tb[30:50, 40:72], img[4:24, 8:40]) and not tb[:30].any() and not tb[:, :40].any()
+    out.map_async("read")
+    assert np.array_equal(out.get_mapped_range(), img.reshape(-1))
+    out.unmap()
+    out2.map_async("read")
+    got = out2.get_mapped_range().copy()
+    out2.unmap()
+    assert np.array_equal(got[512:1536], img.reshape(-1)[256:1280]) and not got[:512].any() and not got[1536:].any()
+    enc = dev.create_command_encoder()
+    enc.clear_texture(a)
+    idx = queue.submit([enc.finish()])
+    dev.poll(True, idx)
+    assert not a.read().any()

@@ -115,6 +115,14 @@ class _RenderPipelineDescriptor(C.Structure):
                 ("targets", C.POINTER(_ColorTargetState))]
 
 
+class _TexelCopyTextureInfo(C.Structure):
+    _fields_ = [("texture", C.c_void_p), ("x", C.c_uint32), ("y", C.c_uint32), ("layer", C.c_uint32)]
+
+
+class _TexelCopyBufferInfo(C.Structure):
+    _fields_ = [("buffer", C.c_void_p), ("offset", C.c_uint64), ("bytes_per_row", C.c_uint32), ("rows_per_image", C.c_uint32)]
+
+
 class _ColorAttachment(C.Structure):
     _fields_ = [("view", C.c_void_p), ("load_op", C.c_uint32), ("store_op", C.c_uint32), ("clear_value", C.c_double * 4)]
 
@@ -384,6 +392,34 @@ class CommandEncoder(_Handle):
         h = C.c_void_p()
         _check(_lib.wgb_command_encoder_begin_render_pass(self._h, C.byref(desc), C.byref(h)))
         return RenderPass(h)
+
+    def copy_buffer_to_buffer(self, source: Buffer, source_offset: int, destination: Buffer, destination_offset: int, size: int = WHOLE_SIZE):
+        _check(_lib.wgb_command_encoder_copy_buffer_to_buffer(self._h, source._h, C.c_uint64(source_offset), destination._h,
+                                                              C.c_uint64(destination_offset), C.c_uint64(size)))
+
+    def copy_buffer_to_texture(self, source: Buffer, destination: Texture, size=None, offset=0, bytes_per_row=0, origin=(0, 0), layer=0):
+        w, h = size if size is not None else (destination.width, destination.height)
+        src = _TexelCopyBufferInfo(source._h, offset, bytes_per_row, 0)
+        dst = _TexelCopyTextureInfo(destination._h, origin[0], origin[1], layer)
+        _check(_lib.wgb_command_encoder_copy_buffer_to_texture(self._h, C.byref(src), C.byref(dst), w, h))
+
+    def copy_texture_to_buffer(self, source: Texture, destination: Buffer, size=None, offset=0, bytes_per_row=0, origin=(0, 0), layer=0):
+        w, h = size if size is not None else (source.width, source.height)
+        src = _TexelCopyTextureInfo(source._h, origin[0], origin[1], layer)
+        dst = _TexelCopyBufferInfo(destination._h, offset, bytes_per_row, 0)
+        _check(_lib.wgb_command_encoder_copy_texture_to_buffer(self._h, C.byref(src), C.byref(dst), w, h))
+
+    def copy_texture_to_texture(self, source: Texture, destination: Texture, size=None, src_origin=(0, 0), dst_origin=(0, 0)):
+        w, h = size if size is not None else (source.width, source.height)
+        src = _TexelCopyTextureInfo(source._h, src_origin[0], src_origin[1], 0)
+        dst = _TexelCopyTextureInfo(destination._h, dst_origin[0], dst_origin[1], 0)
+        _check(_lib.wgb_command_encoder_copy_texture_to_texture(self._h, C.byref(src), C.byref(dst), w, h))
+
+    def clear_buffer(self, buffer: Buffer, offset: int = 0, size: int = WHOLE_SIZE):
+        _check(_lib.wgb_command_encoder_clear_buffer(self._h, buffer._h, C.c_uint64(offset), C.c_uint64(size)))
+
+    def clear_texture(self, texture: Texture):
+        _check(_lib.wgb_command_encoder_clear_texture(self._h, texture._h))
 
     def finish(self) -> CommandBuffer:
         h = C.c_void_p()

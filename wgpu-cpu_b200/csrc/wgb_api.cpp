@@ -530,8 +530,19 @@ struct PassCommand {
     bool has_stencil_ops = false;
     std::vector<SubCommand> sub;
 };
-struct CommandBuffer : Object { Ref<Device> device; std::vector<std::shared_ptr<PassCommand>> passes; bool submitted = false; };
-struct CommandEncoder : Object { Ref<Device> device; std::vector<std::shared_ptr<PassCommand>> passes; bool finished = false; std::mutex mu; };
+// encoder-level copies / clears (command.rs:37-115); executed in order with the render passes
+struct CopyCommand {
+    enum Kind { BufferToBuffer, BufferToTexture, TextureToBuffer, TextureToTexture, ClearBuffer, ClearTexture } kind;
+    Ref<Buffer> src_buffer, dst_buffer;
+    Ref<Texture> src_texture, dst_texture;
+    uint64_t src_offset = 0, dst_offset = 0, size = 0;
+    uint32_t src_x = 0, src_y = 0, src_layer = 0, dst_x = 0, dst_y = 0, dst_layer = 0;
+    uint32_t bytes_per_row = 0, width = 0, height = 0;
+};
+// a recorded command is a render pass or a copy (command.rs:173-196 Command)
+struct Command { std::shared_ptr<PassCommand> pass; std::shared_ptr<CopyCommand> copy; };
+struct CommandBuffer : Object { Ref<Device> device; std::vector<Command> passes; bool submitted = false; };
+struct CommandEncoder : Object { Ref<Device> device; std::vector<Command> passes; bool finished = false; std::mutex mu; };
 struct RenderPass : Object {
     Ref<CommandEncoder> encoder;
     std::shared_ptr<PassCommand> cmd;
@@ -542,7 +553,7 @@ struct RenderPass : Object {
         if (ended) return;
         ended = true;
         std::lock_guard<std::mutex> el(encoder->mu);
-        encoder->passes.push_back(cmd);
+        encoder->passes.push_back(Command{cmd, nullptr});
     }
     ~RenderPass() override { end(); }
 };
@@ -882,6 +893,63 @@ void execute_pass(Device* dev, const PassCommand& pass) {
         cudaEventElapsedTime(&ms, dev->ev[0], dev->ev[2]);
         dev->last_stats.total_ms += ms;
     }
+}
+
+void execute_copy(Device* dev, const CopyCommand& c) {
+    auto tex_ptr = [](Texture* t, uint32_t x, uint32_t y, uint32_t layer) {
+        return (char*)t->dptr + (((uint64_t)layer * t->desc.height + y) * t->desc.width + x) * t->bpp;
+    };
+    switch (c.kind) {
+        case CopyCommand::BufferToBuffer:
+            if (c.size) CUDA_CHECK(cudaMemcpyAsync((char*)c.dst_buffer->dptr + c.dst_offset, (char*)c.src_buffer->dptr + c.src_offset, c.size, cudaMemcpyDeviceToDevice, dev->stream));
+            break;
+        case CopyCommand::ClearBuffer:
+            if (c.size) CUDA_CHECK(cudaMemsetAsync((char*)c.dst_buffer->dptr + c.dst_offset, 0, c.size, dev->stream));
+            break;
+        case CopyCommand::ClearTexture:
+            CUDA_CHECK(cudaMemsetAsync(c.dst_texture->dptr, 0, c.dst_texture->size, dev->stream));
+            break;
+        case CopyCommand::BufferToTexture: {
+            Texture* t = c.dst_texture.get();
+            const size_t row = (size_t)c.width * t->bpp, pitch = c.bytes_per_row ? c.bytes_per_row : row;
+            if (c.width && c.height)
+                CUDA_CHECK(cudaMemcpy2DAsync(tex_ptr(t, c.dst_x, c.dst_y, c.dst_layer), (size_t)t->desc.width * t->bpp,
+                                             (char*)c.src_buffer->dptr + c.src_offset, pitch, row, c.height, cudaMemcpyDeviceToDevice, dev->stream));
+            break;
+        }
+        case CopyCommand::TextureToBuffer: {
+            Texture* t = c.src_texture.get();
+            const size_t row = (size_t)c.width * t->bpp, pitch = c.bytes_per_row ? c.bytes_per_row : row;
+            if (c.width && c.height)
+                CUDA_CHECK(cudaMemcpy2DAsync((char*)c.dst_buffer->dptr + c.dst_offset, pitch, tex_ptr(t, c.src_x, c.src_y, c.src_layer),
+                                             (size_t)t->desc.width * t->bpp, row, c.height, cudaMemcpyDeviceToDevice, dev->stream));
+            break;
+        }
+        case CopyCommand::TextureToTexture: {
+            Texture *st = c.src_texture.get(), *dt = c.dst_texture.get();
+            if (c.width && c.height)
+                CUDA_CHECK(cudaMemcpy2DAsync(tex_ptr(dt, c.dst_x, c.dst_y, c.dst_layer), (size_t)dt->desc.width * dt->bpp,
+                                             tex_ptr(st, c.src_x, c.src_y, c.src_layer), (size_t)st->desc.width * st->bpp,
+                                             (size_t)c.width * st->bpp, c.height, cudaMemcpyDeviceToDevice, dev->stream));
+            break;
+        }
+    }
+}
+
+void record_copy(wgb_command_encoder encoder, std::shared_ptr<CopyCommand> c) {
+    CommandEncoder* enc = from_handle<CommandEncoder>(encoder, "command encoder");
+    std::lock_guard<std::mutex> lk(enc->mu);
+    REQUIRE(!enc->finished, "command encoder is finished");
+    enc->passes.push_back(Command{nullptr, c});
+}
+void check_texture_rect(const Texture* t, uint32_t x, uint32_t y, uint32_t layer, uint32_t w, uint32_t h, const char* what) {
+    REQUIRE((uint64_t)x + w <= t->desc.width && (uint64_t)y + h <= t->desc.height && layer < t->desc.depth_or_array_layers,
+            "%s: texture rectangle out of bounds", what);
+}
+void check_buffer_rect(const Buffer* b, uint64_t offset, uint32_t bytes_per_row, uint32_t bpp, uint32_t w, uint32_t h, const char* what) {
+    const uint64_t row = (uint64_t)w * bpp, pitch = bytes_per_row ? bytes_per_row : row;
+    REQUIRE(pitch >= row, "%s: bytes_per_row smaller than a row", what);
+    REQUIRE(h == 0 || offset + (uint64_t)(h - 1) * pitch + row <= b->size, "%s: buffer range out of bounds", what);
 }
 
 }  // namespace
@@ -1473,6 +1541,84 @@ wgb_status wgb_render_pass_draw_indexed(wgb_render_pass pass, uint32_t first_ind
 wgb_status wgb_render_pass_end(wgb_render_pass pass) {
     return guarded([&] { from_handle<RenderPass>(pass, "render pass")->end(); });
 }
+wgb_status wgb_command_encoder_copy_buffer_to_buffer(wgb_command_encoder encoder, wgb_buffer source, uint64_t source_offset,
+                                                     wgb_buffer destination, uint64_t destination_offset, uint64_t size) {
+    return guarded([&] {
+        auto c = std::make_shared<CopyCommand>();
+        c->kind = CopyCommand::BufferToBuffer;
+        c->src_buffer = Ref<Buffer>(from_handle<Buffer>(source, "buffer"));
+        c->dst_buffer = Ref<Buffer>(from_handle<Buffer>(destination, "buffer"));
+        if (size == WGB_WHOLE_SIZE) size = c->src_buffer->size - std::min(c->src_buffer->size, source_offset);
+        REQUIRE(source_offset + size <= c->src_buffer->size && destination_offset + size <= c->dst_buffer->size, "copy_buffer_to_buffer range out of bounds");
+        c->src_offset = source_offset; c->dst_offset = destination_offset; c->size = size;
+        record_copy(encoder, c);
+    });
+}
+wgb_status wgb_command_encoder_copy_buffer_to_texture(wgb_command_encoder encoder, const wgb_texel_copy_buffer_info* source,
+                                                      const wgb_texel_copy_texture_info* destination, uint32_t width, uint32_t height) {
+    return guarded([&] {
+        REQUIRE(source && destination, "null argument");
+        auto c = std::make_shared<CopyCommand>();
+        c->kind = CopyCommand::BufferToTexture;
+        c->src_buffer = Ref<Buffer>(from_handle<Buffer>(source->buffer, "buffer"));
+        c->dst_texture = Ref<Texture>(from_handle<Texture>(destination->texture, "texture"));
+        check_texture_rect(c->dst_texture.get(), destination->x, destination->y, destination->layer, width, height, "copy_buffer_to_texture");
+        check_buffer_rect(c->src_buffer.get(), source->offset, source->bytes_per_row, c->dst_texture->bpp, width, height, "copy_buffer_to_texture");
+        c->src_offset = source->offset; c->bytes_per_row = source->bytes_per_row;
+        c->dst_x = destination->x; c->dst_y = destination->y; c->dst_layer = destination->layer; c->width = width; c->height = height;
+        record_copy(encoder, c);
+    });
+}
+wgb_status wgb_command_encoder_copy_texture_to_buffer(wgb_command_encoder encoder, const wgb_texel_copy_texture_info* source,
+                                                      const wgb_texel_copy_buffer_info* destination, uint32_t width, uint32_t height) {
+    return guarded([&] {
+        REQUIRE(source && destination, "null argument");
+        auto c = std::make_shared<CopyCommand>();
+        c->kind = CopyCommand::TextureToBuffer;
+        c->src_texture = Ref<Texture>(from_handle<Texture>(source->texture, "texture"));
+        c->dst_buffer = Ref<Buffer>(from_handle<Buffer>(destination->buffer, "buffer"));
+        check_texture_rect(c->src_texture.get(), source->x, source->y, source->layer, width, height, "copy_texture_to_buffer");
+        check_buffer_rect(c->dst_buffer.get(), destination->offset, destination->bytes_per_row, c->src_texture->bpp, width, height, "copy_texture_to_buffer");
+        c->dst_offset = destination->offset; c->bytes_per_row = destination->bytes_per_row;
+        c->src_x = source->x; c->src_y = source->y; c->src_layer = source->layer; c->width = width; c->height = height;
+        record_copy(encoder, c);
+    });
+}
+wgb_status wgb_command_encoder_copy_texture_to_texture(wgb_command_encoder encoder, const wgb_texel_copy_texture_info* source,
+                                                       const wgb_texel_copy_texture_info* destination, uint32_t width, uint32_t height) {
+    return guarded([&] {
+        REQUIRE(source && destination, "null argument");
+        auto c = std::make_shared<CopyCommand>();
+        c->kind = CopyCommand::TextureToTexture;
+        c->src_texture = Ref<Texture>(from_handle<Texture>(source->texture, "texture"));
+        c->dst_texture = Ref<Texture>(from_handle<Texture>(destination->texture, "texture"));
+        REQUIRE(c->src_texture->bpp == c->dst_texture->bpp, "copy_texture_to_texture: texel sizes differ");
+        check_texture_rect(c->src_texture.get(), source->x, source->y, source->layer, width, height, "copy_texture_to_texture source");
+        check_texture_rect(c->dst_texture.get(), destination->x, destination->y, destination->layer, width, height, "copy_texture_to_texture destination");
+        c->src_x = source->x; c->src_y = source->y; c->src_layer = source->layer;
+        c->dst_x = destination->x; c->dst_y = destination->y; c->dst_layer = destination->layer; c->width = width; c->height = height;
+        record_copy(encoder, c);
+    });
+}
+wgb_status wgb_command_encoder_clear_buffer(wgb_command_encoder encoder, wgb_buffer buffer, uint64_t offset, uint64_t size) {
+    return guarded([&] {
+        auto c = std::make_shared<CopyCommand>();
+        c->kind = CopyCommand::ClearBuffer;
+        c->dst_buffer = Ref<Buffer>(from_handle<Buffer>(buffer, "buffer"));
+        if (size == WGB_WHOLE_SIZE) size = c->dst_buffer->size - std::min(c->dst_buffer->size, offset);
+        REQUIRE(offset + size <= c->dst_buffer->size, "clear_buffer range out of bounds");
+        c->dst_offset = offset; c->size = size;
+        record_copy(encoder, c);
+    });
+}
+wgb_status wgb_command_encoder_clear_texture(wgb_command_encoder encoder, wgb_texture texture) {
+    return guarded([&] {
+        auto c = std::make_shared<CopyCommand>();
+        c->kind = CopyCommand::ClearTexture;
+        c->dst_texture = Ref<Texture>(from_handle<Texture>(texture, "texture"));
+        record_copy(encoder, c);
+    });
+}
 wgb_status wgb_command_encoder_finish(wgb_command_encoder encoder, wgb_command_buffer* out) {
     return guarded([&] {
         CommandEncoder* enc = from_handle<CommandEncoder>(encoder, "command encoder");
@@ -1503,10 +1649,10 @@ wgb_status wgb_queue_submit(wgb_queue queue, const wgb_command_buffer* command_b
             REQUIRE(!cb->submitted, "command buffer was already submitted");
             REQUIRE(cb->device.get() == dev, "command buffer belongs to another device");
             cb->submitted = true;
-            for (const auto& pass : cb->passes) {
+            for (const auto& cmd : cb->passes) {
                 // errors raised while a submission executes surface at poll, where the reference's
                 // engine-thread panic would be observed (device.rs:498-503)
-                try { execute_pass(dev, *pass); }
+                try { if (cmd.pass) execute_pass(dev, *cmd.pass); else execute_copy(dev, *cmd.copy); }
                 catch (const Error& e) { st = e.status; msg = e.what(); break; }
             }
             cb->passes.clear();
