@@ -38,7 +38,10 @@ CONFIGS = {
     "c3": ("synthetic 10M-triangle mesh, vertex colours + depth, 3840x2160 (C3)", lambda S: S.synthetic_grid(3840, 2160, 1119, 4)),
     "c3s": ("synthetic 1M-triangle mesh 3840x2160 (reduced C3, smoke only)", lambda S: S.synthetic_grid(3840, 2160, 354, 4)),
     "c4": ("full-screen 64-iteration fragment shader 7680x4320 (C4)", lambda S: S.procedural(7680, 4320)),
+    "c5": ("batch of 64 frames of the textured bunny at 3840x2160, camera yaw = frame*tau/64 (C5); one step = 64 passes",
+           lambda S: S.hello_texture(3840, 2160)),
 }
+C5_FRAMES = 64
 
 
 def measured_peak_hbm():
@@ -213,9 +216,33 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # C5: a step is a batch of 64 frames, each with its own camera (a 64-byte uniform update per frame)
+    cameras = None
+    if args.config == "c5":
+        import math
+        cameras = [S.hello_texture(W, H, yaw=f * 2.0 * math.pi / C5_FRAMES).bindings[(0, 0)][1] for f in range(C5_FRAMES)]
+    passes_per_step = len(cameras) if cameras else 1
+
+    def step():
+        if cameras is None:
+            st = r.render()
+            gather()
+            return st
+        acc = None
+        for cam in cameras:
+            queue.write_buffer(r.resources[(0, 0)], 0, cam)
+            st = r.render()
+            gather()
+            if acc is None:
+                acc = dict(st)
+            else:
+                for k in ("primitives", "fragments", "shaded", "bin_pairs", "big_primitives", "clipped_primitives", "clip_records",
+                          "kernel_launches", "geometry_ms", "tile_ms", "total_ms"):
+                    acc[k] += st[k]
+        return acc
+
     for _ in range(warm):
-        r.render()
-        gather()
+        step()
 
     # ---- timed: K passes, inputs resident in HBM ----
     sampler = ClockSampler(local_rank)
@@ -224,8 +251,7 @@ def main():
     t0 = time.perf_counter()
     stats = []
     for _ in range(args.steps):
-        stats.append(r.render())       # submit + poll(Wait)
-        gather()
+        stats.append(step())           # submit + poll(Wait) (+ presenter exchange)
     barrier()
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -234,7 +260,7 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dt = float(tmax.item())
 
-    prims = scene.num_primitives
+    prims = scene.num_primitives * passes_per_step
     ms_step = dt / args.steps * 1e3
     tile_ms = float(np.mean([s["tile_ms"] for s in stats]))
     geom_ms = float(np.mean([s["geometry_ms"] for s in stats]))
@@ -243,7 +269,7 @@ def main():
 
     # ---- e2e: host buffers in, colour target out, every step ----
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e and world == 1 and cameras is None:
         pinned = []
         for vb in scene.vertex_buffers:
             t = torch.empty(vb.nbytes, dtype=torch.uint8, pin_memory=True)
@@ -301,8 +327,10 @@ def main():
     rec_bytes = 4 + 48
     tex_bytes = sum(res[1].nbytes for res in scene.bindings.values() if res[0] == "texture")
     band_px = W * (row1 - row0)
-    tile_bytes = (4 + (4 if scene.has_depth else 0)) * band_px + rec_bytes * pairs + tex_bytes
-    achieved = tile_bytes / (tile_ms * 1e-3) / 1e9 if tile_ms > 0 else 0.0
+    # per launch (a C5 step holds 64 launches)
+    tile_bytes = (4 + (4 if scene.has_depth else 0)) * band_px + tex_bytes + rec_bytes * pairs // passes_per_step
+    tile_launch_ms = tile_ms / passes_per_step
+    achieved = tile_bytes / (tile_launch_ms * 1e-3) / 1e9 if tile_ms > 0 else 0.0
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this workload
         if args.config == "c3" and world == 1:
@@ -314,13 +342,13 @@ def main():
     roofline = {"bound": "hbm", "kernel": "wgb_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "the kernel is instruction-issue bound (ncu: 77% issue-active, 8.6% DRAM); HBM is the roofline the path is held to",
-                "algorithmic_bytes_per_launch": int(tile_bytes), "avg_launch_ms": tile_ms,
+                "algorithmic_bytes_per_launch": int(tile_bytes), "avg_launch_ms": tile_launch_ms,
                 "frame_algorithmic_bytes": int(scene.algorithmic_bytes()),
-                "frame_hbm_frac": scene.algorithmic_bytes() / (dev_ms * 1e-3) / 1e9 / peak if dev_ms > 0 else None}
+                "frame_hbm_frac": scene.algorithmic_bytes() * passes_per_step / (dev_ms * 1e-3) / 1e9 / peak if dev_ms > 0 else None}
 
     cb = None
     if not args.no_cpu_baseline and world == 1:
-        cb = cpu_baseline(scene)
+        cb = cpu_baseline(scene)     # C5: one frame of the batch (the frames differ only in the camera)
 
     line = {
         "metric": "Mtri/s", "value": prims * args.steps / dt / 1e6, "unit": "Mtri/s", "n_gpus": world, "steps": args.steps,
@@ -334,7 +362,7 @@ def main():
                    "shaders": "WGSL translated to CUDA C++ and compiled with NVRTC for sm_100a"},
         "fragments_mpix_s": last["fragments"] * args.steps / dt / 1e6,
         "shaded_mpix_s": last["shaded"] * args.steps / dt / 1e6,
-        "framebuffer_mpix_s": W * H * args.steps / dt / 1e6,
+        "framebuffer_mpix_s": W * H * passes_per_step * args.steps / dt / 1e6,
         "device_ms_per_step": dev_ms, "geometry_ms": geom_ms, "tile_ms": tile_ms,
         "pass_stats": {k: last[k] for k in ("primitives", "fragments", "shaded", "bin_pairs", "big_primitives", "clipped_primitives",
                                             "clip_records", "kernel_launches", "replays")},

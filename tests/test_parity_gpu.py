@@ -221,3 +221,66 @@ def test_encoder_copies_roundtrip(gpu):
     idx = queue.submit([enc.finish()])
     dev.poll(True, idx)
     assert not a.read().any()
+
+
+def test_multiple_draws_ragged_and_empty(gpu):
+    _compare(S.multi_draw(), gpu)
+
+
+def test_instance_step_mode_buffer(gpu):
+    _compare(S.instanced_step_mode(), gpu)
+
+
+def test_huge_triangles_and_slivers(gpu):
+    got, ref = _compare(S.huge_triangles(), gpu)
+    assert got.stats["big_primitives"] > 0 and got.stats["clipped_primitives"] > 0
+
+
+@pytest.mark.parametrize("size", [(333, 77), (31, 33), (1, 1), (65, 1)])
+def test_odd_framebuffer_sizes(gpu, size):
+    _compare(S.odd_sizes(*size), gpu)
+
+
+def test_empty_scissor_draws_nothing_but_clears(gpu):
+    s = S.random_triangles(count=50, seed=91)
+    s.scissor = (10, 10, 0, 0)
+    s.name += "_empty_scissor"
+    got, ref = _compare(s, gpu)
+    assert got.stats["fragments"] == 0 and (got.color[..., 3] == 255).all() and not got.color[..., :3].any()
+
+
+def test_two_passes_in_one_submission_second_loads(gpu):
+    """A cleared pass followed by a LoadOp::Load pass on the same attachments (state.rs:135-145)."""
+    from oracle import pyoracle
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    s1 = S.random_triangles(count=80, seed=101)
+    r1 = SceneRenderer(dev, queue, s1)
+    cb1 = r1.encode()
+    s2 = S.random_triangles(count=80, seed=102, clear_color=None, clear_depth=None)
+    r2 = SceneRenderer(dev, queue, s2, target=r1.target)
+    r2.depth_texture, r2.depth_view = r1.depth_texture, r1.depth_view
+    cb2 = r2.encode()
+    idx = queue.submit([cb1, cb2])
+    dev.poll(True, idx)
+    f1 = pyoracle.render(s1)
+    s2.initial_color, s2.initial_depth = f1.color, f1.depth
+    f2 = pyoracle.render(s2)
+    assert np.array_equal(r1.target.read(), f2.color)
+    assert np.array_equal(r1.depth_texture.read().view(np.uint32), f2.depth.view(np.uint32))
+
+
+def test_out_of_bounds_index_is_an_error_and_leaves_the_target_untouched(gpu):
+    """The reference panics on the slice index (index.rs:45-51); here the pass aborts before any attachment write
+    and the error surfaces at poll."""
+    from wgpu_cpu_b200 import api
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    s = S.multi_draw()
+    s.draws = [S.Draw(True, 0, 90, 400)]          # base_vertex pushes every fetch outside the vertex buffer
+    r = SceneRenderer(dev, queue, s)
+    idx = r.submit()
+    with pytest.raises(api.WgpuError) as e:
+        dev.poll(True, idx)
+    assert e.value.status == 6
+    assert not r.target.read().any()

@@ -418,3 +418,58 @@ def frag_depth(width=160, height=120) -> Scene:
     s.name = "frag_depth"
     s.shader = "frag_depth"
     return s
+
+
+def multi_draw(width=192, height=128) -> Scene:
+    """Several draws in one pass over the same attachments (later draws see earlier depth/colour), u16 indices with a
+    base_vertex, a ragged index count (the incomplete tail primitive is dropped, util/mod.rs:58-76) and an empty draw."""
+    base = random_triangles(width, height, count=90, seed=61, spread=1.2, with_w=False)
+    idx = np.arange(270, dtype=np.uint16)
+    idx16 = np.concatenate([idx[:90], (idx[90:180] - 60).astype(np.uint16)])   # second range uses base_vertex = 60
+    base.name = "multi_draw"
+    base.index_data = idx16
+    base.draws = [Draw(True, 0, 90), Draw(False, 180, 90), Draw(True, 90, 89, 60), Draw(True, 0, 0), Draw(False, 0, 2)]
+    return base
+
+
+def instanced_step_mode(width=160, height=120, instances=5) -> Scene:
+    """A per-instance vertex buffer (VertexStepMode::Instance, vertex.rs:176-199): colours come from buffer 1."""
+    tri = np.array([[-0.9, -0.8, 0.5, 1.0], [-0.5, 0.1, 0.5, 1.0], [-0.1, -0.8, 0.5, 1.0]], dtype=np.float32)
+    u = splitmix64_u01(instances * 4, 71).reshape(instances, 4)
+    colors = np.ones((instances, 4), dtype=np.float32)
+    colors[:, :3] = u[:, :3]
+    params = np.zeros(20, dtype=np.float32)
+    params[:16] = np.eye(4, dtype=np.float32).reshape(-1)
+    params[16:20] = [0.3, 0.15, 0.05, 0.0]
+    return Scene(
+        name="instanced_step_mode", width=width, height=height, shader="features",
+        vertex_layouts=[VertexBufferLayout(16, "vertex", [VertexAttribute(0, "float32x4", 0)]),
+                        VertexBufferLayout(16, "instance", [VertexAttribute(1, "float32x4", 0)])],
+        vertex_buffers=[tri.view(np.uint8).reshape(-1), colors.view(np.uint8).reshape(-1)],
+        bindings={(0, 0): ("buffer", params.view(np.uint8).reshape(-1).copy())},
+        draws=[Draw(False, 0, 3, 0, 0, instances)],
+    )
+
+
+def huge_triangles(width=300, height=200) -> Scene:
+    """Triangles far larger than the framebuffer (heavy clipping, the all-tiles list) and slivers."""
+    v = np.array([
+        [-50.0, -40.0, 0.2, 1.0, 1, 0, 0, 1], [60.0, -45.0, 0.9, 1.0, 0, 1, 0, 1], [3.0, 70.0, 0.4, 1.0, 0, 0, 1, 1],
+        [-1.0, -1.0, 0.5, 1.0, 1, 1, 0, 1], [1.0, -1.0, 0.5, 1.0, 0, 1, 1, 1], [-1.0, 1.0, 0.5, 1.0, 1, 0, 1, 1],
+        [-0.99, 0.2, 0.1, 1.0, 1, 1, 1, 1], [0.99, 0.21, 0.1, 1.0, 0, 0, 0, 1], [0.99, 0.2, 0.1, 1.0, 1, 0, 0, 1],
+        [0.3, -3.0, 0.3, 0.5, 0, 1, 0, 1], [0.31, 3.0, 0.3, 2.0, 0, 0, 1, 1], [0.3, 3.0, 0.3, 1.0, 1, 1, 0, 1],
+        [-2.0, -2.0, -0.5, 1.0, 1, 0, 0, 1], [2.0, -2.0, 0.5, 1.0, 0, 1, 0, 1], [0.0, 2.0, 1.5, 1.0, 0, 0, 1, 1],
+    ], dtype=np.float32)
+    return Scene(
+        name="huge_triangles", width=width, height=height, shader="hello_mesh",
+        vertex_layouts=[_POS_COLOR_LAYOUT], vertex_buffers=[v.view(np.uint8).reshape(-1)],
+        bindings={(0, 0): ("buffer", identity_matrix_bytes())}, draws=[Draw(False, 0, 15)],
+    )
+
+
+def odd_sizes(width=333, height=77) -> Scene:
+    """A framebuffer that is not a multiple of the 32x32 tile, with a viewport larger than it."""
+    s = random_triangles(width, height, count=150, seed=81)
+    s.name = f"odd_sizes_{width}x{height}"
+    s.viewport = (-20.0, -10.0, 400.0, 100.0, 0.0, 1.0)
+    return s
