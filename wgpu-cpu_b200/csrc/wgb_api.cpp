@@ -271,7 +271,7 @@ struct DevBuf {
 // kernels of one compiled pipeline variant
 struct KernelSet {
     CUmodule module = nullptr;
-    CUfunction geometry = nullptr, clip = nullptr, scan = nullptr, fill = nullptr, tile = nullptr, clear = nullptr, strip_map = nullptr;
+    CUfunction geometry = nullptr, vertex = nullptr, geometry_cached = nullptr, clip = nullptr, scan = nullptr, fill = nullptr, tile = nullptr, clear = nullptr, strip_map = nullptr;
 };
 
 struct Instance : Object {};
@@ -290,7 +290,7 @@ struct Device : Object {
     wgb_status deferred_status = WGB_OK;   // error raised while executing a submission
     std::string deferred_error;
     // work buffers, grown on demand and reused across passes
-    DevBuf counters, prim_box, setup_cache, slow_list, clip_records, big_list, tile_count, tile_offset, tile_cursor, bins, coverage, strip_map, strip_count;
+    DevBuf counters, prim_box, setup_cache, vcache_raster, vcache_ndc, vcache_flags, slow_list, clip_records, big_list, tile_count, tile_offset, tile_cursor, bins, coverage, strip_map, strip_count;
     WgbCounters* host_counters = nullptr;   // pinned
     uint32_t clip_capacity = 0, big_capacity = 0;
     bool coverage_capture = false;
@@ -307,7 +307,7 @@ struct Device : Object {
         if (stream) cudaStreamSynchronize(stream);
         for (auto& f : inflight) cudaEventDestroy(f.done);
         for (auto& kv : kernel_cache) if (kv.second->module && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->module);
-        DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &slow_list, &clip_records, &big_list, &tile_count, &tile_offset, &tile_cursor, &bins, &coverage, &strip_map, &strip_count};
+        DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &vcache_raster, &vcache_ndc, &vcache_flags, &slow_list, &clip_records, &big_list, &tile_count, &tile_offset, &tile_cursor, &bins, &coverage, &strip_map, &strip_count};
         for (DevBuf* b : bufs) b->release();
         if (host_counters) cudaFreeHost(host_counters);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -491,6 +491,8 @@ struct RenderPipeline : Object {
                     if (q != CUDA_SUCCESS) fail(WGB_ERROR_DEVICE, "kernel %s missing: %s", n, cu_error(q));
                 };
                 fn("wgb_geometry_kernel", &ks->geometry);
+                fn("wgb_vertex_kernel", &ks->vertex);
+                fn("wgb_geometry_cached_kernel", &ks->geometry_cached);
                 fn("wgb_clip_kernel", &ks->clip);
                 fn("wgb_scan_kernel", &ks->scan);
                 fn("wgb_fill_kernel", &ks->fill);
@@ -671,6 +673,23 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             }
         }
     }
+    // post-transform vertex cache: indexed draws whose per-vertex buffers bound the vertex range
+    uint64_t vcache_n = 0;
+    if (indexed && !getenv("WGB_NO_VERTEX_CACHE")) {
+        uint64_t vn = UINT64_MAX;
+        bool any = false;
+        for (size_t b = 0; b < pipe->vbs.size(); b++) {
+            if (pipe->vbs[b].step_mode != WGB_VERTEX_STEP_MODE_VERTEX || pipe->vbs[b].attrs.empty()) continue;
+            uint64_t max_end = 0;
+            for (const auto& a : pipe->vbs[b].attrs) max_end = std::max<uint64_t>(max_end, a.offset + vertex_format_size(a.format));
+            any = true;
+            if (d.vb[b].size < max_end) { vn = 0; break; }
+            if (pipe->vbs[b].stride == 0) continue;                  // every vertex reads the same bytes
+            vn = std::min<uint64_t>(vn, (d.vb[b].size - max_end) / pipe->vbs[b].stride + 1);
+        }
+        // worth it only if the cache is not much larger than the index range, and addressable
+        if (any && vn != UINT64_MAX && vn > 0 && vn <= 2ull * sc.count + 1024 && vn * sc.instance_count <= (1ull << 27)) vcache_n = vn;
+    }
     d.num_color = tg.num_color;
     d.has_depth = tg.has_depth ? 1u : 0u;
     for (uint32_t c = 0; c < tg.num_color; c++) d.color[c] = tg.color[c];
@@ -719,7 +738,13 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             dev->clip_capacity = clip_cap; dev->big_capacity = big_cap;
             dev->counters.ensure(sizeof(WgbCounters));
             dev->prim_box.ensure((size_t)np * 4);
-            dev->setup_cache.ensure((size_t)np * 48);
+            if (!vcache_n) dev->setup_cache.ensure((size_t)np * 48);
+            if (vcache_n) {
+                const size_t nv = (size_t)vcache_n * sc.instance_count;
+                dev->vcache_raster.ensure(nv * 16); dev->vcache_ndc.ensure(nv * 8); dev->vcache_flags.ensure(nv * 4);
+                d.vcache_raster = dev->vcache_raster.addr(); d.vcache_ndc = dev->vcache_ndc.addr(); d.vcache_flags = dev->vcache_flags.addr();
+                d.vcache_count = (uint32_t)vcache_n;
+            }
             dev->slow_list.ensure((size_t)np * 4);
             dev->clip_records.ensure((size_t)clip_cap * sizeof(WgbClipRecord));
             dev->big_list.ensure((size_t)big_cap * sizeof(WgbBigEntry));
@@ -738,7 +763,11 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             CUDA_CHECK(cudaMemsetAsync(dev->counters.p, 0, sizeof(WgbCounters), dev->stream));
             CUDA_CHECK(cudaMemsetAsync(dev->tile_count.p, 0, (size_t)(band_tiles + 1) * 4, dev->stream));
             const uint32_t gblocks = (np + 255) / 256;
-            launch(dev, ks->geometry, dim3(gblocks), dim3(256), &d);
+            if (vcache_n) {
+                // the cache holds every instance of the draw, so it is filled once, by the first batch
+                if (base == 0) launch(dev, ks->vertex, dim3((uint32_t)(((uint64_t)vcache_n * sc.instance_count + 255) / 256)), dim3(256), &d);
+                launch(dev, ks->geometry_cached, dim3(gblocks), dim3(256), &d);
+            } else launch(dev, ks->geometry, dim3(gblocks), dim3(256), &d);
             launch(dev, ks->clip, dim3(std::min<uint32_t>((np + 127) / 128, 148 * 8)), dim3(128), &d);
             launch(dev, ks->scan, dim3(1), dim3(1024), &d);
             launch(dev, ks->fill, dim3(gblocks), dim3(256), &d);

@@ -83,6 +83,9 @@ struct WgbCounters {             // 64 bytes
 #define WGB_STATUS_W_ZERO 8u
 #define WGB_STATUS_BIG_OVERFLOW 16u
 
+#define WGB_VFLAG_INSIDE 1u              // inside all six clip planes
+#define WGB_VFLAG_W_ZERO 2u              // clip.w == 0 (the reference panics when such a vertex is used)
+
 // one record per primitive emitted by the clipper (slow path only)
 struct WgbClipRecord {          // 100 bytes
     float frag[3][4];           // to_raster'd CLIPPED vertices: (vp.x, vp.y, ndc.z, 1/w)
@@ -134,6 +137,12 @@ struct WgbDraw {
     wgb_u64 counters;                    // WgbCounters*
     wgb_u64 prim_box;                    // u32 per primitive: kind | packed tile box / clip record base
     wgb_u64 setup_cache;                 // float4 x 3 per primitive: to_raster'd vertices (vp.x, vp.y, ndc.z, 1/w) of unclipped primitives
+    // post-transform vertex cache (indexed draws): the vertex stage runs once per (instance, vertex) instead of once per index
+    wgb_u64 vcache_raster;               // float4 per vertex: (vp.x, vp.y, ndc.z, 1/w)
+    wgb_u64 vcache_ndc;                  // float2 per vertex: ndc.xy (winding)
+    wgb_u64 vcache_flags;                // u32 per vertex: WGB_VFLAG_*
+    wgb_u32 vcache_count;                // vertices per instance in the cache (0 = cache not in use)
+    wgb_u32 pad2;
     wgb_u64 slow_list;                   // u32 per slow primitive
     wgb_u64 clip_records;                // WgbClipRecord*
     wgb_u32 clip_capacity;
