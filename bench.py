@@ -195,6 +195,7 @@ def main():
     row0, row1 = dev.band_rows(H)
     assert (row0, row1) == multigpu.band_rows(H, rank, world)
     frame_t = None
+    host_barrier = multigpu.HostBarrier(rank, world, os.environ.get("MASTER_PORT", "0")) if world > 1 and args.present == "peer" else None
     if world > 1 and args.present == "nccl":
         ptr, nbytes = r.target.device_pointer()
         frame_t = multigpu.tensor_from_device_pointer(ptr, nbytes, local_rank).view(H, W, 4)
@@ -204,8 +205,9 @@ def main():
             return
         if args.present == "peer":
             # the tile kernels already stored every band into rank 0's target over NVLink; the render pass has
-            # completed on each rank's stream (poll(Wait)), so a barrier makes the frame visible to the presenter
-            dist.barrier()
+            # completed on each rank's stream (poll(Wait)), so a barrier between the rank processes (shared-memory
+            # page, no collective) makes the frame visible to the presenter
+            host_barrier.wait()
             return
         # the render pass has completed on the backend's stream (poll(Wait)); NCCL runs on torch's stream
         multigpu.gather_bands(frame_t, rank, world, dst=0)

@@ -52,3 +52,31 @@ def test_bands_tile_the_frame():
             assert rows[0][0] == 0 and rows[-1][1] == h
             assert all(rows[i][1] == rows[i + 1][0] for i in range(n - 1))
             assert all(a % 32 == 0 or a == h for a, _ in rows)
+
+
+def _barrier_worker(rank, world, port, out):
+    import time
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from wgpu_cpu_b200.multigpu import HostBarrier
+        hb = HostBarrier(rank, world, f"test{port}")
+        log = []
+        for i in range(50):
+            if rank == i % world:
+                time.sleep(0.002)          # a straggler: nobody may pass before it arrives
+            log.append(int(hb.slots[:, 0].min()))
+            hb.wait()
+            assert int(hb.slots[:, 0].min()) >= i + 1
+        if rank == 0:
+            np.save(out, np.asarray(log))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_host_barrier_world_size_2(tmp_path):
+    out = str(tmp_path / "log.npy")
+    mp.spawn(_barrier_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    log = np.load(out)
+    assert (log >= np.arange(50)).all()

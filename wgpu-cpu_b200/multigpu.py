@@ -51,6 +51,38 @@ def share_presenter_target(device, texture, rank: int, world: int, width: int, h
     return device.import_texture_ipc(handles[0], width, height, fmt)
 
 
+class HostBarrier:
+    """Barrier between the rank processes of one node through a POSIX shared-memory page: every rank bumps
+    its own 64-byte slot and spins until all slots reached the same count.  A few microseconds, against
+    ~50-80 us for a NCCL barrier driven from Python; used between frames, where the ranks only have to agree
+    that their tile kernels (which already stored the bands into the presenter's memory) have completed."""
+
+    def __init__(self, rank: int, world: int, name: str):
+        import mmap
+        import os
+        import torch.distributed as dist
+        self.rank, self.world, self.count = rank, world, 0
+        self.path = f"/dev/shm/wgb_barrier_{name}"
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.write(b"\0" * 64 * world)
+        dist.barrier()
+        self.fd = os.open(self.path, os.O_RDWR)
+        self.mm = mmap.mmap(self.fd, 64 * world)
+        import numpy as np
+        self.slots = np.frombuffer(self.mm, dtype=np.int64).reshape(world, 8)
+        dist.barrier()
+        if rank == 0:
+            os.unlink(self.path)
+
+    def wait(self):
+        self.count += 1
+        self.slots[self.rank, 0] = self.count
+        s = self.slots
+        while int(s[:, 0].min()) < self.count:
+            pass
+
+
 def tensor_from_device_pointer(ptr: int, nbytes: int, device_index: int):
     """Zero-copy torch uint8 view of device memory owned by the backend (a texture's texel storage)."""
     import torch
