@@ -181,7 +181,10 @@ def main():
 
     scene = make(S)
     W, H = scene.width, scene.height
-    dev, queue = api.instance().request_adapter().request_device(local_rank, band_rank=rank, band_count=world)
+    band_rank, band_count = rank, world
+    if world == 1 and os.environ.get("WGB_BENCH_BAND"):      # profiling aid: one rank's share of an N-way partition on one GPU
+        band_rank, band_count = (int(v) for v in os.environ["WGB_BENCH_BAND"].split("/"))
+    dev, queue = api.instance().request_adapter().request_device(local_rank, band_rank=band_rank, band_count=band_count)
     from wgpu_cpu_b200 import multigpu
     use_emitted = os.environ.get("WGB_USE_EMITTED", "0") == "1"
     target = None
@@ -193,7 +196,7 @@ def main():
 
     # presenter: every rank's colour band -> rank 0
     row0, row1 = dev.band_rows(H)
-    assert (row0, row1) == multigpu.band_rows(H, rank, world)
+    assert (row0, row1) == multigpu.band_rows(H, band_rank, band_count)
     frame_t = None
     host_barrier = multigpu.HostBarrier(rank, world, os.environ.get("MASTER_PORT", "0")) if world > 1 and args.present == "peer" else None
     if world > 1 and args.present == "nccl":

@@ -284,3 +284,17 @@ def test_out_of_bounds_index_is_an_error_and_leaves_the_target_untouched(gpu):
         dev.poll(True, idx)
     assert e.value.status == 6
     assert not r.target.read().any()
+
+
+def test_index_range_outside_the_index_buffer_is_an_error(gpu):
+    from wgpu_cpu_b200 import api
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    s = S.multi_draw()
+    s.draws = [S.Draw(True, 100, 200)]            # the index buffer holds 180 indices
+    r = SceneRenderer(dev, queue, s)
+    idx = r.submit()
+    with pytest.raises(api.WgpuError) as e:
+        dev.poll(True, idx)
+    assert e.value.status == 6 and "index buffer" in str(e.value)
+    assert not r.target.read().any()

@@ -642,6 +642,12 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
         REQUIRE(st.index_buffer.offset <= ib->size, "index buffer offset out of range");
         d.index_ptr = (uint64_t)(uintptr_t)ib->dptr + st.index_buffer.offset;
         d.index_size = std::min<uint64_t>(st.index_buffer.size, ib->size - st.index_buffer.offset);
+        // every index of the range is fetched (state.rs:521-535), so a range that leaves the buffer is a certain
+        // slice panic in the reference (index.rs:45-51); checked once here instead of per index on the device
+        const uint64_t isz = st.index_format == WGB_INDEX_FORMAT_UINT16 ? 2 : 4;
+        if (((uint64_t)sc.first + sc.count) * isz > d.index_size)
+            fail(WGB_ERROR_OUT_OF_BOUNDS, "draw_indexed range [%u, %u) lies outside the bound index buffer (%llu bytes)", sc.first,
+                 sc.first + sc.count, (unsigned long long)d.index_size);
     }
     for (size_t b = 0; b < pipe->vbs.size(); b++) {                                     // vertex.rs:262-272
         Buffer* vb = st.vertex_buffers[b].buffer.get();
