@@ -298,3 +298,37 @@ def test_index_range_outside_the_index_buffer_is_an_error(gpu):
         dev.poll(True, idx)
     assert e.value.status == 6 and "index buffer" in str(e.value)
     assert not r.target.read().any()
+
+
+def test_pinned_uploads_on_the_copy_stream_are_ordered_with_rendering(gpu):
+    """wgb_queue_write_buffer from pinned memory (>= 1 MiB) runs on the device's copy stream; each frame must see
+    exactly the data written before its submission (write-after-read and read-after-write hazards per buffer)."""
+    import torch
+    from oracle import pyoracle
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    scn = [S.random_triangles(count=12000, seed=sd, spread=1.2) for sd in (21, 22)]
+    assert scn[0].vertex_buffers[0].nbytes >= (1 << 20)
+    refs = [pyoracle.render(s, want_coverage=False).color for s in scn]
+    pinned = []
+    for s in scn:
+        t = torch.empty(s.vertex_buffers[0].nbytes, dtype=torch.uint8, pin_memory=True)
+        t.numpy()[:] = s.vertex_buffers[0]
+        pinned.append(t)
+    r = SceneRenderer(dev, queue, scn[0])
+    for k in (1, 0, 1, 1, 0):
+        queue.write_buffer(r.vertex_buffers[0], 0, pinned[k].numpy())
+        r.render()
+        # the next upload is enqueued before this frame is read back
+        queue.write_buffer(r.vertex_buffers[0], 0, pinned[1 - k].numpy())
+        queue.write_buffer(r.vertex_buffers[0], 0, pinned[k].numpy())
+        assert np.array_equal(r.target.read(), refs[k])
+        r.render()
+        assert np.array_equal(r.target.read(), refs[k])
+    # a small (render-stream) write after a pending copy-stream write must land after it
+    queue.write_buffer(r.vertex_buffers[0], 0, pinned[0].numpy())
+    queue.write_buffer(r.vertex_buffers[0], 0, scn[1].vertex_buffers[0][:4096])
+    r.render()
+    mixed = S.random_triangles(count=12000, seed=21, spread=1.2)
+    mixed.vertex_buffers[0][:4096] = scn[1].vertex_buffers[0][:4096]
+    assert np.array_equal(r.target.read(), pyoracle.render(mixed, want_coverage=False).color)

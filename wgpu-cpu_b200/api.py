@@ -253,10 +253,17 @@ class Texture(_Handle):
         v.texture = self
         return v
 
-    def read(self) -> np.ndarray:
-        """Texel bytes, row-major: what wgpu_cpu::dump_texture observes (lib.rs:111-173)."""
+    def read(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Texel bytes, row-major: what wgpu_cpu::dump_texture observes (lib.rs:111-173).  `out`: a caller-owned
+        uint8 destination of the texture's size (e.g. pinned host memory, so the copy is one DMA)."""
         bpp = BYTES_PER_TEXEL[TEXTURE_FORMAT[self.format]]
-        out = np.empty((self.layers, self.height, self.width, bpp), dtype=np.uint8)
+        shape = (self.layers, self.height, self.width, bpp)
+        if out is None:
+            out = np.empty(shape, dtype=np.uint8)
+        else:
+            if out.dtype != np.uint8 or out.size != int(np.prod(shape)) or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError("out must be a C-contiguous uint8 array of the texture's byte size")
+            out = out.reshape(shape)
         _check(_lib.wgb_texture_read(self._h, out.ctypes.data_as(C.c_void_p), C.c_uint64(out.nbytes)))
         if self.format == "depth32float":
             return out.view(np.float32).reshape(self.layers, self.height, self.width)[0]

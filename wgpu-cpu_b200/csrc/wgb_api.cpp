@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -281,6 +282,7 @@ struct Device : Object {
     int ordinal = -1;
     bool compile_only = false;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // large host->device uploads (wgb_queue_write_buffer from pinned memory)
     std::recursive_mutex mu;
     uint32_t band_rank = 0, band_count = 1;
     // submissions (device.rs:436-462, 517-541)
@@ -305,6 +307,7 @@ struct Device : Object {
         if (compile_only) return;
         cudaSetDevice(ordinal);
         if (stream) cudaStreamSynchronize(stream);
+        if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         for (auto& f : inflight) cudaEventDestroy(f.done);
         for (auto& kv : kernel_cache) if (kv.second->module && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->module);
         DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &vcache_raster, &vcache_ndc, &vcache_flags, &slow_list, &clip_records, &big_list, &tile_count, &tile_offset, &tile_cursor, &bins, &coverage, &strip_map, &strip_count};
@@ -327,7 +330,29 @@ struct Buffer : Object {
     bool mapped = false;
     uint32_t map_mode = 0;
     uint64_t map_offset = 0, map_size = 0;
-    ~Buffer() override { if (dptr) { cudaSetDevice(device->ordinal); cudaFree(dptr); } }
+    // hazard tracking between the device's render stream and its copy stream (large write_buffer uploads from
+    // pinned memory run on the copy stream so that they overlap rendering that does not touch this buffer);
+    // guarded by the device mutex
+    cudaEvent_t ev_write = nullptr, ev_use = nullptr;
+    bool write_pending = false, use_pending = false;
+    ~Buffer() override {
+        if (!dptr) return;
+        cudaSetDevice(device->ordinal);
+        if (write_pending) cudaEventSynchronize(ev_write);
+        if (ev_write) cudaEventDestroy(ev_write);
+        if (ev_use) cudaEventDestroy(ev_use);
+        cudaFree(dptr);
+    }
+    // make the render stream wait for an upload still in flight on the copy stream
+    void acquire_on(cudaStream_t stream) {
+        if (write_pending) { cudaStreamWaitEvent(stream, ev_write, 0); write_pending = false; }
+    }
+    // note that work using this buffer has been enqueued on `stream`
+    void mark_used(cudaStream_t stream) {
+        if (!ev_use) cudaEventCreateWithFlags(&ev_use, cudaEventDisableTiming);
+        cudaEventRecord(ev_use, stream);
+        use_pending = true;
+    }
 };
 
 struct Texture : Object {
@@ -1061,6 +1086,7 @@ wgb_status wgb_adapter_request_device(wgb_adapter adapter, const wgb_device_desc
             if (p.major != 10) fail(WGB_ERROR_DEVICE, "device %d is sm_%d%d; this backend is built for sm_100a (B200) only", ord, p.major, p.minor);
             load_driver_api();
             CUDA_CHECK(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
+            CUDA_CHECK(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
             for (auto& e2 : dev->ev) CUDA_CHECK(cudaEventCreate(&e2));
             for (auto& e2 : dev->timer_ev) CUDA_CHECK(cudaEventCreate(&e2));
             CUDA_CHECK(cudaMallocHost((void**)&dev->host_counters, sizeof(WgbCounters)));
@@ -1164,6 +1190,7 @@ wgb_status wgb_buffer_map_async(wgb_buffer buffer, uint32_t mode, uint64_t offse
         if (!dev->compile_only) {
             std::lock_guard<std::recursive_mutex> dl(dev->mu);
             dev->make_current();
+            b->acquire_on(dev->stream);
             CUDA_CHECK(cudaStreamSynchronize(dev->stream));
             // both modes start from the buffer's contents (a write guard derefs to the live Vec<u8>)
             if (b->size) CUDA_CHECK(cudaMemcpy(b->staging.data(), b->dptr, b->size, cudaMemcpyDeviceToHost));
@@ -1193,8 +1220,10 @@ wgb_status wgb_buffer_unmap(wgb_buffer buffer) {
         if (b->map_mode == WGB_MAP_MODE_WRITE && b->size && !dev->compile_only) {
             std::lock_guard<std::recursive_mutex> dl(dev->mu);
             dev->make_current();
+            b->acquire_on(dev->stream);
             CUDA_CHECK(cudaMemcpyAsync(b->dptr, b->staging.data(), b->size, cudaMemcpyHostToDevice, dev->stream));
             CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+            b->mark_used(dev->stream);
         }
         b->mapped = false;
         std::vector<uint8_t>().swap(b->staging);
@@ -1210,8 +1239,25 @@ wgb_status wgb_queue_write_buffer(wgb_queue queue, wgb_buffer buffer, uint64_t o
         if (dev->compile_only || size == 0) return;
         std::lock_guard<std::recursive_mutex> dl(dev->mu);
         dev->make_current();
-        // pageable source: the copy is staged before the call returns, so `data` may be reused
-        CUDA_CHECK(cudaMemcpyAsync((char*)b->dptr + offset, data, size, cudaMemcpyHostToDevice, dev->stream));
+        cudaPointerAttributes attr;
+        const bool pinned = size >= (1u << 20) && cudaPointerGetAttributes(&attr, data) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (pinned) {
+            // a large upload from pinned memory: DMA on the copy stream, ordered after the last use of this buffer
+            // only, so it overlaps rendering that reads other buffers; the next submission that uses the buffer
+            // waits for it.  (`data` must stay valid until then, as with any pinned asynchronous copy.)
+            if (b->use_pending) { CUDA_CHECK(cudaStreamWaitEvent(dev->copy_stream, b->ev_use, 0)); b->use_pending = false; }
+            if (b->write_pending) CUDA_CHECK(cudaStreamWaitEvent(dev->copy_stream, b->ev_write, 0));
+            CUDA_CHECK(cudaMemcpyAsync((char*)b->dptr + offset, data, size, cudaMemcpyHostToDevice, dev->copy_stream));
+            if (!b->ev_write) CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_write, cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventRecord(b->ev_write, dev->copy_stream));
+            b->write_pending = true;
+        } else {
+            // pageable source: the copy is staged before the call returns, so `data` may be reused
+            b->acquire_on(dev->stream);
+            CUDA_CHECK(cudaMemcpyAsync((char*)b->dptr + offset, data, size, cudaMemcpyHostToDevice, dev->stream));
+            b->mark_used(dev->stream);
+        }
     });
 }
 
@@ -1684,6 +1730,26 @@ wgb_status wgb_queue_submit(wgb_queue queue, const wgb_command_buffer* command_b
             REQUIRE(!cb->submitted, "command buffer was already submitted");
             REQUIRE(cb->device.get() == dev, "command buffer belongs to another device");
             cb->submitted = true;
+            // buffers this command buffer touches: wait for uploads still running on the copy stream
+            std::vector<Buffer*> used;
+            for (const auto& cmd : cb->passes) {
+                if (cmd.pass) {
+                    for (const SubCommand& sc : cmd.pass->sub) {
+                        if (sc.buffer) used.push_back(sc.buffer.get());
+                        if (sc.bind_group) for (const auto& e : sc.bind_group->entries) if (e.buffer) used.push_back(e.buffer.get());
+                    }
+                } else {
+                    if (cmd.copy->src_buffer) used.push_back(cmd.copy->src_buffer.get());
+                    if (cmd.copy->dst_buffer) used.push_back(cmd.copy->dst_buffer.get());
+                }
+            }
+            std::sort(used.begin(), used.end());
+            used.erase(std::unique(used.begin(), used.end()), used.end());
+            for (Buffer* b : used) b->acquire_on(dev->stream);
+            struct MarkUsed {
+                std::vector<Buffer*>& v; cudaStream_t s;
+                ~MarkUsed() { for (Buffer* b : v) b->mark_used(s); }
+            } mark_used{used, dev->stream};
             for (const auto& cmd : cb->passes) {
                 // errors raised while a submission executes surface at poll, where the reference's
                 // engine-thread panic would be observed (device.rs:498-503)
