@@ -332,3 +332,40 @@ def test_pinned_uploads_on_the_copy_stream_are_ordered_with_rendering(gpu):
     mixed = S.random_triangles(count=12000, seed=21, spread=1.2)
     mixed.vertex_buffers[0][:4096] = scn[1].vertex_buffers[0][:4096]
     assert np.array_equal(r.target.read(), pyoracle.render(mixed, want_coverage=False).color)
+
+
+def test_direct_bins_overflow_replays_then_learns_the_capacity(gpu):
+    """Direct binning gives every tile a fixed number of bin slots; a scene that piles its primitives into a few
+    tiles overflows them on first sight, the pass is aborted before any texel is written, and the draw replays with
+    the capacity the tile kernel reported."""
+    from wgpu_cpu_b200.render import SceneRenderer
+    from oracle import pyoracle
+    dev, queue = gpu
+    scene = S.random_triangles(count=4000, seed=31, spread=0.12)
+    ref = pyoracle.render(scene, want_coverage=False)
+    r = SceneRenderer(dev, queue, scene)
+    st = r.render()
+    assert st["replays"] >= 1
+    f = r.read()
+    assert np.array_equal(f.color, ref.color) and np.array_equal(f.depth.view(np.uint32), ref.depth.view(np.uint32))
+    st = r.render()
+    assert st["replays"] == 0
+    assert np.array_equal(r.read().color, ref.color)
+
+
+def test_count_scan_fill_binning_matches_direct_binning(monkeypatch):
+    """WGB_NO_DIRECT_BINS=1 keeps the exact-size bins (count, scan, fill kernels); both binning modes must give the
+    same frame."""
+    from wgpu_cpu_b200 import api
+    from wgpu_cpu_b200.render import render_scene
+    monkeypatch.setenv("WGB_NO_DIRECT_BINS", "1")
+    dev2, queue2 = api.instance().request_adapter().request_device(0)
+    monkeypatch.delenv("WGB_NO_DIRECT_BINS")
+    dev1, queue1 = api.instance().request_adapter().request_device(0)
+    for scene in (S.synthetic_grid(640, 360, n=120, layers=3), S.random_triangles(count=900, seed=5), S.hello_mesh(256, 256)):
+        a = render_scene(dev1, queue1, scene)
+        b = render_scene(dev2, queue2, scene)
+        assert a.stats["kernel_launches"] < b.stats["kernel_launches"]
+        assert np.array_equal(a.color, b.color) and np.array_equal(a.coverage, b.coverage)
+        assert np.array_equal(a.depth.view(np.uint32), b.depth.view(np.uint32))
+        assert a.stats["bin_pairs"] == b.stats["bin_pairs"] and a.stats["fragments"] == b.stats["fragments"]

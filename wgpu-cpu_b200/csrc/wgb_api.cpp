@@ -292,6 +292,8 @@ struct Device : Object {
     wgb_status deferred_status = WGB_OK;   // error raised while executing a submission
     std::string deferred_error;
     // work buffers, grown on demand and reused across passes
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> bin_cap_hint;   // (primitives, band tiles) of a draw -> slots per tile it needed
+    bool no_direct_bins = false;
     DevBuf counters, prim_box, setup_cache, vcache_raster, vcache_ndc, vcache_flags, slow_list, clip_records, big_list, tile_count, tile_offset, tile_cursor, bins, coverage, strip_map, strip_count;
     WgbCounters* host_counters = nullptr;   // pinned
     uint32_t clip_capacity = 0, big_capacity = 0;
@@ -782,7 +784,20 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             dev->tile_count.ensure((size_t)(band_tiles + 1) * 4);
             dev->tile_offset.ensure((size_t)(band_tiles + 1) * 4);
             dev->tile_cursor.ensure((size_t)(band_tiles + 1) * 4);
-            dev->bins.ensure(((size_t)np + clip_cap) * WGB_SMALL_MAX_TILES * 4);
+            // direct binning: a fixed number of slots per tile, sized from what this draw shape needed before
+            // (or twice the mean on first sight); the geometry kernels then store the bin entries themselves and
+            // the scan + fill kernels are skipped.  A tile that overflows flags the pass and the draw is replayed.
+            uint32_t bin_cap = 0;
+            {
+                const std::pair<uint32_t, uint32_t> key(np, band_tiles);
+                auto it = dev->bin_cap_hint.find(key);
+                uint64_t cap = it != dev->bin_cap_hint.end() ? it->second
+                                                             : 2 * ((uint64_t)np * 5 / 4) / std::max<uint32_t>(band_tiles, 1) + 64;
+                cap = (std::max<uint64_t>(cap, 256) + 255) & ~255ull;
+                if (!dev->no_direct_bins && band_tiles > 0 && (uint64_t)band_tiles * cap * 4 <= (1ull << 30)) bin_cap = (uint32_t)cap;
+            }
+            d.bin_cap = bin_cap;
+            dev->bins.ensure(bin_cap ? (size_t)band_tiles * bin_cap * 4 : ((size_t)np + clip_cap) * WGB_SMALL_MAX_TILES * 4);
             d.counters = dev->counters.addr(); d.prim_box = dev->prim_box.addr(); d.slow_list = dev->slow_list.addr();
             d.setup_cache = dev->setup_cache.addr();
             d.clip_records = dev->clip_records.addr(); d.clip_capacity = clip_cap;
@@ -799,9 +814,11 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 if (base == 0) launch(dev, ks->vertex, dim3((uint32_t)(((uint64_t)vcache_n * sc.instance_count + 255) / 256)), dim3(256), &d);
                 launch(dev, ks->geometry_cached, dim3(gblocks), dim3(256), &d);
             } else launch(dev, ks->geometry, dim3(gblocks), dim3(256), &d);
-            launch(dev, ks->clip, dim3(std::min<uint32_t>((np + 127) / 128, 148 * 8)), dim3(128), &d);
-            launch(dev, ks->scan, dim3(1), dim3(1024), &d);
-            launch(dev, ks->fill, dim3(gblocks), dim3(256), &d);
+            launch(dev, ks->clip, dim3(std::min<uint32_t>((np + 31) / 32, 148 * 16)), dim3(128), &d);   // 8 primitives per warp
+            if (!bin_cap) {
+                launch(dev, ks->scan, dim3(1), dim3(1024), &d);
+                launch(dev, ks->fill, dim3(gblocks), dim3(256), &d);
+            }
             CUDA_CHECK(cudaEventRecord(dev->ev[1], dev->stream));
             launch(dev, ks->tile, dim3(d.tiles_x, d.band_ty1 - d.band_ty0), dim3(256), &d);
             CUDA_CHECK(cudaEventRecord(dev->ev[2], dev->stream));
@@ -814,7 +831,10 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             dev->last_stats.geometry_ms += g_ms;
             dev->last_stats.tile_ms += t_ms;
             dev->last_stats.total_ms += g_ms + t_ms;
-            if (c.status & (WGB_STATUS_CLIP_OVERFLOW | WGB_STATUS_BIG_OVERFLOW)) {
+            if (dev->bin_cap_hint.size() > 4096) dev->bin_cap_hint.clear();
+            if (c.max_tile_pairs)
+                dev->bin_cap_hint[std::make_pair(np, band_tiles)] = (uint32_t)std::min<uint64_t>((uint64_t)c.max_tile_pairs * 5 / 4 + 64, 0xFFFFFF00ull);
+            if (c.status & (WGB_STATUS_CLIP_OVERFLOW | WGB_STATUS_BIG_OVERFLOW | WGB_STATUS_BIN_OVERFLOW)) {
                 // the tile kernel saw the flag and left the attachments untouched: grow and replay
                 if (attempt >= 8) fail(WGB_ERROR_OUT_OF_MEMORY, "work buffers still too small after %d replays", attempt);
                 if (c.status & WGB_STATUS_CLIP_OVERFLOW) dev->clip_capacity = std::max<uint32_t>(dev->clip_capacity * 2, c.num_clip_records + 1024);
@@ -1087,6 +1107,7 @@ wgb_status wgb_adapter_request_device(wgb_adapter adapter, const wgb_device_desc
             load_driver_api();
             CUDA_CHECK(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
             CUDA_CHECK(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
+            dev->no_direct_bins = getenv("WGB_NO_DIRECT_BINS") != nullptr;      // testing knob: always count / scan / fill
             for (auto& e2 : dev->ev) CUDA_CHECK(cudaEventCreate(&e2));
             for (auto& e2 : dev->timer_ev) CUDA_CHECK(cudaEventCreate(&e2));
             CUDA_CHECK(cudaMallocHost((void**)&dev->host_counters, sizeof(WgbCounters)));

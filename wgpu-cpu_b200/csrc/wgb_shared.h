@@ -72,7 +72,7 @@ struct WgbCounters {             // 64 bytes
     wgb_u32 num_big;            // entries in the big list
     wgb_u32 num_small_pairs;    // total (entry, tile) pairs in the bins (after the scan)
     wgb_u32 status;             // WGB_STATUS_* bits
-    wgb_u32 pad0;
+    wgb_u32 max_tile_pairs;     // largest per-tile pair count the tile kernel saw (sizes bin_cap for the next draw)
     wgb_u64 fragments;          // rasterised fragments (what the reference runs its fragment stage on)
     wgb_u64 shaded;             // fragment-shader invocations for surviving fragments
     wgb_u32 pad[6];
@@ -82,6 +82,7 @@ struct WgbCounters {             // 64 bytes
 #define WGB_STATUS_VERTEX_OOB 4u
 #define WGB_STATUS_W_ZERO 8u
 #define WGB_STATUS_BIG_OVERFLOW 16u
+#define WGB_STATUS_BIN_OVERFLOW 32u    // direct binning: a tile received more than bin_cap entries
 
 #define WGB_VFLAG_INSIDE 1u              // inside all six clip planes
 #define WGB_VFLAG_W_ZERO 2u              // clip.w == 0 (the reference panics when such a vertex is used)
@@ -150,7 +151,7 @@ struct WgbDraw {
     wgb_u32 pad1;
     wgb_u64 big_list;                    // WgbBigEntry*
     wgb_u32 big_capacity;
-    wgb_u32 pad0;
+    wgb_u32 bin_cap;                     // direct binning: entries reserved per tile, bins[tile * bin_cap + slot]; 0 = count / scan / fill
     wgb_u64 tile_count;                  // u32 per tile in the band
     wgb_u64 tile_offset;                 // u32 per tile (+1)
     wgb_u64 tile_cursor;                 // u32 per tile
