@@ -814,7 +814,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 if (base == 0) launch(dev, ks->vertex, dim3((uint32_t)(((uint64_t)vcache_n * sc.instance_count + 255) / 256)), dim3(256), &d);
                 launch(dev, ks->geometry_cached, dim3(gblocks), dim3(256), &d);
             } else launch(dev, ks->geometry, dim3(gblocks), dim3(256), &d);
-            launch(dev, ks->clip, dim3(std::min<uint32_t>((np + 31) / 32, 148 * 16)), dim3(128), &d);   // 8 primitives per warp
+            launch(dev, ks->clip, dim3(std::min<uint32_t>((np + 127) / 128, 148 * 8)), dim3(128), &d);
             if (!bin_cap) {
                 launch(dev, ks->scan, dim3(1), dim3(1024), &d);
                 launch(dev, ks->fill, dim3(gblocks), dim3(256), &d);
