@@ -769,7 +769,8 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             const uint32_t clip_cap = std::max<uint32_t>(dev->clip_capacity, np / 16);
             const uint32_t big_cap = std::max<uint32_t>(dev->big_capacity, std::max<uint32_t>(65536, np / 8));
             dev->clip_capacity = clip_cap; dev->big_capacity = big_cap;
-            dev->counters.ensure(sizeof(WgbCounters));
+            // the counters and the per-tile pair counts share one buffer: one memset clears both
+            dev->counters.ensure(sizeof(WgbCounters) + (size_t)(band_tiles + 1) * 4);
             dev->prim_box.ensure((size_t)np * 4);
             if (!vcache_n) dev->setup_cache.ensure((size_t)np * 48);
             if (vcache_n) {
@@ -781,7 +782,6 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             dev->slow_list.ensure((size_t)np * 4);
             dev->clip_records.ensure((size_t)clip_cap * sizeof(WgbClipRecord));
             dev->big_list.ensure((size_t)big_cap * sizeof(WgbBigEntry));
-            dev->tile_count.ensure((size_t)(band_tiles + 1) * 4);
             dev->tile_offset.ensure((size_t)(band_tiles + 1) * 4);
             dev->tile_cursor.ensure((size_t)(band_tiles + 1) * 4);
             // direct binning: a fixed number of slots per tile, sized from what this draw shape needed before
@@ -802,12 +802,11 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             d.setup_cache = dev->setup_cache.addr();
             d.clip_records = dev->clip_records.addr(); d.clip_capacity = clip_cap;
             d.big_list = dev->big_list.addr(); d.big_capacity = big_cap;
-            d.tile_count = dev->tile_count.addr(); d.tile_offset = dev->tile_offset.addr(); d.tile_cursor = dev->tile_cursor.addr();
+            d.tile_count = dev->counters.addr() + sizeof(WgbCounters); d.tile_offset = dev->tile_offset.addr(); d.tile_cursor = dev->tile_cursor.addr();
             d.bins = dev->bins.addr();
 
             CUDA_CHECK(cudaEventRecord(dev->ev[0], dev->stream));
-            CUDA_CHECK(cudaMemsetAsync(dev->counters.p, 0, sizeof(WgbCounters), dev->stream));
-            CUDA_CHECK(cudaMemsetAsync(dev->tile_count.p, 0, (size_t)(band_tiles + 1) * 4, dev->stream));
+            CUDA_CHECK(cudaMemsetAsync(dev->counters.p, 0, sizeof(WgbCounters) + (size_t)(band_tiles + 1) * 4, dev->stream));
             const uint32_t gblocks = (np + 255) / 256;
             if (vcache_n) {
                 // the cache holds every instance of the draw, so it is filled once, by the first batch
