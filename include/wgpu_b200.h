@@ -303,7 +303,8 @@ WGB_API wgb_status wgb_queue_submit(wgb_queue queue, const wgb_command_buffer* c
  *      render_pass/mod.rs:346,392-393 and state.rs:516-517,592) ---- */
 typedef struct {
     uint64_t primitives;          /* submitted (assembled) primitives */
-    uint64_t fragments;           /* rasterised fragments = the reference's fragment-stage invocations */
+    uint64_t fragments;           /* rasterised fragments = the reference's fragment-stage invocations (with coverage capture
+                                     on; otherwise fragments of primitives dropped by the hierarchical depth test are not counted) */
     uint64_t shaded;              /* fragment-shader invocations this backend ran for surviving fragments */
     uint64_t bin_pairs;           /* (primitive, tile) pairs in the per-tile bins */
     uint64_t big_primitives;      /* primitives on the all-tiles list */
@@ -314,6 +315,7 @@ typedef struct {
     float tile_ms;                /* tile kernels */
     float total_ms;               /* whole pass on the device */
     uint32_t replays;             /* draws replayed after growing a work buffer */
+    uint64_t hiz_culled;          /* (primitive, tile) pairs dropped before rasterisation: every fragment provably fails the depth test */
 } wgb_pass_stats;
 /* statistics of the most recently executed render pass on this device */
 WGB_API wgb_status wgb_device_get_last_pass_stats(wgb_device device, wgb_pass_stats* out);

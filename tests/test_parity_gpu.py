@@ -42,6 +42,12 @@ def _compare(scene, gpu, use_emitted=False):
     assert not msg, f"{scene.name}: " + "; ".join(msg)
     assert got.stats["fragments"] == ref.stats["fragments_shaded"] or scene.shader in ("features",), \
         f"{scene.name}: fragment count {got.stats['fragments']} != {ref.stats['fragments_shaded']}"
+    # the production configuration: no coverage capture, so the hierarchical depth test is active
+    fast = render_scene(dev, queue, scene, want_coverage=False, use_emitted=use_emitted)
+    assert np.array_equal(fast.color, ref.color), f"{scene.name}: colour differs with the hierarchical depth test on"
+    if ref.depth is not None:
+        assert np.array_equal(fast.depth.view(np.uint32), ref.depth.view(np.uint32)), \
+            f"{scene.name}: depth differs with the hierarchical depth test on"
     return got, ref
 
 
@@ -369,3 +375,25 @@ def test_count_scan_fill_binning_matches_direct_binning(monkeypatch):
         assert np.array_equal(a.color, b.color) and np.array_equal(a.coverage, b.coverage)
         assert np.array_equal(a.depth.view(np.uint32), b.depth.view(np.uint32))
         assert a.stats["bin_pairs"] == b.stats["bin_pairs"] and a.stats["fragments"] == b.stats["fragments"]
+
+
+@pytest.mark.parametrize("order", ["front_to_back", "back_to_front"])
+def test_hierarchical_depth_test_drops_hidden_triangles_without_changing_the_frame(gpu, order):
+    """Layered small triangles (the C3 structure): with the near layer drawn first most of the far layers is dropped
+    before rasterisation; the frame must not change, whatever the order."""
+    from oracle import pyoracle
+    from wgpu_cpu_b200.render import render_scene
+    dev, queue = gpu
+    scene = S.synthetic_grid(960, 540, n=280, layers=4)
+    if order == "back_to_front":
+        idx = scene.index_data.reshape(4, -1)
+        scene.index_data = np.ascontiguousarray(idx[::-1]).reshape(-1)
+    ref = pyoracle.render(scene, want_coverage=False)
+    got = render_scene(dev, queue, scene, want_coverage=False)
+    assert np.array_equal(got.color, ref.color)
+    assert np.array_equal(got.depth.view(np.uint32), ref.depth.view(np.uint32))
+    if order == "front_to_back":
+        assert got.stats["hiz_culled"] > 0.25 * got.stats["bin_pairs"]
+    full = render_scene(dev, queue, scene, want_coverage=True)
+    assert full.stats["hiz_culled"] == 0 and full.stats["fragments"] == ref.stats["fragments_shaded"]
+    assert got.stats["fragments"] <= full.stats["fragments"]

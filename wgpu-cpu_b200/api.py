@@ -141,7 +141,7 @@ class PassStats(C.Structure):
     _fields_ = [("primitives", C.c_uint64), ("fragments", C.c_uint64), ("shaded", C.c_uint64), ("bin_pairs", C.c_uint64),
                 ("big_primitives", C.c_uint64), ("clipped_primitives", C.c_uint64), ("clip_records", C.c_uint64),
                 ("draws", C.c_uint32), ("kernel_launches", C.c_uint32), ("geometry_ms", C.c_float), ("tile_ms", C.c_float),
-                ("total_ms", C.c_float), ("replays", C.c_uint32)]
+                ("total_ms", C.c_float), ("replays", C.c_uint32), ("hiz_culled", C.c_uint64)]
 
     def as_dict(self):
         return {f[0]: getattr(self, f[0]) for f in self._fields_}

@@ -851,6 +851,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             dev->last_stats.big_primitives += c.num_big;
             dev->last_stats.clipped_primitives += c.num_slow;
             dev->last_stats.clip_records += c.num_clip_records;
+            dev->last_stats.hiz_culled += c.hiz_culled;
             break;
         }
         // the clear has been applied by the first executed batch

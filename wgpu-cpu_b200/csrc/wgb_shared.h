@@ -75,7 +75,8 @@ struct WgbCounters {             // 64 bytes
     wgb_u32 max_tile_pairs;     // largest per-tile pair count the tile kernel saw (sizes bin_cap for the next draw)
     wgb_u64 fragments;          // rasterised fragments (what the reference runs its fragment stage on)
     wgb_u64 shaded;             // fragment-shader invocations for surviving fragments
-    wgb_u32 pad[6];
+    wgb_u32 hiz_culled;         // bin entries the tile kernel dropped by the hierarchical depth test
+    wgb_u32 pad[5];
 };
 #define WGB_STATUS_CLIP_OVERFLOW 1u
 #define WGB_STATUS_INDEX_OOB 2u
