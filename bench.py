@@ -340,26 +340,30 @@ def main():
     # ---- roofline of the dominant kernel (tile kernel): algorithmic bytes per launch / CUDA-event time ----
     peak, peak_src = measured_peak_hbm()
     # bytes_tile = (Bc + Bd)*W*H + R*P + Tex, with P = (primitive, tile) pairs and R = the bytes of the
-    # per-primitive record the tile kernel reads: a 4-byte bin entry + the 48-byte setup-cache record
+    # per-primitive record the tile kernel reads: a 4-byte bin entry plus, for indexed draws, three
+    # 4-byte indices and three 16-byte post-transform vertices (64 B), else the 48-byte setup-cache record (52 B)
     pairs = last["bin_pairs"] + last["big_primitives"]
-    rec_bytes = 4 + 48
+    rec_bytes = 4 + (12 + 48 if scene.index_data is not None else 48)
     tex_bytes = sum(res[1].nbytes for res in scene.bindings.values() if res[0] == "texture")
     band_px = W * (row1 - row0)
     # per launch (a C5 step holds 64 launches)
     tile_bytes = (4 + (4 if scene.has_depth else 0)) * band_px + tex_bytes + rec_bytes * pairs // passes_per_step
     tile_launch_ms = tile_ms / passes_per_step
     achieved = tile_bytes / (tile_launch_ms * 1e-3) / 1e9 if tile_ms > 0 else 0.0
-    traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this workload
+    traffic, note = None, "the kernel is instruction-issue bound; HBM is the roofline the path is held to"
+    try:   # one `ncu --set full` capture of this kernel on this workload (tools/make_profiles.py)
         if args.config == "c3" and world == 1:
-            for k in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_c3_v5.json"))):
+            for k in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_c3.json"))):
                 if k["Kernel Name"] == "wgb_tile_kernel":
-                    traffic = int((float(k["dram__bytes_read.sum"].split()[0]) + float(k["dram__bytes_write.sum"].split()[0])) * 1e6)
+                    num = lambda key: float(k[key].split()[0].replace(",", ""))
+                    traffic = int((num("dram__bytes_read.sum") + num("dram__bytes_write.sum")) * 1e6)
+                    note = (f"the kernel is instruction-issue bound (ncu: {num('smsp__issue_active.avg.pct_of_peak_sustained_active'):.0f}% issue-active, "
+                            f"{num('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f}% DRAM throughput; DRAM traffic below the algorithmic bytes "
+                            "= vertices shared by neighbouring triangles hit L2); HBM is the roofline the path is held to")
     except Exception:
         traffic = None
     roofline = {"bound": "hbm", "kernel": "wgb_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "note": "the kernel is instruction-issue bound (ncu: 77% issue-active, 8.6% DRAM); HBM is the roofline the path is held to",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "note": note,
                 "algorithmic_bytes_per_launch": int(tile_bytes), "avg_launch_ms": tile_launch_ms,
                 "frame_algorithmic_bytes": int(scene.algorithmic_bytes()),
                 "frame_hbm_frac": scene.algorithmic_bytes() * passes_per_step / (dev_ms * 1e-3) / 1e9 / peak if dev_ms > 0 else None}
@@ -382,8 +386,8 @@ def main():
         "shaded_mpix_s": last["shaded"] * args.steps / dt / 1e6,
         "framebuffer_mpix_s": W * H * passes_per_step * args.steps / dt / 1e6,
         "device_ms_per_step": dev_ms, "geometry_ms": geom_ms, "tile_ms": tile_ms,
-        "pass_stats": {k: last[k] for k in ("primitives", "fragments", "shaded", "bin_pairs", "big_primitives", "clipped_primitives",
-                                            "clip_records", "kernel_launches", "replays")},
+        "pass_stats": {k: last[k] for k in ("primitives", "fragments", "shaded", "bin_pairs", "hiz_culled", "big_primitives",
+                                            "clipped_primitives", "clip_records", "kernel_launches", "replays")},
         "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "clocks": clocks,
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
     }
