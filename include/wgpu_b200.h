@@ -165,6 +165,12 @@ WGB_API wgb_status wgb_queue_write_texture(wgb_queue queue, wgb_texture texture,
 /* Read-back of a texture's texels, row-major and tightly packed: what wgpu_cpu::dump_texture /
  * image::rgba_texture_image observe (lib.rs:111-173).  Waits for earlier submissions. */
 WGB_API wgb_status wgb_texture_read(wgb_texture texture, void* dst, uint64_t dst_size);
+/* wgpu_cpu::dump_texture (lib.rs:111-158): layer 0 of the texture as a PNG file.  Rgba8Unorm[Srgb] bytes as they are,
+ * Bgra8Unorm[Srgb] swizzled to RGBA, Depth32Float as 8-bit grey `(depth * 255.0) as u8`; other formats are
+ * WGB_ERROR_UNSUPPORTED (`todo!()` in the reference).  The file is a plain (stored, uncompressed) PNG. */
+WGB_API wgb_status wgb_texture_dump_png(wgb_texture texture, const char* path);
+/* the PNG writer behind it: `channels` = 1 (grey), 3 (RGB) or 4 (RGBA), 8 bits each, rows top to bottom */
+WGB_API wgb_status wgb_write_png(const char* path, const void* pixels, uint32_t width, uint32_t height, uint32_t channels);
 /* Peer-memory presenter (one process per GPU on an NVLink box): the presenting rank exports its colour target,
  * every other rank imports it and uses the imported texture as ITS colour attachment, so that its tile kernel
  * stores the finished tiles of its band straight into the presenter's memory over NVLink -- compute and the

@@ -160,3 +160,39 @@ def test_encoder_copy_validation(offline):
     enc.finish()
     with pytest.raises(api.WgpuError):
         enc.clear_buffer(buf)                                    # encoder already finished
+
+
+def _decode_png(path):
+    """Minimal PNG reader for the files the library writes (8-bit, filter 0 rows)."""
+    import struct
+    import zlib
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, hdr = 8, b"", None
+    while pos < len(raw):
+        n, typ = struct.unpack(">I4s", raw[pos:pos + 8])
+        body = raw[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(typ + body)
+        if typ == b"IHDR":
+            hdr = struct.unpack(">IIBBBBB", body)
+        elif typ == b"IDAT":
+            idat += body
+        pos += 12 + n
+    w, h, depth, ctype = hdr[:4]
+    assert depth == 8
+    ch = {0: 1, 2: 3, 6: 4}[ctype]
+    rows = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + w * ch)
+    assert not rows[:, 0].any()
+    return rows[:, 1:].reshape(h, w, ch)
+
+
+@pytest.mark.parametrize("shape", [(5, 7, 4), (300, 301, 3), (33, 2)])
+def test_png_writer_roundtrip(tmp_path, shape):
+    """wgb_write_png (behind wgb_texture_dump_png, the reference's dump_texture lib.rs:111-158): stored-deflate PNG,
+    valid CRCs and Adler-32, more than one 64 KiB block."""
+    from wgpu_cpu_b200 import api
+    px = np.random.default_rng(1).integers(0, 256, shape, dtype=np.uint8)
+    path = str(tmp_path / "t.png")
+    api.write_png(path, px)
+    got = _decode_png(path)
+    assert np.array_equal(got.reshape(px.shape), px)

@@ -144,15 +144,20 @@ def test_load_op_load(gpu):
     _compare(s, gpu)
 
 
+@pytest.mark.parametrize("scene_name", ["hello_mesh", "synthetic_clipped", "random_clipped"])
 @pytest.mark.parametrize("bands", [2, 3, 8])
-def test_sort_first_bands_reassemble_the_single_gpu_frame(gpu, bands):
+def test_sort_first_bands_reassemble_the_single_gpu_frame(gpu, bands, scene_name):
     """each band renders with the full scene and only its tile rows; per-pixel primitive order
     is preserved inside a band, so the reassembled frame is bit-identical to the oracle's."""
     from oracle import pyoracle
     from wgpu_cpu_b200 import api
     from wgpu_cpu_b200.multigpu import band_rows
     from wgpu_cpu_b200.render import render_scene
-    scene = S.hello_mesh(320, 200)
+    # synthetic_clipped: an indexed mesh whose border triangles cross the clip volume (the cached geometry kernel
+    # drops primitives -- clipped ones included -- whose vertex rows miss the band); random_clipped: non-indexed
+    scene = {"hello_mesh": lambda: S.hello_mesh(320, 200),
+             "synthetic_clipped": lambda: S.synthetic_grid(320, 200, n=60, layers=2),
+             "random_clipped": lambda: S.random_triangles(320, 200, count=300, seed=3)}[scene_name]()
     ref = pyoracle.render(scene)
     color = np.zeros_like(ref.color)
     depth = np.zeros_like(ref.depth)
@@ -166,7 +171,8 @@ def test_sort_first_bands_reassemble_the_single_gpu_frame(gpu, bands):
         depth[a:b] = got.depth[a:b]
         # rows outside the band are never touched (textures start zeroed)
         assert not got.color[:a].any() and not got.color[b:].any()
-        frags += got.stats["fragments"]
+        # every fragment is rasterised by exactly one band (counted with the hierarchical depth test off)
+        frags += render_scene(dev, queue, scene, want_coverage=True).stats["fragments"]
     assert np.array_equal(color, ref.color)
     assert np.array_equal(depth.view(np.uint32), ref.depth.view(np.uint32))
     assert frags == ref.stats["fragments_shaded"]
@@ -397,3 +403,19 @@ def test_hierarchical_depth_test_drops_hidden_triangles_without_changing_the_fra
     full = render_scene(dev, queue, scene, want_coverage=True)
     assert full.stats["hiz_culled"] == 0 and full.stats["fragments"] == ref.stats["fragments_shaded"]
     assert got.stats["fragments"] <= full.stats["fragments"]
+
+
+def test_dump_texture_png(gpu, tmp_path):
+    """dump_texture (lib.rs:111-158) of the colour target and of the depth attachment."""
+    from tests.test_c_abi import _decode_png
+    from wgpu_cpu_b200 import api
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    r = SceneRenderer(dev, queue, S.hello_mesh(96, 64))
+    r.render()
+    api.dump_texture(r.target, str(tmp_path / "color.png"))
+    assert np.array_equal(_decode_png(str(tmp_path / "color.png")), r.target.read())
+    r.depth_texture.dump_png(str(tmp_path / "depth.png"))
+    d = r.depth_texture.read()
+    want = np.clip(np.trunc(d * np.float32(255.0)), 0, 255).astype(np.uint8)
+    assert np.array_equal(_decode_png(str(tmp_path / "depth.png"))[:, :, 0], want)

@@ -269,6 +269,10 @@ class Texture(_Handle):
             return out.view(np.float32).reshape(self.layers, self.height, self.width)[0]
         return out[0]
 
+    def dump_png(self, path: str):
+        """wgpu_cpu::dump_texture (lib.rs:111-158)."""
+        _check(_lib.wgb_texture_dump_png(self._h, os.fsencode(path)))
+
     def export_ipc(self) -> bytes:
         """cudaIpcMemHandle_t of the texel storage (peer-memory presenter, see wgpu_b200.h)."""
         h = (C.c_uint8 * 64)()
@@ -660,3 +664,17 @@ def translate_wgsl(wgsl: str, stage: int, entry_point: str) -> str:
     s = C.string_at(p).decode()
     lib.wgb_free(p)
     return s
+
+
+def dump_texture(texture: Texture, path: str):
+    """`wgpu_cpu::dump_texture(&texture, path, None)` (lib.rs:111-158): what the reference's examples and tests call to
+    look at a render target."""
+    texture.dump_png(path)
+
+
+def write_png(path: str, pixels: np.ndarray):
+    """The library's PNG writer on a host array of shape (h, w), (h, w, 3) or (h, w, 4), uint8."""
+    a = np.ascontiguousarray(pixels, dtype=np.uint8)
+    ch = 1 if a.ndim == 2 else a.shape[2]
+    load_library()
+    _check(_lib.wgb_write_png(os.fsencode(path), a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], ch))

@@ -1032,6 +1032,67 @@ void check_buffer_rect(const Buffer* b, uint64_t offset, uint32_t bytes_per_row,
     REQUIRE(h == 0 || offset + (uint64_t)(h - 1) * pitch + row <= b->size, "%s: buffer range out of bounds", what);
 }
 
+
+// ---- PNG (stored deflate blocks: no compression library in the dependency list) ----
+uint32_t crc32_update(uint32_t crc, const uint8_t* p, size_t n) {
+    static uint32_t table[256];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+    });
+    for (size_t i = 0; i < n; i++) crc = table[(crc ^ p[i]) & 0xFF] ^ (crc >> 8);
+    return crc;
+}
+void png_chunk(FILE* f, const char type[4], const std::vector<uint8_t>& data) {
+    uint8_t len[4] = {(uint8_t)(data.size() >> 24), (uint8_t)(data.size() >> 16), (uint8_t)(data.size() >> 8), (uint8_t)data.size()};
+    uint32_t crc = crc32_update(0xFFFFFFFFu, reinterpret_cast<const uint8_t*>(type), 4);
+    crc = crc32_update(crc, data.data(), data.size()) ^ 0xFFFFFFFFu;
+    uint8_t c[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+    if (fwrite(len, 1, 4, f) != 4 || fwrite(type, 1, 4, f) != 4 || (data.size() && fwrite(data.data(), 1, data.size(), f) != data.size()) ||
+        fwrite(c, 1, 4, f) != 4)
+        fail(WGB_ERROR_DEVICE, "short write while saving a PNG");
+}
+void write_png(const char* path, const uint8_t* px, uint32_t w, uint32_t h, uint32_t channels) {
+    REQUIRE(path && px, "null argument");
+    REQUIRE(w > 0 && h > 0 && (channels == 1 || channels == 3 || channels == 4), "unsupported PNG layout");
+    const size_t row = (size_t)w * channels;
+    std::vector<uint8_t> raw;                     // filter byte 0 + pixels, per row
+    raw.reserve((row + 1) * h);
+    for (uint32_t y = 0; y < h; y++) { raw.push_back(0); raw.insert(raw.end(), px + y * row, px + (y + 1) * row); }
+    std::vector<uint8_t> z;                        // zlib stream of stored blocks
+    z.reserve(raw.size() + raw.size() / 65535 * 5 + 16);
+    z.push_back(0x78); z.push_back(0x01);
+    uint32_t a = 1, b = 0;                         // Adler-32
+    for (size_t off = 0; off < raw.size();) {
+        const size_t n = std::min<size_t>(65535, raw.size() - off);
+        z.push_back(off + n == raw.size() ? 1 : 0);
+        z.push_back((uint8_t)n); z.push_back((uint8_t)(n >> 8)); z.push_back((uint8_t)~n); z.push_back((uint8_t)(~n >> 8));
+        z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+        for (size_t i = 0; i < n; i += 5552) {
+            const size_t m = std::min<size_t>(5552, n - i);
+            for (size_t k = 0; k < m; k++) { a += raw[off + i + k]; b += a; }
+            a %= 65521; b %= 65521;
+        }
+        off += n;
+    }
+    const uint32_t adler = (b << 16) | a;
+    z.push_back((uint8_t)(adler >> 24)); z.push_back((uint8_t)(adler >> 16)); z.push_back((uint8_t)(adler >> 8)); z.push_back((uint8_t)adler);
+    FILE* f = fopen(path, "wb");
+    if (!f) fail(WGB_ERROR_VALIDATION, "cannot open %s for writing", path);
+    struct Close { FILE* f; ~Close() { fclose(f); } } closer{f};
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    if (fwrite(sig, 1, 8, f) != 8) fail(WGB_ERROR_DEVICE, "short write while saving a PNG");
+    std::vector<uint8_t> ihdr = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w,
+                                 (uint8_t)(h >> 24), (uint8_t)(h >> 16), (uint8_t)(h >> 8), (uint8_t)h,
+                                 8, (uint8_t)(channels == 1 ? 0 : channels == 3 ? 2 : 6), 0, 0, 0};
+    png_chunk(f, "IHDR", ihdr);
+    png_chunk(f, "IDAT", z);
+    png_chunk(f, "IEND", {});
+}
 }  // namespace
 
 // ==========================================================================================
@@ -1348,6 +1409,46 @@ wgb_status wgb_texture_read(wgb_texture texture, void* dst, uint64_t dst_size) {
         dev->make_current();
         CUDA_CHECK(cudaMemcpyAsync(dst, t->dptr, t->size, cudaMemcpyDeviceToHost, dev->stream));
         CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+    });
+}
+wgb_status wgb_write_png(const char* path, const void* pixels, uint32_t width, uint32_t height, uint32_t channels) {
+    return guarded([&] { write_png(path, static_cast<const uint8_t*>(pixels), width, height, channels); });
+}
+wgb_status wgb_texture_dump_png(wgb_texture texture, const char* path) {
+    return guarded([&] {
+        Texture* t = from_handle<Texture>(texture, "texture");
+        REQUIRE(path, "path is null");
+        Device* dev = t->device.get();
+        if (dev->compile_only) fail(WGB_ERROR_DEVICE, "a compile-only device has no texture storage");
+        const uint32_t w = t->desc.width, h = t->desc.height;
+        std::vector<uint8_t> texels((size_t)w * h * t->bpp);
+        {
+            std::lock_guard<std::recursive_mutex> dl(dev->mu);
+            dev->make_current();
+            CUDA_CHECK(cudaMemcpyAsync(texels.data(), t->dptr, texels.size(), cudaMemcpyDeviceToHost, dev->stream));
+            CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+        }
+        switch (t->desc.format) {                                                       // lib.rs:124-154
+            case WGB_TEXTURE_FORMAT_RGBA8_UNORM: case WGB_TEXTURE_FORMAT_RGBA8_UNORM_SRGB:
+                write_png(path, texels.data(), w, h, 4);
+                break;
+            case WGB_TEXTURE_FORMAT_BGRA8_UNORM: case WGB_TEXTURE_FORMAT_BGRA8_UNORM_SRGB:
+                for (size_t i = 0; i < texels.size(); i += 4) std::swap(texels[i], texels[i + 2]);
+                write_png(path, texels.data(), w, h, 4);
+                break;
+            case WGB_TEXTURE_FORMAT_DEPTH32_FLOAT: {
+                std::vector<uint8_t> grey((size_t)w * h);
+                for (size_t i = 0; i < grey.size(); i++) {
+                    float d;
+                    memcpy(&d, texels.data() + i * 4, 4);
+                    const float v = d * 255.0f;                                         // `as u8`: saturating, NaN -> 0
+                    grey[i] = !(v == v) ? 0 : v <= 0.0f ? 0 : v >= 255.0f ? 255 : (uint8_t)v;
+                }
+                write_png(path, grey.data(), w, h, 1);
+                break;
+            }
+            default: fail(WGB_ERROR_UNSUPPORTED, "output texture format not implemented: %u (lib.rs:155)", t->desc.format);
+        }
     });
 }
 wgb_status wgb_texture_export_ipc(wgb_texture texture, uint8_t handle[WGB_IPC_HANDLE_SIZE]) {

@@ -88,6 +88,7 @@ struct WgbCounters {             // 64 bytes
 #define WGB_VFLAG_INSIDE 1u              // inside all six clip planes
 #define WGB_VFLAG_W_ZERO 2u              // clip.w == 0 (the reference panics when such a vertex is used)
 #define WGB_VFLAG_ROW_SHIFT 2            // bits 2..17: the vertex's framebuffer row, min(trunc(vp.y), 65535)
+#define WGB_VFLAG_W_POS (1u << 18)       // clip.w > 0: clipping keeps the primitive inside the row range of its vertices
 
 // one record per primitive emitted by the clipper (slow path only)
 struct WgbClipRecord {          // 100 bytes
