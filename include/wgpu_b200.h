@@ -119,7 +119,19 @@ typedef struct {
     int32_t cuda_device;     /* CUDA ordinal; -1 = the calling thread's current device */
     uint32_t band_rank;      /* this device renders tile-row band `band_rank` ... */
     uint32_t band_count;     /* ... of `band_count` contiguous bands (0 or 1 = whole framebuffer) */
+    uint32_t features;       /* WGB_FEATURE_* bits: behaviour beyond the reference, off by default (wgpu's required_features) */
 } wgb_device_descriptor;
+/* Pipeline features that the reference accepts and ignores.  With none requested the backend is
+ * in parity mode: results are the reference's, bit for bit.  Each bit switches one WebGPU behaviour on. */
+#define WGB_FEATURE_VIEWPORT_DEPTH_RANGE 1u  /* fragment depth = min_depth + ndc.z * (max_depth - min_depth); the reference keeps ndc.z (raster.rs:141-158) */
+#define WGB_FEATURE_COLOR_WRITE_MASK 2u      /* wgb_color_target_state.write_mask is applied (ignored by the reference, fragment.rs:480-485) */
+#define WGB_FEATURE_SRGB_ENCODE 4u           /* *Srgb colour targets store sRGB-encoded values (the reference stores them linearly, texture.rs:393-400) */
+#define WGB_FEATURE_DYNAMIC_OFFSETS 8u       /* set_bind_group dynamic offsets move buffer bindings (stored and ignored by the reference, state.rs:194-205) */
+#define WGB_COLOR_WRITE_RED 1u
+#define WGB_COLOR_WRITE_GREEN 2u
+#define WGB_COLOR_WRITE_BLUE 4u
+#define WGB_COLOR_WRITE_ALPHA 8u
+#define WGB_COLOR_WRITE_ALL 15u
 WGB_API wgb_status wgb_adapter_request_device(wgb_adapter adapter, const wgb_device_descriptor* desc,
                                               wgb_device* out_device, wgb_queue* out_queue);
 /* DeviceInterface::poll (device.rs:237-295): wait != 0 blocks until `submission_index` (or, for
@@ -207,7 +219,7 @@ WGB_API void wgb_free(void* p);
 
 /* ---- binding model ---- */
 /* DeviceInterface::create_bind_group_layout / create_pipeline_layout (device.rs:102-127): descriptors are kept, not interpreted */
-typedef struct { uint32_t binding; uint32_t visibility; uint32_t kind; } wgb_bind_group_layout_entry;
+typedef struct { uint32_t binding; uint32_t visibility; uint32_t kind; uint32_t has_dynamic_offset; } wgb_bind_group_layout_entry;
 WGB_API wgb_status wgb_device_create_bind_group_layout(wgb_device device, const wgb_bind_group_layout_entry* entries,
                                                        uint32_t count, wgb_bind_group_layout* out);
 WGB_API wgb_status wgb_device_create_pipeline_layout(wgb_device device, const wgb_bind_group_layout* layouts,

@@ -306,7 +306,10 @@ struct Bresenham {
 struct ToRaster {
     float tx, ty, sx, sy;
     uint32_t sc0x, sc0y, sc1x, sc1y;
+    bool depth_range; float depth_min, depth_scale;     /* ORC_EXT_VIEWPORT_DEPTH_RANGE (not in the reference) */
     explicit ToRaster(const orc_raster_state& rs) {
+        depth_range = (rs.ext_features & ORC_EXT_VIEWPORT_DEPTH_RANGE) != 0;
+        depth_min = rs.vp_min_depth; depth_scale = rs.vp_max_depth - rs.vp_min_depth;
         tx = rs.vp_x + 0.5f * rs.vp_w;                /* :131 */
         ty = rs.vp_y + 0.5f * rs.vp_h;
         sx = 0.5f * rs.vp_w;                          /* :132-133 */
@@ -319,7 +322,9 @@ struct ToRaster {
     bool to_raster(Vec4 clip, uint32_t fb[2], Vec4& frag) const {
         if (clip.w == 0.0f) return false;
         /* Point3::from_homogeneous: coords / w, a true division per component */
-        const float nx = clip.x / clip.w, ny = clip.y / clip.w, nz = clip.z / clip.w;
+        const float nx = clip.x / clip.w, ny = clip.y / clip.w;
+        float nz = clip.z / clip.w;
+        if (depth_range) nz = depth_min + nz * depth_scale;
         const float pd = 1.0f / clip.w;
         float vx = nx * sx + tx;
         float vy = ny * sy + ty;
@@ -355,8 +360,15 @@ static inline uint8_t f32_to_u8(float value) {         /* texture.rs:376-379 */
     if (v > 255.0f) v = 255.0f;
     return (uint8_t)v;
 }
+static inline float srgb_oetf(float v) {                /* ORC_EXT_SRGB_ENCODE (not in the reference) */
+    if (!(v > 0.0031308f)) return v * 12.92f;
+    return 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+}
 /* TexelWriter::from_color (texture.rs:373-411); returns texel size or 0 if the format panics */
-static int encode_color(Vec4 c, uint32_t format, uint8_t out[4]) {
+static int encode_color(Vec4 c, uint32_t format, uint8_t out[4], bool srgb_encode = false) {
+    if (srgb_encode && (format == ORC_FMT_RGBA8_UNORM_SRGB || format == ORC_FMT_BGRA8_UNORM_SRGB)) {
+        c.x = srgb_oetf(c.x); c.y = srgb_oetf(c.y); c.z = srgb_oetf(c.z);
+    }
     switch (format) {
         case ORC_FMT_R8_UNORM: out[0] = f32_to_u8(c.x); return 1;
         case ORC_FMT_RG8_UNORM: out[0] = f32_to_u8(c.x); out[1] = f32_to_u8(c.y); return 2;
@@ -457,6 +469,7 @@ struct DrawCtx {
     uint32_t* coverage;
     int err;
     int color_bpp[ORC_MAX_COLOR];
+    const orc_raster_state* rs;
 };
 
 /* vertex.rs:286-316 VertexProcessingState::process + VertexInput::write_into (:128-156) */
@@ -574,9 +587,18 @@ static void process_fragment(DrawCtx& cx, int n, const VertexOut* const* unclipp
             if (loc >= cx.pass->num_color) { cx.err = ORC_ERR_INVALID; return; }
             const orc_texture& t = cx.pass->color[loc];
             uint8_t texel[4];
-            const int bpp = encode_color(out.color[k], t.format, texel);
+            const int bpp = encode_color(out.color[k], t.format, texel, (cx.rs->ext_features & ORC_EXT_SRGB_ENCODE) != 0);
             if (bpp == 0) { cx.err = ORC_ERR_UNSUPPORTED; return; }
-            std::memcpy(t.data + texel_offset(t, fx, fy, bpp), texel, bpp);   /* put_pixel texture.rs:213-218 */
+            uint8_t* dst = t.data + texel_offset(t, fx, fy, bpp);
+            if (cx.rs->ext_features & ORC_EXT_COLOR_WRITE_MASK) {             /* not in the reference: channels outside the mask keep their value */
+                const uint32_t m = cx.rs->color_write_mask[loc];
+                const bool bgra = t.format == ORC_FMT_BGRA8_UNORM || t.format == ORC_FMT_BGRA8_UNORM_SRGB;
+                for (int ch = 0; ch < bpp; ch++) {
+                    const int bit = (bgra && ch == 0) ? 2 : (bgra && ch == 2) ? 0 : ch;    /* stored byte -> R G B A */
+                    if (!((m >> bit) & 1u)) texel[ch] = dst[ch];
+                }
+            }
+            std::memcpy(dst, texel, bpp);                                     /* put_pixel texture.rs:213-218 */
             wrote = true;
         }
     }
@@ -793,7 +815,7 @@ int orc_pass_load(const orc_pass* pass) {
         Vec4 col = {(float)pass->clear_color[c][0], (float)pass->clear_color[c][1],
                     (float)pass->clear_color[c][2], (float)pass->clear_color[c][3]};
         uint8_t texel[4];
-        const int bpp = encode_color(col, t.format, texel);
+        const int bpp = encode_color(col, t.format, texel, (pass->ext_features & ORC_EXT_SRGB_ENCODE) != 0);
         if (bpp == 0) return ORC_ERR_UNSUPPORTED;
         const uint64_t n = (uint64_t)t.width * t.height;
         for (uint64_t i = 0; i < n; i++) std::memcpy(t.data + i * bpp, texel, bpp);
@@ -813,6 +835,8 @@ void orc_default_raster_state(uint32_t width, uint32_t height, orc_raster_state*
     out->vp_w = (float)width; out->vp_h = (float)height;
     out->vp_min_depth = 0.0f; out->vp_max_depth = 1.0f;
     out->sc_x = 0; out->sc_y = 0; out->sc_w = width; out->sc_h = height;
+    out->ext_features = 0;
+    for (int c = 0; c < ORC_MAX_COLOR; c++) out->color_write_mask[c] = 15u;
 }
 
 int orc_draw_execute(const orc_pass* pass, const orc_pipeline* pipe, const orc_raster_state* rs,
@@ -832,7 +856,7 @@ int orc_draw_execute(const orc_pass* pass, const orc_pipeline* pipe, const orc_r
     if (coverage && pass->num_color == 0) return ORC_ERR_INVALID;
     orc_stats local;
     std::memset(&local, 0, sizeof(local));
-    DrawCtx cx{pass, pipe, draw, sh, Resources{bindings}, ToRaster(*rs), stats ? stats : &local, coverage, 0, {0, 0, 0, 0}};
+    DrawCtx cx{pass, pipe, draw, sh, Resources{bindings}, ToRaster(*rs), stats ? stats : &local, coverage, 0, {0, 0, 0, 0}, rs};
     const int e = draw_execute(cx);
     return e ? e : cx.err;
 }

@@ -98,12 +98,21 @@ typedef struct {
     orc_texture depth;
     uint32_t depth_clear;
     float clear_depth;
+    uint32_t ext_features;                    /* ORC_EXT_SRGB_ENCODE applies to the clear colour too */
 } orc_pass;
 
 typedef struct {
     float vp_x, vp_y, vp_w, vp_h, vp_min_depth, vp_max_depth;
     uint32_t sc_x, sc_y, sc_w, sc_h;
+    /* Behaviour BEYOND the reference (it accepts and ignores these states): the product's opt-in WGB_FEATURE_* bits,
+     * restated from the WebGPU specification -- there is nothing in the reference to pin them against.  0 = the
+     * reference's behaviour. */
+    uint32_t ext_features;
+    uint32_t color_write_mask[ORC_MAX_COLOR]; /* ORC_EXT_COLOR_WRITE_MASK: R=1 G=2 B=4 A=8 */
 } orc_raster_state;
+#define ORC_EXT_VIEWPORT_DEPTH_RANGE 1u   /* fragment depth = min_depth + ndc.z * (max_depth - min_depth) */
+#define ORC_EXT_COLOR_WRITE_MASK 2u
+#define ORC_EXT_SRGB_ENCODE 4u            /* *Srgb targets store the sRGB-encoded value */
 
 typedef struct {
     uint32_t indexed;

@@ -71,13 +71,14 @@ class Pipeline(C.Structure):
 class Pass(C.Structure):
     _fields_ = [("num_color", C.c_uint32), ("color", Texture * MAX_COLOR), ("color_clear", C.c_uint32 * MAX_COLOR),
                 ("clear_color", (C.c_double * 4) * MAX_COLOR), ("has_depth", C.c_uint32), ("depth", Texture),
-                ("depth_clear", C.c_uint32), ("clear_depth", C.c_float)]
+                ("depth_clear", C.c_uint32), ("clear_depth", C.c_float), ("ext_features", C.c_uint32)]
 
 
 class RasterState(C.Structure):
     _fields_ = [("vp_x", C.c_float), ("vp_y", C.c_float), ("vp_w", C.c_float), ("vp_h", C.c_float),
                 ("vp_min_depth", C.c_float), ("vp_max_depth", C.c_float),
-                ("sc_x", C.c_uint32), ("sc_y", C.c_uint32), ("sc_w", C.c_uint32), ("sc_h", C.c_uint32)]
+                ("sc_x", C.c_uint32), ("sc_y", C.c_uint32), ("sc_w", C.c_uint32), ("sc_h", C.c_uint32),
+                ("ext_features", C.c_uint32), ("color_write_mask", C.c_uint32 * MAX_COLOR)]
 
 
 class DrawDesc(C.Structure):
@@ -153,6 +154,7 @@ def render(scene, want_coverage: bool = True) -> Frame:
     if scene.clear_color is not None:
         for k in range(4):
             p.clear_color[0][k] = float(scene.clear_color[k])
+    p.ext_features = getattr(scene, "features", 0) & 7
     p.has_depth = 1 if scene.has_depth else 0
     if scene.has_depth:
         p.depth = Texture(_ptr(depth), W, H, FORMAT["depth32float"])
@@ -184,12 +186,20 @@ def render(scene, want_coverage: bool = True) -> Frame:
         rs.vp_x, rs.vp_y, rs.vp_w, rs.vp_h, rs.vp_min_depth, rs.vp_max_depth = scene.viewport
     if scene.scissor is not None:
         rs.sc_x, rs.sc_y, rs.sc_w, rs.sc_h = scene.scissor
+    rs.ext_features = getattr(scene, "features", 0) & 7        # depth range, write mask, sRGB encode (oracle.h ORC_EXT_*)
+    rs.color_write_mask[0] = getattr(scene, "color_write_mask", 15)
+    dyn = {}
+    if getattr(scene, "features", 0) & 8 and scene.dynamic_offsets:       # dynamic offsets: the k-th offset moves the k-th dynamic binding
+        for g, offs in scene.dynamic_offsets.items():
+            for b, off in zip(sorted(scene.dynamic_bindings[g]), offs):
+                dyn[(g, b)] = off
 
     binds = Bindings()
     for (g, b), res in scene.bindings.items():
         e = binds.b[g][b]
         if res[0] == "buffer":
             arr = np.ascontiguousarray(res[1]).view(np.uint8).reshape(-1)
+            arr = arr[dyn.get((g, b), 0):]
             keep.append(arr)
             e.kind = 1
             e.buffer = Buffer(_ptr(arr), arr.nbytes)

@@ -196,3 +196,11 @@ def test_png_writer_roundtrip(tmp_path, shape):
     api.write_png(path, px)
     got = _decode_png(path)
     assert np.array_equal(got.reshape(px.shape), px)
+
+
+def test_unknown_feature_bits_are_rejected():
+    adapter = api.instance().request_adapter()
+    with pytest.raises(api.WgpuError):
+        adapter.request_device(api.CUDA_DEVICE_COMPILE_ONLY, features=1 << 20)
+    dev, _ = adapter.request_device(api.CUDA_DEVICE_COMPILE_ONLY, features=sum(api.FEATURE.values()))
+    assert dev is not None

@@ -52,7 +52,11 @@ class WgpuError(RuntimeError):
 
 # ---- ctypes mirrors of the descriptor structs ----
 class _DeviceDescriptor(C.Structure):
-    _fields_ = [("cuda_device", C.c_int32), ("band_rank", C.c_uint32), ("band_count", C.c_uint32)]
+    _fields_ = [("cuda_device", C.c_int32), ("band_rank", C.c_uint32), ("band_count", C.c_uint32), ("features", C.c_uint32)]
+
+
+FEATURE = {"VIEWPORT_DEPTH_RANGE": 1, "COLOR_WRITE_MASK": 2, "SRGB_ENCODE": 4, "DYNAMIC_OFFSETS": 8}
+COLOR_WRITE = {"RED": 1, "GREEN": 2, "BLUE": 4, "ALPHA": 8, "ALL": 15}
 
 
 class _AdapterInfo(C.Structure):
@@ -83,7 +87,7 @@ class _ShaderModuleDescriptor(C.Structure):
 
 
 class _BindGroupLayoutEntry(C.Structure):
-    _fields_ = [("binding", C.c_uint32), ("visibility", C.c_uint32), ("kind", C.c_uint32)]
+    _fields_ = [("binding", C.c_uint32), ("visibility", C.c_uint32), ("kind", C.c_uint32), ("has_dynamic_offset", C.c_uint32)]
 
 
 class _BindGroupEntry(C.Structure):
@@ -207,8 +211,9 @@ class Adapter(_Handle):
         _check(_lib.wgb_adapter_get_info(self._h, C.byref(info)))
         return {"name": info.name.decode(), "device_type": info.device_type, "cuda_device_count": info.cuda_device_count}
 
-    def request_device(self, cuda_device: int = CUDA_DEVICE_CURRENT, band_rank: int = 0, band_count: int = 1):
-        desc = _DeviceDescriptor(cuda_device, band_rank, band_count)
+    def request_device(self, cuda_device: int = CUDA_DEVICE_CURRENT, band_rank: int = 0, band_count: int = 1, features: int = 0):
+        """`features`: FEATURE[...] bits -- WebGPU behaviour the reference accepts and ignores; 0 = parity mode."""
+        desc = _DeviceDescriptor(cuda_device, band_rank, band_count, features)
         d, q = C.c_void_p(), C.c_void_p()
         _check(_lib.wgb_adapter_request_device(self._h, C.byref(desc), C.byref(d), C.byref(q)))
         dev = Device(d)
@@ -329,7 +334,9 @@ class RenderPass(_Handle):
         _check(_lib.wgb_render_pass_set_pipeline(self._h, pipeline._h))
 
     def set_bind_group(self, index: int, bind_group: Optional[BindGroup], offsets: Sequence[int] = ()):
-        _check(_lib.wgb_render_pass_set_bind_group(self._h, index, bind_group._h if bind_group else None, None, 0))
+        n = len(offsets)
+        arr = (C.c_uint32 * max(n, 1))(*offsets)
+        _check(_lib.wgb_render_pass_set_bind_group(self._h, index, bind_group._h if bind_group else None, arr if n else None, n))
 
     def set_index_buffer(self, buffer: Buffer, index_format: str, offset=0, size=WHOLE_SIZE):
         _check(_lib.wgb_render_pass_set_index_buffer(self._h, buffer._h, INDEX_FORMAT[index_format], C.c_uint64(offset), C.c_uint64(size)))

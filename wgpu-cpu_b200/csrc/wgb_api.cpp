@@ -234,9 +234,26 @@ uint32_t f32_to_u8(float v) {
     if (s > 255.0f) s = 255.0f;
     return (uint32_t)s;
 }
-uint32_t encode_color(const double c[4], uint32_t format) {
+bool is_srgb_format(uint32_t f) { return f == WGB_TEXTURE_FORMAT_RGBA8_UNORM_SRGB || f == WGB_TEXTURE_FORMAT_BGRA8_UNORM_SRGB; }
+float srgb_oetf(float v) {      // same operation sequence as wgb_srgb_oetf on the device
+    if (!(v > 0.0031308f)) return v * 12.92f;
+    return 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+}
+// colour write mask (WGB_COLOR_WRITE_* bits) -> byte mask over the stored texel
+uint32_t texel_write_mask(uint32_t mask, uint32_t format) {
+    const bool bgra = format == WGB_TEXTURE_FORMAT_BGRA8_UNORM || format == WGB_TEXTURE_FORMAT_BGRA8_UNORM_SRGB;
+    uint32_t m = 0;
+    if (mask & WGB_COLOR_WRITE_RED) m |= bgra ? 0x00FF0000u : 0x000000FFu;
+    if (mask & WGB_COLOR_WRITE_GREEN) m |= 0x0000FF00u;
+    if (mask & WGB_COLOR_WRITE_BLUE) m |= bgra ? 0x000000FFu : 0x00FF0000u;
+    if (mask & WGB_COLOR_WRITE_ALPHA) m |= 0xFF000000u;
+    return m;
+}
+uint32_t encode_color(const double c[4], uint32_t format, bool srgb_encode = false) {
     // wgpu_color_to_vec4 casts the f64 colour to f32 first (texture.rs:505-507)
-    const uint32_t r = f32_to_u8((float)c[0]), g = f32_to_u8((float)c[1]), b = f32_to_u8((float)c[2]), a = f32_to_u8((float)c[3]);
+    float v[4] = {(float)c[0], (float)c[1], (float)c[2], (float)c[3]};
+    if (srgb_encode) for (int i = 0; i < 3; i++) v[i] = srgb_oetf(v[i]);
+    const uint32_t r = f32_to_u8(v[0]), g = f32_to_u8(v[1]), b = f32_to_u8(v[2]), a = f32_to_u8(v[3]);
     if (format == WGB_TEXTURE_FORMAT_BGRA8_UNORM || format == WGB_TEXTURE_FORMAT_BGRA8_UNORM_SRGB)
         return b | (g << 8) | (r << 16) | (a << 24);
     return r | (g << 8) | (b << 16) | (a << 24);
@@ -285,6 +302,7 @@ struct Device : Object {
     cudaStream_t copy_stream = nullptr;    // large host->device uploads (wgb_queue_write_buffer from pinned memory)
     std::recursive_mutex mu;
     uint32_t band_rank = 0, band_count = 1;
+    uint32_t features = 0;                  // WGB_FEATURE_* (opt-in behaviour beyond the reference)
     // submissions (device.rs:436-462, 517-541)
     uint64_t next_submission = 1;
     struct InFlight { uint64_t index; cudaEvent_t done; };
@@ -409,6 +427,7 @@ struct ShaderModule : Object {
 struct BindGroupLayout : Object { std::vector<wgb_bind_group_layout_entry> entries; };
 struct PipelineLayout : Object { std::vector<Ref<BindGroupLayout>> layouts; };
 struct BindGroup : Object {
+    Ref<BindGroupLayout> layout;       // names the bindings that take a dynamic offset
     struct Entry {
         uint32_t binding, kind;
         Ref<Buffer> buffer; uint64_t offset = 0, size = 0;
@@ -547,6 +566,7 @@ struct SubCommand {
     uint32_t sc[4] = {0, 0, 0, 0};
     uint32_t first = 0, count = 0, first_instance = 0, instance_count = 0;
     int32_t base_vertex = 0;
+    std::vector<uint32_t> dynamic_offsets;
 };
 struct PassCommand {
     struct Color { Ref<TextureView> view; uint32_t load_op, store_op; double clear[4]; };
@@ -593,6 +613,7 @@ struct RenderPass : Object {
 struct PassState {   // render_pass/state.rs:58-75
     Ref<RenderPipeline> pipeline;
     Ref<BindGroup> bind_groups[WGB_MAX_GROUPS];
+    std::vector<uint32_t> dynamic_offsets[WGB_MAX_GROUPS];
     struct Slice { Ref<Buffer> buffer; uint64_t offset = 0, size = 0; };
     Slice vertex_buffers[WGB_MAX_VERTEX_BUFFERS];
     Slice index_buffer;
@@ -686,14 +707,25 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
     for (uint32_t g = 0; g < WGB_MAX_GROUPS; g++) {                                     // binding.rs:22-52
         BindGroup* bg = st.bind_groups[g].get();
         if (!bg) continue;
+        // WGB_FEATURE_DYNAMIC_OFFSETS: the k-th offset belongs to the k-th dynamic binding in increasing binding number
+        std::map<uint32_t, uint64_t> dyn;
+        if ((dev->features & WGB_FEATURE_DYNAMIC_OFFSETS) && bg->layout) {
+            std::vector<uint32_t> dynamic_bindings;
+            for (const auto& le : bg->layout->entries) if (le.has_dynamic_offset) dynamic_bindings.push_back(le.binding);
+            std::sort(dynamic_bindings.begin(), dynamic_bindings.end());
+            REQUIRE(dynamic_bindings.size() == st.dynamic_offsets[g].size(), "bind group %u takes %zu dynamic offsets, %zu were given",
+                    g, dynamic_bindings.size(), st.dynamic_offsets[g].size());
+            for (size_t k = 0; k < dynamic_bindings.size(); k++) dyn[dynamic_bindings[k]] = st.dynamic_offsets[g][k];
+        }
         for (const auto& e : bg->entries) {
             if (e.binding >= WGB_MAX_BINDINGS) fail(WGB_ERROR_UNSUPPORTED, "binding index %u exceeds the supported %d", e.binding, WGB_MAX_BINDINGS);
             WgbResource& r = d.res[g][e.binding];
             r.kind = e.kind;
             if (e.kind == WGB_BINDING_BUFFER) {
-                REQUIRE(e.offset <= e.buffer->size, "bind group buffer offset out of range");
-                r.ptr = (uint64_t)(uintptr_t)e.buffer->dptr + e.offset;
-                r.a = (uint32_t)std::min<uint64_t>(e.size, e.buffer->size - e.offset);
+                const uint64_t off = e.offset + (dyn.count(e.binding) ? dyn[e.binding] : 0);
+                REQUIRE(off <= e.buffer->size, "bind group buffer offset out of range");
+                r.ptr = (uint64_t)(uintptr_t)e.buffer->dptr + off;
+                r.a = (uint32_t)std::min<uint64_t>(e.size, e.buffer->size - off);
             } else if (e.kind == WGB_BINDING_TEXTURE_VIEW) {
                 Texture* t = e.view->texture.get();
                 if (t->desc.format != WGB_TEXTURE_FORMAT_RGBA8_UNORM && t->desc.format != WGB_TEXTURE_FORMAT_RGBA8_UNORM_SRGB)
@@ -725,8 +757,14 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
     }
     d.num_color = tg.num_color;
     d.has_depth = tg.has_depth ? 1u : 0u;
-    for (uint32_t c = 0; c < tg.num_color; c++) d.color[c] = tg.color[c];
+    for (uint32_t c = 0; c < tg.num_color; c++) {
+        d.color[c] = tg.color[c];
+        if (dev->features & WGB_FEATURE_COLOR_WRITE_MASK) d.color[c].write_mask = texel_write_mask(pipe->targets[c].write_mask, tg.color[c].format);
+    }
     if (tg.has_depth) d.depth = tg.depth;
+    if (dev->features & WGB_FEATURE_VIEWPORT_DEPTH_RANGE) {
+        d.depth_range = 1u; d.depth_min = st.vp[4]; d.depth_scale = st.vp[5] - st.vp[4];
+    }
     d.stats = dev->coverage_capture ? 1u : 0u;
 
     const uint32_t band_tiles = d.tiles_x * (d.band_ty1 - d.band_ty0);
@@ -881,7 +919,9 @@ void execute_pass(Device* dev, const PassCommand& pass) {
         a.format = t->desc.format;
         a.bytes_per_texel = t->bpp;
         a.load_clear = c.load_op == WGB_LOAD_OP_CLEAR ? 1u : 0u;
-        a.clear_texel = encode_color(c.clear, t->desc.format);
+        a.srgb_encode = ((dev->features & WGB_FEATURE_SRGB_ENCODE) && is_srgb_format(t->desc.format)) ? 1u : 0u;
+        a.write_mask = 0xFFFFFFFFu;
+        a.clear_texel = encode_color(c.clear, t->desc.format, a.srgb_encode != 0);
     }
     if (pass.has_depth) {
         Texture* t = pass.depth_view->texture.get();
@@ -912,6 +952,7 @@ void execute_pass(Device* dev, const PassCommand& pass) {
             case SubCommand::SetBindGroup:
                 if (sc.index >= WGB_MAX_GROUPS) fail(WGB_ERROR_UNSUPPORTED, "bind group index %u", sc.index);
                 st.bind_groups[sc.index] = sc.bind_group;          // dynamic offsets are stored then ignored (state.rs:194-205)
+                st.dynamic_offsets[sc.index] = sc.dynamic_offsets;  // ... unless WGB_FEATURE_DYNAMIC_OFFSETS was requested
                 break;
             case SubCommand::SetIndexBuffer:
                 st.index_buffer.buffer = sc.buffer; st.index_buffer.offset = sc.offset; st.index_buffer.size = sc.size;
@@ -1175,6 +1216,9 @@ wgb_status wgb_adapter_request_device(wgb_adapter adapter, const wgb_device_desc
         }
         dev->band_rank = dd.band_rank;
         dev->band_count = dd.band_count ? dd.band_count : 1;
+        const uint32_t known = WGB_FEATURE_VIEWPORT_DEPTH_RANGE | WGB_FEATURE_COLOR_WRITE_MASK | WGB_FEATURE_SRGB_ENCODE | WGB_FEATURE_DYNAMIC_OFFSETS;
+        if (dd.features & ~known) fail(WGB_ERROR_UNSUPPORTED, "unknown device feature bits 0x%x", dd.features & ~known);
+        dev->features = dd.features;
         REQUIRE(dev->band_rank < dev->band_count, "band_rank %u >= band_count %u", dev->band_rank, dev->band_count);
         Queue* q = new Queue();
         q->device = dev;
@@ -1558,6 +1602,7 @@ wgb_status wgb_device_create_bind_group(wgb_device device, wgb_bind_group_layout
         if (layout) from_handle<BindGroupLayout>(layout, "bind group layout");
         REQUIRE(out && (entries || count == 0), "null argument");
         std::unique_ptr<BindGroup> g(new BindGroup());
+        if (layout) g->layout = Ref<BindGroupLayout>(from_handle<BindGroupLayout>(layout, "bind group layout"));
         for (uint32_t i = 0; i < count; i++) {
             BindGroup::Entry e;
             e.binding = entries[i].binding;
@@ -1687,11 +1732,13 @@ wgb_status wgb_render_pass_set_pipeline(wgb_render_pass pass, wgb_render_pipelin
         record(pass, SubCommand::SetPipeline).pipeline = Ref<RenderPipeline>(rp);
     });
 }
-wgb_status wgb_render_pass_set_bind_group(wgb_render_pass pass, uint32_t index, wgb_bind_group group, const uint32_t*, uint32_t) {
+wgb_status wgb_render_pass_set_bind_group(wgb_render_pass pass, uint32_t index, wgb_bind_group group, const uint32_t* dynamic_offsets, uint32_t dynamic_offset_count) {
     return guarded([&] {
         BindGroup* g = group ? from_handle<BindGroup>(group, "bind group") : nullptr;
+        REQUIRE(dynamic_offsets || dynamic_offset_count == 0, "dynamic offsets are null");
         SubCommand& s = record(pass, SubCommand::SetBindGroup);
         s.index = index;
+        s.dynamic_offsets.assign(dynamic_offsets, dynamic_offsets + dynamic_offset_count);
         if (g) s.bind_group = Ref<BindGroup>(g);
     });
 }

@@ -58,6 +58,8 @@ struct WgbAttachment {
     wgb_u32 load_clear;         // 1: LoadOp::Clear still pending for this pass (first draw), 0: load stored texels
     wgb_u32 clear_texel;        // encoded clear colour (colour) / f32 bits (depth)
     wgb_u32 bytes_per_texel;
+    wgb_u32 write_mask;         // opt-in colour write mask as a byte mask over the texel (0xFFFFFFFF = write everything)
+    wgb_u32 srgb_encode;        // opt-in: apply the sRGB transfer function to r, g, b before the 8-bit encode
 };
 
 struct WgbVertexBuffer {
@@ -116,6 +118,9 @@ struct WgbDraw {
     wgb_u32 band_ty0, band_ty1;          // this rank's tile-row band [ty0, ty1) (sort-first partition)
     // raster state (state.rs:604-628, raster.rs:129-143)
     float vp_tx, vp_ty, vp_sx, vp_sy;    // ToRaster translation / scaling
+    float depth_min, depth_scale;        // opt-in viewport depth range: z = depth_min + ndc.z * depth_scale
+    wgb_u32 depth_range;                 // 0: the reference's behaviour (ndc.z as it is, raster.rs:141-158)
+    wgb_u32 pad3;
     wgb_u32 sc_x0, sc_y0, sc_x1, sc_y1;  // scissor_bb
     // draw call (state.rs:225-236)
     wgb_u32 indexed;                     // 0 direct, 1 u16, 2 u32

@@ -59,7 +59,14 @@ class SceneRenderer:
                 smp = device.create_sampler(address_mode_u=res[1], address_mode_v=res[2], address_mode_w=res[1])
                 self.resources[(g, b)] = smp
                 groups.setdefault(g, []).append({"binding": b, "sampler": smp})
-        self.bind_groups = {g: device.create_bind_group(None, entries) for g, entries in groups.items()}
+        self.bind_groups = {}
+        for g, entries in groups.items():
+            layout = None
+            if s.dynamic_bindings and g in s.dynamic_bindings:       # bindings that take a dynamic offset need a layout that says so
+                layout = device.create_bind_group_layout(
+                    [(e["binding"], 3, 1 if "buffer" in e else 2 if "texture_view" in e else 3,
+                      1 if e["binding"] in s.dynamic_bindings[g] else 0) for e in entries])
+            self.bind_groups[g] = device.create_bind_group(layout, entries)
         depth_state = None
         if s.depth_compare is not None:
             depth_state = {"format": "depth32float", "depth_write_enabled": s.depth_write, "depth_compare": s.depth_compare}
@@ -68,7 +75,8 @@ class SceneRenderer:
             vertex_buffers=[{"array_stride": l.stride, "step_mode": l.step_mode,
                              "attributes": [(a.format, a.offset, a.location) for a in l.attributes]} for l in s.vertex_layouts],
             topology=s.topology, strip_index_format=s.strip_index_format, front_face=s.front_face, cull_mode=s.cull_mode,
-            depth_stencil=depth_state, targets=[s.color_format])
+            depth_stencil=depth_state,
+            targets=[s.color_format if s.color_write_mask == 15 else {"format": s.color_format, "write_mask": s.color_write_mask}])
         self.target = target if target is not None else device.create_texture(s.width, s.height, s.color_format)
         self.target_view = self.target.create_view()
         self.depth_texture = self.depth_view = None
@@ -91,7 +99,7 @@ class SceneRenderer:
         with enc.begin_render_pass([color], depth) as rp:
             rp.set_pipeline(self.pipeline)
             for g, bg in self.bind_groups.items():
-                rp.set_bind_group(g, bg)
+                rp.set_bind_group(g, bg, (s.dynamic_offsets or {}).get(g, ()))
             if self.index_buffer is not None:
                 rp.set_index_buffer(self.index_buffer, self.index_format)
             for i, vb in enumerate(self.vertex_buffers):

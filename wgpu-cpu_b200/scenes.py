@@ -73,6 +73,11 @@ class Scene:
     draws: List[Draw] = field(default_factory=list)
     viewport: Optional[Tuple[float, float, float, float, float, float]] = None
     scissor: Optional[Tuple[int, int, int, int]] = None
+    # opt-in behaviour beyond the reference (api.FEATURE bits; the device must be requested with them)
+    features: int = 0
+    color_write_mask: int = 15                       # api.COLOR_WRITE bits, honoured with FEATURE["COLOR_WRITE_MASK"]
+    dynamic_offsets: Optional[dict] = None           # {group: [offsets]} for bindings listed in dynamic_bindings
+    dynamic_bindings: Optional[dict] = None          # {group: [binding numbers with has_dynamic_offset]}
     initial_color: Optional[np.ndarray] = None  # for LoadOp::Load passes
     initial_depth: Optional[np.ndarray] = None
 
