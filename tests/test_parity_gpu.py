@@ -419,3 +419,12 @@ def test_dump_texture_png(gpu, tmp_path):
     d = r.depth_texture.read()
     want = np.clip(np.trunc(d * np.float32(255.0)), 0, 255).astype(np.uint8)
     assert np.array_equal(_decode_png(str(tmp_path / "depth.png"))[:, :, 0], want)
+
+
+@pytest.mark.parametrize("seed", range(64))
+def test_fuzz(gpu, seed):
+    """Random pipeline state x random geometry (scenes.fuzz): framebuffer sizes from 1x1, all topologies, u16/u32
+    indices with base vertex / first index / primitive restart, cull and depth states, viewports reaching outside
+    the framebuffer, scissors, load ops, instancing -- coverage, depth and colour bit-exact, with and without the
+    hierarchical depth test."""
+    _compare(S.fuzz(seed), gpu)

@@ -478,3 +478,79 @@ def odd_sizes(width=333, height=77) -> Scene:
     s.name = f"odd_sizes_{width}x{height}"
     s.viewport = (-20.0, -10.0, 400.0, 100.0, 0.0, 1.0)
     return s
+
+
+def fuzz(seed: int) -> Scene:
+    """A random scene for the parity fuzz test: random framebuffer size, topology, index format / base vertex / first
+    index, cull state, depth state, viewport, scissor and load ops over random (partly clipped, partly tiny and layered)
+    geometry.  Everything is derived from `seed` with numpy's PCG64, so the oracle and the device see the same bytes."""
+    rng = np.random.default_rng(1000 + seed)
+    width, height = int(rng.integers(1, 330)), int(rng.integers(1, 230))
+    topology = str(rng.choice(["triangle-list"] * 5 + ["triangle-strip", "line-list", "line-strip", "point-list"]))
+    nverts = int(rng.integers(3, 1200))
+    u = rng.random((nverts, 8), dtype=np.float32)
+    v = np.ones((nverts, 8), dtype=np.float32)
+    spread = np.float32(rng.choice([0.6, 1.0, 1.6, 3.0]))
+    v[:, 0] = (u[:, 0] * 2 - 1) * spread
+    v[:, 1] = (u[:, 1] * 2 - 1) * spread
+    v[:, 2] = u[:, 2] * np.float32(1.3) - np.float32(0.15)
+    if rng.random() < 0.5:
+        v[:, 3] = np.float32(0.3) + u[:, 3] * np.float32(1.4)
+    v[:, 4:7] = u[:, 4:7]
+    small = rng.random() < 0.5
+    if small and topology == "triangle-list":
+        # tiny triangles in depth layers (the regime of C3, where the hierarchical depth test engages)
+        t = v[: nverts // 3 * 3].reshape(-1, 3, 8)
+        t[:, 1:, 0:2] = t[:, :1, 0:2] + (t[:, 1:, 0:2] - t[:, :1, 0:2]) * np.float32(0.02)
+        layer = (np.arange(t.shape[0]) * 4 // max(t.shape[0], 1)).astype(np.float32).reshape(-1, 1)
+        if rng.random() < 0.5:
+            layer = layer[::-1]
+        t[:, :, 2] = (layer + np.float32(0.5) + np.float32(0.4) * (t[:, :, 2] - np.float32(0.5))) / np.float32(4.0)
+        t[:, :, 3] = 1.0
+    indexed = bool(rng.random() < 0.6)
+    index_data, strip_fmt, draws = None, None, []
+    if indexed:
+        fmt = np.uint16 if rng.random() < 0.5 else np.uint32
+        nidx = int(rng.integers(3, 2500))
+        base_vertex = int(rng.integers(0, max(nverts // 4, 1)))
+        idx = rng.integers(0, nverts - base_vertex, nidx).astype(fmt)
+        if small and topology == "triangle-list":      # keep the tiny triangles: consecutive vertices
+            k = (nverts - base_vertex) // 3 * 3
+            idx = np.resize(np.arange(k, dtype=fmt), nidx if k == 0 else max(nidx // 3 * 3, 3)) if k >= 3 else idx
+        if topology.endswith("strip") and rng.random() < 0.6:
+            strip_fmt = "uint16" if fmt == np.uint16 else "uint32"
+            cut = rng.random(idx.size) < 0.08
+            idx[cut] = np.iinfo(fmt).max
+        first = int(rng.integers(0, max(idx.size // 5, 1)))
+        index_data = idx
+        draws.append(Draw(True, first, int(idx.size - first), base_vertex, 0, int(rng.integers(1, 3))))
+    else:
+        first = int(rng.integers(0, max(nverts // 5, 1)))
+        draws.append(Draw(False, first, nverts - first, 0, 0, 1))
+    compare = str(rng.choice(["less", "less", "less-equal", "greater", "greater-equal", "always", "never", "equal", "none"]))
+    write = bool(rng.random() < 0.75)
+    if compare == "not-equal":
+        write = False
+    s = Scene(
+        name=f"fuzz_{seed}", width=width, height=height, shader="hello_mesh", topology=topology, strip_index_format=strip_fmt,
+        front_face=str(rng.choice(["ccw", "cw"])), cull_mode=rng.choice([None, None, "front", "back"]),
+        depth_compare=None if compare == "none" else compare, depth_write=write,
+        clear_depth=float(rng.choice([1.0, 0.5, 0.25])),
+        vertex_layouts=[_POS_COLOR_LAYOUT], vertex_buffers=[np.ascontiguousarray(v).view(np.uint8).reshape(-1)],
+        index_data=index_data, bindings={(0, 0): ("buffer", identity_matrix_bytes())}, draws=draws,
+    )
+    if s.cull_mode is not None:
+        s.cull_mode = str(s.cull_mode)
+    if rng.random() < 0.3:
+        s.viewport = (float(rng.integers(-20, 40)), float(rng.integers(-20, 40)), float(rng.integers(1, width + 60)),
+                      float(rng.integers(1, height + 60)), 0.0, 1.0)
+    if rng.random() < 0.3:
+        x0, y0 = int(rng.integers(0, width)), int(rng.integers(0, height))
+        s.scissor = (x0, y0, int(rng.integers(0, width - x0 + 1)), int(rng.integers(0, height - y0 + 1)))
+    if rng.random() < 0.25:
+        s.clear_color = None
+        s.initial_color = rng.integers(0, 255, (height, width, 4), dtype=np.uint8)
+        if s.depth_compare is not None:
+            s.clear_depth = None
+            s.initial_depth = rng.random((height, width), dtype=np.float32)
+    return s
