@@ -127,6 +127,8 @@ typedef struct {
 #define WGB_FEATURE_COLOR_WRITE_MASK 2u      /* wgb_color_target_state.write_mask is applied (ignored by the reference, fragment.rs:480-485) */
 #define WGB_FEATURE_SRGB_ENCODE 4u           /* *Srgb colour targets store sRGB-encoded values (the reference stores them linearly, texture.rs:393-400) */
 #define WGB_FEATURE_DYNAMIC_OFFSETS 8u       /* set_bind_group dynamic offsets move buffer bindings (stored and ignored by the reference, state.rs:194-205) */
+#define WGB_FEATURE_BLEND 16u                /* wgb_color_target_state blend states and set_blend_constant are applied (ignored by the reference,
+                                              * fragment.rs:480-485); triangle topologies only; such pipelines take the ordered tile kernel */
 #define WGB_COLOR_WRITE_RED 1u
 #define WGB_COLOR_WRITE_GREEN 2u
 #define WGB_COLOR_WRITE_BLUE 4u
@@ -238,7 +240,15 @@ WGB_API wgb_status wgb_device_create_bind_group(wgb_device device, wgb_bind_grou
 /* ---- render pipeline ---- */
 typedef struct { uint32_t format; uint64_t offset; uint32_t shader_location; } wgb_vertex_attribute;
 typedef struct { uint64_t array_stride; uint32_t step_mode; uint32_t attribute_count; const wgb_vertex_attribute* attributes; } wgb_vertex_buffer_layout;
-typedef struct { uint32_t format; uint32_t has_blend; uint32_t write_mask; } wgb_color_target_state;
+/* wgpu::BlendFactor / BlendOperation / BlendComponent */
+enum { WGB_BLEND_FACTOR_ZERO = 0, WGB_BLEND_FACTOR_ONE = 1, WGB_BLEND_FACTOR_SRC = 2, WGB_BLEND_FACTOR_ONE_MINUS_SRC = 3,
+       WGB_BLEND_FACTOR_SRC_ALPHA = 4, WGB_BLEND_FACTOR_ONE_MINUS_SRC_ALPHA = 5, WGB_BLEND_FACTOR_DST = 6,
+       WGB_BLEND_FACTOR_ONE_MINUS_DST = 7, WGB_BLEND_FACTOR_DST_ALPHA = 8, WGB_BLEND_FACTOR_ONE_MINUS_DST_ALPHA = 9,
+       WGB_BLEND_FACTOR_SRC_ALPHA_SATURATED = 10, WGB_BLEND_FACTOR_CONSTANT = 11, WGB_BLEND_FACTOR_ONE_MINUS_CONSTANT = 12 };
+enum { WGB_BLEND_OPERATION_ADD = 0, WGB_BLEND_OPERATION_SUBTRACT = 1, WGB_BLEND_OPERATION_REVERSE_SUBTRACT = 2,
+       WGB_BLEND_OPERATION_MIN = 3, WGB_BLEND_OPERATION_MAX = 4 };
+typedef struct { uint32_t src_factor, dst_factor, operation; } wgb_blend_component;
+typedef struct { uint32_t format; uint32_t has_blend; uint32_t write_mask; wgb_blend_component blend_color, blend_alpha; } wgb_color_target_state;
 typedef struct {
     wgb_pipeline_layout layout;                /* may be NULL */
     /* VertexState (render_pass/vertex.rs:43-93) */

@@ -381,6 +381,48 @@ static int encode_color(Vec4 c, uint32_t format, uint8_t out[4], bool srgb_encod
         default: return 0;
     }
 }
+/* ORC_EXT_BLEND (not in the reference; fragment.rs:480-485 ignores the blend state): the WebGPU blend equation */
+static inline float srgb_eotf(float v) {
+    if (!(v > 0.04045f)) return v / 12.92f;
+    return powf((v + 0.055f) / 1.055f, 2.4f);
+}
+static Vec4 decode_color(const uint8_t* texel, uint32_t format, bool srgb) {
+    float c[4] = {0, 0, 0, 0};
+    const int bpp = bytes_per_texel(format);
+    for (int k = 0; k < bpp && k < 4; k++) c[k] = (float)texel[k] / 255.0f;
+    if (format == ORC_FMT_BGRA8_UNORM || format == ORC_FMT_BGRA8_UNORM_SRGB) { const float t = c[0]; c[0] = c[2]; c[2] = t; }
+    if (srgb && (format == ORC_FMT_RGBA8_UNORM_SRGB || format == ORC_FMT_BGRA8_UNORM_SRGB)) { c[0] = srgb_eotf(c[0]); c[1] = srgb_eotf(c[1]); c[2] = srgb_eotf(c[2]); }
+    return {c[0], c[1], c[2], c[3]};
+}
+static float blend_factor(uint32_t f, float s, float sa, float dv, float da, float c, bool alpha) {
+    switch (f) {
+        case 0: return 0.0f; case 1: return 1.0f;
+        case 2: return s; case 3: return 1.0f - s;
+        case 4: return sa; case 5: return 1.0f - sa;
+        case 6: return dv; case 7: return 1.0f - dv;
+        case 8: return da; case 9: return 1.0f - da;
+        case 10: return alpha ? 1.0f : fminf(sa, 1.0f - da);
+        case 11: return c;
+        default: return 1.0f - c;
+    }
+}
+static float blend_channel(uint32_t sf, uint32_t df, uint32_t op, float s, float sa, float dv, float da, float c, bool alpha) {
+    if (op == 3) return fminf(s, dv);
+    if (op == 4) return fmaxf(s, dv);
+    const float a = s * blend_factor(sf, s, sa, dv, da, c, alpha);
+    const float b = dv * blend_factor(df, s, sa, dv, da, c, alpha);
+    return op == 0 ? a + b : op == 1 ? a - b : b - a;
+}
+static inline float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+static Vec4 blend_color(const uint32_t st[7], const float constant[4], Vec4 src, Vec4 dst) {
+    src = {clamp01(src.x), clamp01(src.y), clamp01(src.z), clamp01(src.w)};
+    Vec4 r;
+    r.x = blend_channel(st[1], st[2], st[3], src.x, src.w, dst.x, dst.w, constant[0], false);
+    r.y = blend_channel(st[1], st[2], st[3], src.y, src.w, dst.y, dst.w, constant[1], false);
+    r.z = blend_channel(st[1], st[2], st[3], src.z, src.w, dst.z, dst.w, constant[2], false);
+    r.w = blend_channel(st[4], st[5], st[6], src.w, src.w, dst.w, dst.w, constant[3], true);
+    return r;
+}
 static inline uint64_t texel_offset(const orc_texture& t, uint32_t x, uint32_t y, int bpp) {
     /* TextureDataLayout::texel_byte_offset (texture.rs:283-285): x*bpp + y*W*bpp (+ z*W*H*bpp) */
     return (uint64_t)x * bpp + (uint64_t)y * t.width * bpp;
@@ -587,7 +629,15 @@ static void process_fragment(DrawCtx& cx, int n, const VertexOut* const* unclipp
             if (loc >= cx.pass->num_color) { cx.err = ORC_ERR_INVALID; return; }
             const orc_texture& t = cx.pass->color[loc];
             uint8_t texel[4];
-            const int bpp = encode_color(out.color[k], t.format, texel, (cx.rs->ext_features & ORC_EXT_SRGB_ENCODE) != 0);
+            const bool srgb = (cx.rs->ext_features & ORC_EXT_SRGB_ENCODE) != 0;
+            Vec4 value = out.color[k];
+            if ((cx.rs->ext_features & ORC_EXT_BLEND) && cx.rs->blend[loc][0]) {
+                const int dbpp = bytes_per_texel(t.format);
+                if (dbpp == 0) { cx.err = ORC_ERR_UNSUPPORTED; return; }
+                value = blend_color(cx.rs->blend[loc], cx.rs->blend_constant, value,
+                                    decode_color(t.data + texel_offset(t, fx, fy, dbpp), t.format, srgb));
+            }
+            const int bpp = encode_color(value, t.format, texel, srgb);
             if (bpp == 0) { cx.err = ORC_ERR_UNSUPPORTED; return; }
             uint8_t* dst = t.data + texel_offset(t, fx, fy, bpp);
             if (cx.rs->ext_features & ORC_EXT_COLOR_WRITE_MASK) {             /* not in the reference: channels outside the mask keep their value */
@@ -837,6 +887,8 @@ void orc_default_raster_state(uint32_t width, uint32_t height, orc_raster_state*
     out->sc_x = 0; out->sc_y = 0; out->sc_w = width; out->sc_h = height;
     out->ext_features = 0;
     for (int c = 0; c < ORC_MAX_COLOR; c++) out->color_write_mask[c] = 15u;
+    std::memset(out->blend, 0, sizeof(out->blend));
+    for (int k = 0; k < 4; k++) out->blend_constant[k] = 0.0f;
 }
 
 int orc_draw_execute(const orc_pass* pass, const orc_pipeline* pipe, const orc_raster_state* rs,

@@ -109,10 +109,15 @@ typedef struct {
      * reference's behaviour. */
     uint32_t ext_features;
     uint32_t color_write_mask[ORC_MAX_COLOR]; /* ORC_EXT_COLOR_WRITE_MASK: R=1 G=2 B=4 A=8 */
+    /* ORC_EXT_BLEND: per target {enabled, colour src factor, dst factor, operation, alpha src, dst, operation}
+     * (wgpu::BlendFactor / BlendOperation numbering of include/wgpu_b200.h) and the blend constant */
+    uint32_t blend[ORC_MAX_COLOR][7];
+    float blend_constant[4];
 } orc_raster_state;
 #define ORC_EXT_VIEWPORT_DEPTH_RANGE 1u   /* fragment depth = min_depth + ndc.z * (max_depth - min_depth) */
 #define ORC_EXT_COLOR_WRITE_MASK 2u
 #define ORC_EXT_SRGB_ENCODE 4u            /* *Srgb targets store the sRGB-encoded value */
+#define ORC_EXT_BLEND 16u                 /* WebGPU blend equation on [0,1] values against the stored (8-bit) texel */
 
 typedef struct {
     uint32_t indexed;

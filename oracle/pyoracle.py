@@ -78,7 +78,8 @@ class RasterState(C.Structure):
     _fields_ = [("vp_x", C.c_float), ("vp_y", C.c_float), ("vp_w", C.c_float), ("vp_h", C.c_float),
                 ("vp_min_depth", C.c_float), ("vp_max_depth", C.c_float),
                 ("sc_x", C.c_uint32), ("sc_y", C.c_uint32), ("sc_w", C.c_uint32), ("sc_h", C.c_uint32),
-                ("ext_features", C.c_uint32), ("color_write_mask", C.c_uint32 * MAX_COLOR)]
+                ("ext_features", C.c_uint32), ("color_write_mask", C.c_uint32 * MAX_COLOR),
+                ("blend", (C.c_uint32 * 7) * MAX_COLOR), ("blend_constant", C.c_float * 4)]
 
 
 class DrawDesc(C.Structure):
@@ -154,7 +155,7 @@ def render(scene, want_coverage: bool = True) -> Frame:
     if scene.clear_color is not None:
         for k in range(4):
             p.clear_color[0][k] = float(scene.clear_color[k])
-    p.ext_features = getattr(scene, "features", 0) & 7
+    p.ext_features = getattr(scene, "features", 0) & 23
     p.has_depth = 1 if scene.has_depth else 0
     if scene.has_depth:
         p.depth = Texture(_ptr(depth), W, H, FORMAT["depth32float"])
@@ -186,7 +187,14 @@ def render(scene, want_coverage: bool = True) -> Frame:
         rs.vp_x, rs.vp_y, rs.vp_w, rs.vp_h, rs.vp_min_depth, rs.vp_max_depth = scene.viewport
     if scene.scissor is not None:
         rs.sc_x, rs.sc_y, rs.sc_w, rs.sc_h = scene.scissor
-    rs.ext_features = getattr(scene, "features", 0) & 7        # depth range, write mask, sRGB encode (oracle.h ORC_EXT_*)
+    rs.ext_features = getattr(scene, "features", 0) & 23       # depth range, write mask, sRGB encode, blend (oracle.h ORC_EXT_*)
+    if getattr(scene, "blend", None):
+        from wgpu_cpu_b200.api import BLEND_FACTOR, BLEND_OPERATION
+        (cs, cd, co), (as_, ad, ao) = scene.blend["color"], scene.blend["alpha"]
+        for k, v in enumerate([1, BLEND_FACTOR[cs], BLEND_FACTOR[cd], BLEND_OPERATION[co], BLEND_FACTOR[as_], BLEND_FACTOR[ad], BLEND_OPERATION[ao]]):
+            rs.blend[0][k] = v
+        for k in range(4):
+            rs.blend_constant[k] = float(scene.blend_constant[k])
     rs.color_write_mask[0] = getattr(scene, "color_write_mask", 15)
     dyn = {}
     if getattr(scene, "features", 0) & 8 and scene.dynamic_offsets:       # dynamic offsets: the k-th offset moves the k-th dynamic binding

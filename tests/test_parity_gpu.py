@@ -428,3 +428,15 @@ def test_fuzz(gpu, seed):
     the framebuffer, scissors, load ops, instancing -- coverage, depth and colour bit-exact, with and without the
     hierarchical depth test."""
     _compare(S.fuzz(seed), gpu)
+
+
+@pytest.mark.parametrize("scene_name", ["random", "indexed_small", "huge"])
+def test_not_equal_with_depth_write_takes_the_ordered_kernel(gpu, scene_name):
+    """NotEqual + depth write: every fragment's outcome depends on the one before it, so there is no closed form; the
+    ordered tile kernel applies the fragments of each pixel in primitive order, like the reference's loop."""
+    scene = {"random": lambda: S.random_triangles(count=250, seed=77, clear_depth=0.5),
+             "indexed_small": lambda: S.synthetic_grid(300, 200, n=50, layers=3),
+             "huge": lambda: S.huge_triangles()}[scene_name]()
+    scene.depth_compare, scene.depth_write = "not-equal", True
+    scene.name += "_not_equal_write"
+    _compare(scene, gpu)

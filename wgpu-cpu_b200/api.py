@@ -55,7 +55,7 @@ class _DeviceDescriptor(C.Structure):
     _fields_ = [("cuda_device", C.c_int32), ("band_rank", C.c_uint32), ("band_count", C.c_uint32), ("features", C.c_uint32)]
 
 
-FEATURE = {"VIEWPORT_DEPTH_RANGE": 1, "COLOR_WRITE_MASK": 2, "SRGB_ENCODE": 4, "DYNAMIC_OFFSETS": 8}
+FEATURE = {"VIEWPORT_DEPTH_RANGE": 1, "COLOR_WRITE_MASK": 2, "SRGB_ENCODE": 4, "DYNAMIC_OFFSETS": 8, "BLEND": 16}
 COLOR_WRITE = {"RED": 1, "GREEN": 2, "BLUE": 4, "ALPHA": 8, "ALL": 15}
 
 
@@ -104,8 +104,24 @@ class _VertexBufferLayout(C.Structure):
                 ("attributes", C.POINTER(_VertexAttribute))]
 
 
+class _BlendComponent(C.Structure):
+    _fields_ = [("src_factor", C.c_uint32), ("dst_factor", C.c_uint32), ("operation", C.c_uint32)]
+
+
 class _ColorTargetState(C.Structure):
-    _fields_ = [("format", C.c_uint32), ("has_blend", C.c_uint32), ("write_mask", C.c_uint32)]
+    _fields_ = [("format", C.c_uint32), ("has_blend", C.c_uint32), ("write_mask", C.c_uint32),
+                ("blend_color", _BlendComponent), ("blend_alpha", _BlendComponent)]
+
+
+BLEND_FACTOR = {"zero": 0, "one": 1, "src": 2, "one-minus-src": 3, "src-alpha": 4, "one-minus-src-alpha": 5, "dst": 6,
+                "one-minus-dst": 7, "dst-alpha": 8, "one-minus-dst-alpha": 9, "src-alpha-saturated": 10, "constant": 11,
+                "one-minus-constant": 12}
+BLEND_OPERATION = {"add": 0, "subtract": 1, "reverse-subtract": 2, "min": 3, "max": 4}
+
+
+def _blend_component(c):
+    src, dst, op = c
+    return _BlendComponent(BLEND_FACTOR[src], BLEND_FACTOR[dst], BLEND_OPERATION[op])
 
 
 class _RenderPipelineDescriptor(C.Structure):
@@ -596,9 +612,13 @@ class Device(_Handle):
         ts = (_ColorTargetState * max(nt, 1))()
         for i, t in enumerate(targets):
             if isinstance(t, dict):
-                ts[i] = _ColorTargetState(TEXTURE_FORMAT[t["format"]], 1 if t.get("blend") else 0, t.get("write_mask", 15))
+                # blend: {"color": (src_factor, dst_factor, operation), "alpha": (...)} as in wgpu::BlendState
+                blend = t.get("blend")
+                ts[i] = _ColorTargetState(TEXTURE_FORMAT[t["format"]], 1 if blend else 0, t.get("write_mask", 15),
+                                          _blend_component(blend["color"]) if blend else _BlendComponent(1, 0, 0),
+                                          _blend_component(blend["alpha"]) if blend else _BlendComponent(1, 0, 0))
             else:
-                ts[i] = _ColorTargetState(TEXTURE_FORMAT[t], 0, 15)
+                ts[i] = _ColorTargetState(TEXTURE_FORMAT[t], 0, 15, _BlendComponent(1, 0, 0), _BlendComponent(1, 0, 0))
         d = _RenderPipelineDescriptor()
         d.layout = layout._h if layout else None
         d.vertex_module = vertex_module._h

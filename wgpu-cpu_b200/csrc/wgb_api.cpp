@@ -289,7 +289,9 @@ struct DevBuf {
 // kernels of one compiled pipeline variant
 struct KernelSet {
     CUmodule module = nullptr;
-    CUfunction geometry = nullptr, vertex = nullptr, geometry_cached = nullptr, clip = nullptr, scan = nullptr, fill = nullptr, tile = nullptr, clear = nullptr, strip_map = nullptr;
+    CUfunction geometry = nullptr, vertex = nullptr, geometry_cached = nullptr, clip = nullptr, scan = nullptr, fill = nullptr, tile = nullptr, clear = nullptr, strip_map = nullptr,
+               big_sort = nullptr;     // ordered variants only
+    bool ordered = false;
 };
 
 struct Instance : Object {};
@@ -451,6 +453,11 @@ struct RenderPipeline : Object {
     std::map<uint32_t, std::shared_ptr<KernelSet>> variants;   // key: has_depth_attachment | separated << 1
     std::map<uint32_t, std::string> variant_source;
 
+    bool blends() const {       // WGB_FEATURE_BLEND: a target with a blend state sends the pipeline down the ordered path
+        if (!(device->features & WGB_FEATURE_BLEND)) return false;
+        for (const auto& t : targets) if (t.has_blend) return true;
+        return false;
+    }
     int prim_size() const {
         return topology == WGB_TOPOLOGY_POINT_LIST ? 1 : (topology == WGB_TOPOLOGY_LINE_LIST || topology == WGB_TOPOLOGY_LINE_STRIP) ? 2 : 3;
     }
@@ -467,16 +474,17 @@ struct RenderPipeline : Object {
             case WGB_COMPARE_GREATER: return write ? 3 : 5;
             case WGB_COMPARE_GREATER_EQUAL: return write ? 4 : 5;
             case WGB_COMPARE_EQUAL: return 5;
-            case WGB_COMPARE_NOT_EQUAL:
-                if (write) fail(WGB_ERROR_UNSUPPORTED, "depth compare NotEqual with depth writes is order-dependent per fragment and is not supported");
-                return 5;
+            case WGB_COMPARE_NOT_EQUAL: return write ? 7 : 5;    // with writes every outcome depends on the previous fragment: ordered kernel
             default: fail(WGB_ERROR_VALIDATION, "invalid depth compare function %u", compare);
         }
     }
 
     std::string build_source(bool has_depth_attachment, bool separated) const {
         const bool test = has_depth_stencil && has_depth_attachment;
-        const int mode = resolve_mode(test, depth_compare, depth_write != 0);
+        int mode = resolve_mode(test, depth_compare, depth_write != 0);
+        if (blends()) mode = 7;
+        if (mode == 7 && prim_size() != 3)
+            fail(WGB_ERROR_UNSUPPORTED, "blending and NotEqual depth tests with depth writes are supported for triangle topologies only");
         std::string s;
         char line[256];
         auto def = [&](const char* name, long long v) { snprintf(line, sizeof(line), "#define %s %lld\n", name, v); s += line; };
@@ -499,6 +507,17 @@ struct RenderPipeline : Object {
                          (unsigned long long)a.offset, a.shader_location, vbs[b].step_mode == WGB_VERTEX_STEP_MODE_INSTANCE ? "true" : "false");
                 s += line;
             }
+        // blend state of target t: field 0 = enabled, 1..3 = colour src / dst / op, 4..6 = alpha src / dst / op
+        s += "#define WGB_HAVE_BLEND_STATE 1\nstatic __device__ __forceinline__ constexpr int wgb_blend_state(int t, int f) { return ";
+        for (size_t t = 0; t < targets.size(); t++) {
+            const auto& ts = targets[t];
+            const bool on = blends() && ts.has_blend;
+            snprintf(line, sizeof(line), "t == %zu ? (f == 0 ? %d : f == 1 ? %u : f == 2 ? %u : f == 3 ? %u : f == 4 ? %u : f == 5 ? %u : %u) : ", t, on ? 1 : 0,
+                     ts.blend_color.src_factor, ts.blend_color.dst_factor, ts.blend_color.operation,
+                     ts.blend_alpha.src_factor, ts.blend_alpha.dst_factor, ts.blend_alpha.operation);
+            s += line;
+        }
+        s += "0; }\n";
         s += "#include \"wgb_prelude.cuh\"\n";
         s += vs_text;
         s += "\n";
@@ -536,6 +555,8 @@ struct RenderPipeline : Object {
                     CUresult q = g_drv.ModuleGetFunction(f, ks->module, n);
                     if (q != CUDA_SUCCESS) fail(WGB_ERROR_DEVICE, "kernel %s missing: %s", n, cu_error(q));
                 };
+                ks->ordered = src.find("#define WGB_RESOLVE 7\n") != std::string::npos;
+                if (ks->ordered) fn("wgb_big_sort_kernel", &ks->big_sort);
                 fn("wgb_geometry_kernel", &ks->geometry);
                 fn("wgb_vertex_kernel", &ks->vertex);
                 fn("wgb_geometry_cached_kernel", &ks->geometry_cached);
@@ -567,6 +588,7 @@ struct SubCommand {
     uint32_t first = 0, count = 0, first_instance = 0, instance_count = 0;
     int32_t base_vertex = 0;
     std::vector<uint32_t> dynamic_offsets;
+    float blend_constant[4] = {0, 0, 0, 0};
 };
 struct PassCommand {
     struct Color { Ref<TextureView> view; uint32_t load_op, store_op; double clear[4]; };
@@ -614,6 +636,7 @@ struct PassState {   // render_pass/state.rs:58-75
     Ref<RenderPipeline> pipeline;
     Ref<BindGroup> bind_groups[WGB_MAX_GROUPS];
     std::vector<uint32_t> dynamic_offsets[WGB_MAX_GROUPS];
+    float blend_constant[4] = {0, 0, 0, 0};
     struct Slice { Ref<Buffer> buffer; uint64_t offset = 0, size = 0; };
     Slice vertex_buffers[WGB_MAX_VERTEX_BUFFERS];
     Slice index_buffer;
@@ -762,6 +785,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
         if (dev->features & WGB_FEATURE_COLOR_WRITE_MASK) d.color[c].write_mask = texel_write_mask(pipe->targets[c].write_mask, tg.color[c].format);
     }
     if (tg.has_depth) d.depth = tg.depth;
+    memcpy(d.blend_constant, st.blend_constant, sizeof(d.blend_constant));
     if (dev->features & WGB_FEATURE_VIEWPORT_DEPTH_RANGE) {
         d.depth_range = 1u; d.depth_min = st.vp[4]; d.depth_scale = st.vp[5] - st.vp[4];
     }
@@ -856,6 +880,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 launch(dev, ks->scan, dim3(1), dim3(1024), &d);
                 launch(dev, ks->fill, dim3(gblocks), dim3(256), &d);
             }
+            if (ks->ordered) launch(dev, ks->big_sort, dim3(1), dim3(1024), &d);
             CUDA_CHECK(cudaEventRecord(dev->ev[1], dev->stream));
             launch(dev, ks->tile, dim3(d.tiles_x, d.band_ty1 - d.band_ty0), dim3(256), &d);
             CUDA_CHECK(cudaEventRecord(dev->ev[2], dev->stream));
@@ -964,7 +989,8 @@ void execute_pass(Device* dev, const PassCommand& pass) {
                 break;
             case SubCommand::SetViewport: memcpy(st.vp, sc.vp, sizeof(st.vp)); break;
             case SubCommand::SetScissor: memcpy(st.sc, sc.sc, sizeof(st.sc)); break;
-            case SubCommand::SetBlendConstant: case SubCommand::SetStencilReference: break;   // stored, unused (state.rs:207-221)
+            case SubCommand::SetBlendConstant: memcpy(st.blend_constant, sc.blend_constant, sizeof(st.blend_constant)); break;   // used by WGB_FEATURE_BLEND only
+            case SubCommand::SetStencilReference: break;   // stored, unused (state.rs:207-221)
             case SubCommand::Draw: case SubCommand::DrawIndexed: execute_draw(dev, st, tg, sc); break;
         }
     }
@@ -1216,7 +1242,8 @@ wgb_status wgb_adapter_request_device(wgb_adapter adapter, const wgb_device_desc
         }
         dev->band_rank = dd.band_rank;
         dev->band_count = dd.band_count ? dd.band_count : 1;
-        const uint32_t known = WGB_FEATURE_VIEWPORT_DEPTH_RANGE | WGB_FEATURE_COLOR_WRITE_MASK | WGB_FEATURE_SRGB_ENCODE | WGB_FEATURE_DYNAMIC_OFFSETS;
+        const uint32_t known = WGB_FEATURE_VIEWPORT_DEPTH_RANGE | WGB_FEATURE_COLOR_WRITE_MASK | WGB_FEATURE_SRGB_ENCODE | WGB_FEATURE_DYNAMIC_OFFSETS |
+                               WGB_FEATURE_BLEND;
         if (dd.features & ~known) fail(WGB_ERROR_UNSUPPORTED, "unknown device feature bits 0x%x", dd.features & ~known);
         dev->features = dd.features;
         REQUIRE(dev->band_rank < dev->band_count, "band_rank %u >= band_count %u", dev->band_rank, dev->band_count);
@@ -1769,8 +1796,12 @@ wgb_status wgb_render_pass_set_scissor_rect(wgb_render_pass pass, uint32_t x, ui
         s.sc[0] = x; s.sc[1] = y; s.sc[2] = width; s.sc[3] = height;
     });
 }
-wgb_status wgb_render_pass_set_blend_constant(wgb_render_pass pass, const double*) {
-    return guarded([&] { record(pass, SubCommand::SetBlendConstant); });
+wgb_status wgb_render_pass_set_blend_constant(wgb_render_pass pass, const double* color) {
+    return guarded([&] {
+        REQUIRE(color, "colour is null");
+        SubCommand& s = record(pass, SubCommand::SetBlendConstant);
+        for (int k = 0; k < 4; k++) s.blend_constant[k] = (float)color[k];
+    });
 }
 wgb_status wgb_render_pass_set_stencil_reference(wgb_render_pass pass, uint32_t) {
     return guarded([&] { record(pass, SubCommand::SetStencilReference); });

@@ -121,6 +121,7 @@ struct WgbDraw {
     float depth_min, depth_scale;        // opt-in viewport depth range: z = depth_min + ndc.z * depth_scale
     wgb_u32 depth_range;                 // 0: the reference's behaviour (ndc.z as it is, raster.rs:141-158)
     wgb_u32 pad3;
+    float blend_constant[4];             // set_blend_constant (used by WGB_FEATURE_BLEND pipelines only)
     wgb_u32 sc_x0, sc_y0, sc_x1, sc_y1;  // scissor_bb
     // draw call (state.rs:225-236)
     wgb_u32 indexed;                     // 0 direct, 1 u16, 2 u32

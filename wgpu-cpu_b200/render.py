@@ -76,7 +76,8 @@ class SceneRenderer:
                              "attributes": [(a.format, a.offset, a.location) for a in l.attributes]} for l in s.vertex_layouts],
             topology=s.topology, strip_index_format=s.strip_index_format, front_face=s.front_face, cull_mode=s.cull_mode,
             depth_stencil=depth_state,
-            targets=[s.color_format if s.color_write_mask == 15 else {"format": s.color_format, "write_mask": s.color_write_mask}])
+            targets=[s.color_format if s.color_write_mask == 15 and not s.blend
+                     else {"format": s.color_format, "write_mask": s.color_write_mask, "blend": s.blend}])
         self.target = target if target is not None else device.create_texture(s.width, s.height, s.color_format)
         self.target_view = self.target.create_view()
         self.depth_texture = self.depth_view = None
@@ -104,6 +105,8 @@ class SceneRenderer:
                 rp.set_index_buffer(self.index_buffer, self.index_format)
             for i, vb in enumerate(self.vertex_buffers):
                 rp.set_vertex_buffer(i, vb)
+            if s.blend:
+                rp.set_blend_constant(s.blend_constant)
             if s.viewport is not None:
                 rp.set_viewport(*s.viewport)
             if s.scissor is not None:

@@ -78,6 +78,8 @@ class Scene:
     color_write_mask: int = 15                       # api.COLOR_WRITE bits, honoured with FEATURE["COLOR_WRITE_MASK"]
     dynamic_offsets: Optional[dict] = None           # {group: [offsets]} for bindings listed in dynamic_bindings
     dynamic_bindings: Optional[dict] = None          # {group: [binding numbers with has_dynamic_offset]}
+    blend: Optional[dict] = None                     # {"color": (src, dst, op), "alpha": (src, dst, op)}, FEATURE["BLEND"]
+    blend_constant: Tuple[float, float, float, float] = (0.0, 0.0, 0.0, 0.0)
     initial_color: Optional[np.ndarray] = None  # for LoadOp::Load passes
     initial_depth: Optional[np.ndarray] = None
 
@@ -527,10 +529,10 @@ def fuzz(seed: int) -> Scene:
     else:
         first = int(rng.integers(0, max(nverts // 5, 1)))
         draws.append(Draw(False, first, nverts - first, 0, 0, 1))
-    compare = str(rng.choice(["less", "less", "less-equal", "greater", "greater-equal", "always", "never", "equal", "none"]))
+    compare = str(rng.choice(["less", "less", "less-equal", "greater", "greater-equal", "always", "never", "equal", "not-equal", "none"]))
     write = bool(rng.random() < 0.75)
-    if compare == "not-equal":
-        write = False
+    if compare == "not-equal" and not topology.startswith("triangle"):
+        write = False       # NotEqual + write runs on the ordered kernel, which rasterises triangles only
     s = Scene(
         name=f"fuzz_{seed}", width=width, height=height, shader="hello_mesh", topology=topology, strip_index_format=strip_fmt,
         front_face=str(rng.choice(["ccw", "cw"])), cull_mode=rng.choice([None, None, "front", "back"]),
