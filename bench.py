@@ -228,9 +228,14 @@ def main():
         cameras = [S.hello_texture(W, H, yaw=f * 2.0 * math.pi / C5_FRAMES).bindings[(0, 0)][1] for f in range(C5_FRAMES)]
     passes_per_step = len(cameras) if cameras else 1
 
+    # The timed span mirrors the reference's own (render_pass/mod.rs:346-392: State::new -> load -> draws -> store, i.e.
+    # execution, not recording -- SURVEY 8d): command buffers are recorded before the timed region, one per step, and a
+    # step is submit + poll(Wait) (+ the presenter exchange)
+    recorded = []
+
     def step():
         if cameras is None:
-            st = r.render()
+            st = r.render(recorded.pop() if recorded else None)
             gather()
             return st
         acc = None
@@ -248,6 +253,8 @@ def main():
 
     for _ in range(warm):
         step()
+    if cameras is None:
+        recorded.extend(r.encode() for _ in range(args.steps))
 
     # ---- timed: K passes, inputs resident in HBM ----
     sampler = ClockSampler(local_rank)
@@ -378,6 +385,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "width": W, "height": H, "triangles": prims,
                    "l2": "inputs (280 MB vertex+index) and attachments (66 MB) exceed the 126 MB L2 at C3; no explicit flush",
+                   "timed_span": "submit + poll(Wait) per step (execution, as the reference's own pass timer); command buffers recorded before the timed region",
                    "parallelism": (f"sort-first x{world}, bands presented to rank 0 by " +
                                    ("NVLink peer stores from the tile kernel" if args.present == "peer" else "NCCL send/recv"))
                    if world > 1 else "single GPU",

@@ -119,12 +119,13 @@ class SceneRenderer:
                     rp.draw(range(d.first, d.first + d.count), range(d.first_instance, d.first_instance + d.instance_count))
         return enc.finish()
 
-    def submit(self) -> int:
-        idx = self.queue.submit([self.encode()])
+    def submit(self, command_buffer: Optional[api.CommandBuffer] = None) -> int:
+        idx = self.queue.submit([command_buffer if command_buffer is not None else self.encode()])
         return idx
 
-    def render(self) -> dict:
-        idx = self.submit()
+    def render(self, command_buffer: Optional[api.CommandBuffer] = None) -> dict:
+        """Submit (a command buffer recorded earlier with encode(), or a fresh one) and wait for it."""
+        idx = self.submit(command_buffer)
         self.device.poll(True, idx)
         return self.device.last_pass_stats()
 
