@@ -499,7 +499,9 @@ struct RenderPipeline : Object {
         def("WGB_DEPTH_WRITE", (test && depth_write) ? 1 : 0);
         def("WGB_HAS_DEPTH", has_depth_attachment ? 1 : 0);
         def("WGB_NUM_COLOR", (long long)targets.size());
-        if (const char* mb = getenv("WGB_TILE_MIN_BLOCKS")) def("WGB_TILE_MIN_BLOCKS", atoi(mb));   // tuning knob
+        if (const char* mb = getenv("WGB_TILE_MIN_BLOCKS")) def("WGB_TILE_MIN_BLOCKS", atoi(mb));   // tuning knobs
+        if (const char* mb = getenv("WGB_FILL_ROUNDS")) def("WGB_FILL_ROUNDS", atoi(mb));
+        if (const char* mb = getenv("WGB_FILL_TARGET")) def("WGB_FILL_TARGET", atoi(mb));
         for (size_t b = 0; b < vbs.size(); b++)
             for (const auto& a : vbs[b].attrs) {
                 snprintf(line, sizeof(line), "#define WGB_ATTR%u_SLOT %zu\n#define WGB_ATTR%u_STRIDE %lluu\n#define WGB_ATTR%u_OFFSET %lluu\n#define WGB_ATTR%u_INSTANCE %s\n",
