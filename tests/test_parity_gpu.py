@@ -440,3 +440,23 @@ def test_not_equal_with_depth_write_takes_the_ordered_kernel(gpu, scene_name):
     scene.depth_compare, scene.depth_write = "not-equal", True
     scene.name += "_not_equal_write"
     _compare(scene, gpu)
+
+
+@pytest.mark.parametrize("fmt", ["rgba8unorm", "rgba8unorm-srgb", "bgra8unorm", "bgra8unorm-srgb", "r8unorm", "rg8unorm", "rgba8snorm"])
+@pytest.mark.parametrize("size", [(256, 192), (250, 190)])
+def test_color_target_formats(gpu, fmt, size):
+    """TexelWriter::from_color (texture.rs:373-411): every colour target format the reference can write, incl. the
+    1- and 2-byte ones (per-texel stores instead of the staged TMA write-back) and Rgba8Snorm, which the reference
+    encodes like unorm; widths that are and are not a multiple of 4 texels."""
+    _compare(S.random_triangles(size[0], size[1], count=200, seed=17, color_format=fmt), gpu)
+
+
+@pytest.mark.parametrize("addr", [("clamp-to-edge", "clamp-to-edge"), ("repeat", "mirror-repeat"), ("mirror-repeat", "clamp-to-edge"),
+                                  ("mirror-repeat", "repeat")])
+def test_sampler_address_modes(gpu, addr):
+    """texel_coordinate (binding.rs:151-164): ClampToEdge / Repeat / MirrorRepeat per axis, uv up to 5 (hello_texture.rs:651-659)."""
+    scene = S.hello_texture(320, 200)
+    key = [k for k, v in scene.bindings.items() if v[0] == "sampler"][0]
+    scene.bindings[key] = ("sampler", addr[0], addr[1])
+    scene.name += f"_{addr[0]}_{addr[1]}"
+    _compare(scene, gpu)
