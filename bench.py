@@ -375,6 +375,16 @@ def main():
                 "frame_algorithmic_bytes": int(scene.algorithmic_bytes()),
                 "frame_hbm_frac": scene.algorithmic_bytes() * passes_per_step / (dev_ms * 1e-3) / 1e9 / peak if dev_ms > 0 else None}
 
+    if args.config == "c4":
+        # C4 is FP32-ALU bound.  shaders/procedural.wgsl: 12 flops per iteration x 64 iterations + 12 outside the
+        # loop per pixel; no FMA contraction is allowed (bit-exactness), so the peak is one FP32 operation per lane and clock
+        flops_px = 12 * 64 + 12
+        sm_clock = 1.965e9
+        alu_peak = 148 * 128 * sm_clock / 1e12
+        alu = flops_px * W * (row1 - row0) / (tile_launch_ms * 1e-3) / 1e12 if tile_ms > 0 else 0.0
+        roofline["alu"] = {"bound": "fp32 (no FMA)", "achieved": alu, "peak": alu_peak, "unit": "TFLOP/s", "frac": alu / alu_peak,
+                           "flops_per_pixel": flops_px, "peak_source": "148 SMs x 128 lanes x 1.965 GHz x 1 op (FMA contraction is off)"}
+
     cb = None
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_baseline(scene)     # C5: one frame of the batch (the frames differ only in the camera)
