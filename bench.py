@@ -281,7 +281,7 @@ def main():
 
     # ---- e2e: host buffers in, colour target out, every step ----
     e2e = None
-    if not args.no_e2e and world == 1 and cameras is None:
+    if not args.no_e2e and cameras is None and (world == 1 or args.present == "peer"):
         pinned = []
         for vb in scene.vertex_buffers:
             t = torch.empty(vb.nbytes, dtype=torch.uint8, pin_memory=True)
@@ -304,7 +304,9 @@ def main():
         # double-buffered: step k+1's inputs upload on the backend's copy stream (wgb_queue_write_buffer from
         # pinned memory) while step k renders and its colour target is read back; every step still uploads one
         # full input set, renders it and reads the frame
-        sets = [r, SceneRenderer(dev, queue, scene, use_emitted=use_emitted)]
+        # (N > 1: every rank uploads the whole scene over its own PCIe link -- geometry is replicated in a sort-first
+        # partition -- renders its band into the presenter's target, and rank 0 reads the frame back)
+        sets = [r, SceneRenderer(dev, queue, scene, use_emitted=use_emitted, target=target)]
         frame_host = torch.empty(d2h, dtype=torch.uint8, pin_memory=True)
 
         def upload(rr):
@@ -322,20 +324,25 @@ def main():
             cur, nxt = sets[k % 2], sets[(k + 1) % 2]
             upload(nxt)
             cur.render()
-            return cur.target.read(out=frame_host.numpy())
+            gather()
+            return cur.target.read(out=frame_host.numpy()) if rank == 0 else None
 
         upload(sets[0])
         for k in range(2):
             e2e_step(k)
         n_e2e = max(4, min(args.steps, 10)) & ~1
-        torch.cuda.synchronize()
+        barrier()
         t1 = time.perf_counter()
         for k in range(n_e2e):
             img = e2e_step(k)
         dev.poll(True)
-        torch.cuda.synchronize()
+        barrier()
         de = time.perf_counter() - t1
-        e2e = {"value": prims * n_e2e / de / 1e6, "unit": "Mtri/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        if world > 1:
+            tmax = torch.tensor([de], device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            de = float(tmax.item())
+        e2e = {"value": prims * n_e2e / de / 1e6, "unit": "Mtri/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h),
                "ms_per_step": de / n_e2e * 1e3, "steps": n_e2e,
                "pipelining": "inputs of step k+1 upload on the copy stream while step k renders (two resident input sets)"}
 
