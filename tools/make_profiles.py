@@ -107,6 +107,16 @@ def main():
       f"compare shares), `r01_ncu_full_c3_{tag}.json` (`ncu --set full --clock-control none --import-source on`, one launch of each "
       f"kernel of a pass), `r01_ptxas_{tag}.log` (`ptxas -v` of the kernels as cross-compiled by `build()`). Earlier files in this "
       f"directory (v1, v5) are kept for the history of the round.\n")
+    w("Commands (one `gpurun` call on a fresh B200, `tools/gpu.sh`):\n\n```\n"
+      "python bench.py --steps 50 --warmup 5 > gpurun_out/bench_final.json\n"
+      "python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.json\n"
+      "ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_final.csv \\\n"
+      "    python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e\n"
+      "(cd wgpu-cpu_b200/csrc && ncu --set full --import-source on --clock-control none -k regex:wgb_ -s 12 -c 4 \\\n"
+      "    -o gpurun_out/prof_final python ../../bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e)\n"
+      "python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\\n"
+      "    bench.py --gpus N --steps 50 --warmup 5        # N = 2, 4, 8 (gpurun --gpus 8)\n"
+      "python tools/make_profiles.py <tag>                 # this file\n```\n")
     w("## bench.py\n\n| | |\n|---|---|")
     w(f"| value | {bench['value']:.0f} Mtri/s ({bench['ms_per_step']:.3f} ms/pass; device {bench['device_ms_per_step']:.3f} ms = "
       f"geometry stage {bench['geometry_ms']:.3f} + tile {bench['tile_ms']:.3f}) |")
