@@ -95,3 +95,21 @@ def test_unsupported_wgsl_is_rejected_with_a_message(src, fragment):
     with pytest.raises(api.WgpuError) as e:
         api.translate_wgsl(src, api.STAGE_FRAGMENT, "fs_main")
     assert fragment in str(e.value)
+
+
+def test_array_length_translates():
+    """Expression::ArrayLength (SURVEY 2.3; tests.rs:997-1103): (bound size - array offset) / element stride."""
+    from wgpu_cpu_b200 import api
+    src = """
+struct Output { @builtin(position) p: vec4f, @location(0) @interpolate(flat) output: u32, }
+@group(0) @binding(0) var<storage, read> what_len_is_this_array: array<i32>;
+struct Tail { head: vec4f, items: array<vec3f>, }
+@group(1) @binding(2) var<storage, read> tail: Tail;
+@vertex fn main() -> Output { return Output(vec4f(), arrayLength(&what_len_is_this_array) + arrayLength(&tail.items)); }
+"""
+    cu = api.translate_wgsl(src, api.STAGE_VERTEX, "main")
+    assert "wgb_array_length(wgb, 0, 0, 0u, 4u)" in cu and "wgb_array_length(wgb, 1, 2, 16u, 16u)" in cu
+    assert "struct Tail { vec4f head; };" in cu
+    import pytest
+    with pytest.raises(api.WgpuError):
+        api.translate_wgsl(src.replace("arrayLength(&tail.items)", "arrayLength(&tail.head)"), api.STAGE_VERTEX, "main")

@@ -17,7 +17,7 @@ def gpu():
     return dev, queue
 
 
-def evaluate(dev, queue, wgsl: str) -> float:
+def evaluate(dev, queue, wgsl: str, bind_group_entries=None) -> float:
     module = dev.create_shader_module(wgsl)
     pipe = dev.create_render_pipeline(vertex_module=module, fragment_module=module,
                                       depth_stencil={"depth_compare": "always", "depth_write_enabled": True},
@@ -28,6 +28,8 @@ def evaluate(dev, queue, wgsl: str) -> float:
     with enc.begin_render_pass([{"view": color.create_view(), "load": ("clear", (0, 0, 0, 0))}],
                                {"view": depth.create_view(), "depth_load": ("clear", 0.0)}) as rp:
         rp.set_pipeline(pipe)
+        if bind_group_entries:
+            rp.set_bind_group(0, dev.create_bind_group(None, bind_group_entries))
         rp.draw(range(0, 3))
     idx = queue.submit([enc.finish()])
     dev.poll(True, idx)
@@ -43,3 +45,24 @@ def test_wgsl_case(gpu, case):
     dev, queue = gpu
     got = evaluate(dev, queue, module_for(case))
     assert got == np.float32(case[4]), f"{case[0]}: got {got!r}, expected {case[4]!r}"
+
+
+def test_array_length_of_storage_bindings(gpu):
+    """tests.rs:997-1103 `array_length`: a storage buffer of 123 i32 reports 123; also the runtime-sized tail of a
+    struct (offset 16, vec3f stride 16) and element reads through both."""
+    from wgpu_cpu_b200 import api
+    dev, queue = gpu
+    ints = np.full(123, 42, dtype=np.int32)
+    ints[2] = 7
+    tail = np.zeros(4 + 4 * 9, dtype=np.float32)            # head vec4f + 9 x vec3f (stride 16)
+    tail[4 + 4 * 1 + 1] = 5.0                               # items[1].y
+    a = dev.create_buffer_init(ints, api.BUFFER_USAGE["STORAGE"])
+    b = dev.create_buffer_init(tail, api.BUFFER_USAGE["STORAGE"])
+    case = ("array_length",
+            "@group(0) @binding(0) var<storage, read> what_len_is_this_array: array<i32>;\n"
+            "struct Tail { head: vec4f, items: array<vec3f>, }\n"
+            "@group(0) @binding(1) var<storage, read> tail: Tail;",
+            "let n = arrayLength(&what_len_is_this_array); let m = arrayLength(&tail.items);",
+            "f32(n) + 1000.0 * f32(m) + 0.25 * tail.items[1].y + 0.125 * f32(what_len_is_this_array[2])", 0.0)
+    got = evaluate(dev, queue, module_for(case), [{"binding": 0, "buffer": a}, {"binding": 1, "buffer": b}])
+    assert got == np.float32(123 + 9000 + 1.25 + 0.875)

@@ -370,6 +370,11 @@ WGB_DEV vec4f wgb_reflect(vec4f e, vec4f n) { return e - n * __fmul_rn(2.0f, wgb
 // ---------------------------------------------------------------------------------------
 // resources
 // ---------------------------------------------------------------------------------------
+// arrayLength(&binding.array): elements that fit between the array's offset and the end of the bound range
+WGB_DEV u32 wgb_array_length(const WgbDraw& d, int g, int b, u32 offset, u32 stride) {
+    const u32 size = d.res[g][b].a;
+    return size > offset ? (size - offset) / stride : 0u;
+}
 // uniform / storage loads: `offset` is the WGSL-layout byte offset computed by the emitter
 template <class T> WGB_DEV T wgb_load(const WgbDraw& d, int group, int binding, u32 offset);
 template <> WGB_DEV f32 wgb_load<f32>(const WgbDraw& d, int g, int b, u32 off) {

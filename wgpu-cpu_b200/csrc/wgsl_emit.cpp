@@ -445,7 +445,8 @@ struct Parser {
         const int line = cur().line;
         for (const char* op : {"-", "!", "~"})
             if (is(op)) { p++; auto e = mk(Expr::Unary, line); e->name = op; e->args.push_back(unary()); return e; }
-        if (is("&") || is("*")) err(line, "pointers are not supported");
+        if (is("&")) { p++; auto e = mk(Expr::Unary, line); e->name = "&"; e->args.push_back(unary()); return e; }   // arrayLength(&buffer.array) only
+        if (is("*")) err(line, "pointers are not supported");
         return postfix();
     }
     ExprP binary_level(int level) {
@@ -894,6 +895,7 @@ struct Emitter {
                 err(line, "unknown identifier '" + e->name + "'");
             }
             case Expr::Unary: {
+                if (e->name == "&") err(line, "pointers are not supported (except arrayLength(&runtime_sized_array))");
                 Val a = expr(e->args[0]);
                 Val v; v.t = a.t;
                 if (a.is_const_num && e->name == "-") { v.is_const_num = true; v.num = -a.num; v.s = lit_text(v, v.t, line); return v; }
@@ -1231,6 +1233,19 @@ struct Emitter {
             v.s = "wgb_texture_load(wgb, " + std::to_string(tg->group) + ", " + std::to_string(tg->binding) + ", " + c.s + ")";
             return v;
         }
+        if (name == "arrayLength") {
+            // Expression::ArrayLength: elements of the runtime-sized array at the end of a storage binding,
+            // from the bound size -- (binding size - offset of the array) / element stride
+            if (e->args.size() != 1 || e->args[0]->k != Expr::Unary || e->args[0]->name != "&") err(line, "arrayLength takes a pointer to a runtime-sized array");
+            const Global* g = nullptr; uint32_t off = 0; std::string dyn; Type ty;
+            if (!resource_chain(e->args[0]->args[0], g, off, dyn, ty) || ty.k != Type::Array || ty.count != 0 || !dyn.empty())
+                err(line, "arrayLength takes a pointer to a runtime-sized array of a storage buffer");
+            uint32_t a, sz; layout_of(*ty.elem, a, sz, line);
+            const uint32_t stride = (sz + a - 1) / a * a;
+            Val v; v.t = T(Type::U32);
+            v.s = "wgb_array_length(wgb, " + std::to_string(g->group) + ", " + std::to_string(g->binding) + ", " + std::to_string(off) + "u, " + std::to_string(stride) + "u)";
+            return v;
+        }
         for (auto& a : e->args) args.push_back(expr(a));
         if (name == "select") {
             if (args.size() != 3) err(line, "select needs 3 arguments");
@@ -1241,7 +1256,6 @@ struct Emitter {
             Val v; v.t = rt; v.s = "wgb_select(" + f.s + ", " + t.s + ", " + c.s + ")";
             return v;
         }
-        if (name == "arrayLength") err(line, "arrayLength needs pointers, which are not supported");
         // math builtins (all todo!() in the reference, expression/math.rs:23,29)
         struct B { const char* name; int nargs; int ret; };   // ret: 0 same as arg0, 1 scalar of arg0, 2 bool, 3 vec3
         static const B table[] = {
@@ -1544,7 +1558,10 @@ struct Emitter {
             if (kind == "s:") {
                 for (auto& sd : m.structs) if (sd->name == name) {
                     out += "struct " + sd->name + " {";
-                    for (auto& mb : sd->members) out += " " + cuda_type(mb.type, mb.line) + " " + mb.name + ";";
+                    for (auto& mb : sd->members) {
+                        if (mb.type.k == Type::Array && mb.type.count == 0) continue;   // a runtime-sized tail lives in the buffer only (reached through access chains)
+                        out += " " + cuda_type(mb.type, mb.line) + " " + mb.name + ";";
+                    }
                     out += " };\n";
                 }
             } else if (kind == "g:") {
