@@ -83,6 +83,26 @@ CASES = [
     ("vec_vec", "", "var a = vec3f(1,2,3); var b = vec3f(4,5,6); let o = a * b + a;", "o.x + o.y + o.z", 38.0),
     # tests.rs:1372-1401 private matrix init
     ("private_matrix", "var<private> pm: mat4x4f = mat4x4f(vec4f(1,0,0,0), vec4f(0,2,0,0), vec4f(0,0,3,0), vec4f(0,0,0,4));", "", "pm[1].y + pm[3].w", 6.0),
+    # tests.rs:361-375 early_return / if_early_return (here through a helper: the harness returns `expr` after the body)
+    ("early_return", "fn f() -> u32 { return 456u; return 123u; }", "let x = f();", "f32(x)", 456.0),
+    ("if_early_return", "fn f() -> u32 { var c: bool = true; if c { return 456u; } return 123u; }", "let x = f();", "f32(x)", 456.0),
+    # tests.rs:613-648 switch_break: statements after `break` are dead
+    ("switch_break", "", "var a: i32 = 3; var b: i32; switch a { case 1: { b = 2; } case 2, 3: { b = 3; break; b = 123; } case 4, 5, 6: { b = 4; } default: { b = 12; } }",
+     "f32(b)", 3.0),
+    # tests.rs:762-789 insert_lane_into_i32x2_bug: vec2i(a, b) from two variables = [1, 2]
+    ("vec2i_from_vars", "", "var a = 1; var b = 2; let v = vec2i(a, b);", "f32(v.x * 10 + v.y)", 12.0),
+    # tests.rs:928-971 access_global_variable_array_in_bounds_static / _dynamic
+    ("private_array_static", "var<private> foo: array<i32, 4> = array<i32, 4>(4, 5, 6, 7);", "var out = foo[2];", "f32(out)", 6.0),
+    ("private_array_dynamic", "var<private> foo: array<i32, 4> = array<i32, 4>(4, 5, 6, 7);",
+     "var out = 0; for (var i = 0; i < 4; i += 1) { out += foo[i]; }", "f32(out)", 22.0),
+    # tests.rs:1156-1196 vector_access_dynamic / _static = 340
+    ("vec4i_dynamic", "", "var v: vec4i = vec4i(12, 23, 34, 45); var s: i32 = 0; for (var i = 0; i < 4; i += 1) { s += (i + 1) * v[i]; }", "f32(s)", 340.0),
+    ("vec4i_static", "", "var v: vec4i = vec4i(12, 23, 34, 45); var s: i32 = v.x + 2 * v.y + 3 * v.z + 4 * v.w;", "f32(s)", 340.0),
+    # tests.rs:1199-1223 vectorized_function_argument
+    ("vector_argument", "fn do_stuff(input: vec4i) -> i32 { return input.y; }", "let output = do_stuff(vec4i(1, 2, 3, 4));", "f32(output)", 2.0),
+    # tests.rs:1226-1284 return_if_else_diverging / return_from_loop_body_diverging
+    ("return_if_else", "fn do_stuff(x: i32) -> i32 { if x == 1234 { return 45; } else { return 67; } }", "let output = do_stuff(1234);", "f32(output)", 45.0),
+    ("return_from_loop", "fn do_stuff() -> i32 { loop { return 45; } return 123; }", "let output = do_stuff();", "f32(output)", 45.0),
     # ---- beyond the reference's JIT (todo!() there): swizzle, splat, math, vector compare, mat*mat ----
     ("swizzle", "", "var v = vec4f(1.0, 2.0, 3.0, 4.0); let s = v.zyx; let t = v.xy;", "s.x * 100.0 + s.z * 10.0 + t.y", 312.0),
     ("swizzle_rgba", "", "var v = vec4f(1.0, 2.0, 3.0, 4.0); let s = v.bgr;", "s.x + s.z * 10.0", 13.0),
