@@ -207,3 +207,27 @@ def test_unknown_feature_bits_are_rejected():
         adapter.request_device(api.CUDA_DEVICE_COMPILE_ONLY, features=1 << 20)
     dev, _ = adapter.request_device(api.CUDA_DEVICE_COMPILE_ONLY, features=sum(api.FEATURE.values()))
     assert dev is not None
+
+
+def test_ordered_variants_compile_offline():
+    """The ordered tile kernel (NotEqual + depth write in parity mode; blending on a WGB_FEATURE_BLEND device) is a
+    separate variant of the pipeline translation unit: translate + NVRTC-compile it without a GPU."""
+    adapter = api.instance().request_adapter()
+    dev, _ = adapter.request_device(api.CUDA_DEVICE_COMPILE_ONLY, features=api.FEATURE["BLEND"] | api.FEATURE["COLOR_WRITE_MASK"])
+    m = dev.create_shader_module(shaders.wgsl("hello_mesh"))
+    vbs = [{"array_stride": 32, "attributes": [("float32x4", 0, 0), ("float32x4", 16, 1)]}]
+    blend = {"color": ("src-alpha", "one-minus-src-alpha", "add"), "alpha": ("one", "one-minus-dst-alpha", "reverse-subtract")}
+    p = dev.create_render_pipeline(vertex_module=m, fragment_module=m, vertex_buffers=vbs, depth_stencil={"depth_compare": "less"},
+                                   targets=[{"format": "bgra8unorm-srgb", "blend": blend, "write_mask": 7}])
+    src = p.get_source()
+    assert "#define WGB_RESOLVE 7" in src
+    assert "t == 0 ? (f == 0 ? 1 : f == 1 ? 4 : f == 2 ? 5 : f == 3 ? 0 : f == 4 ? 1 : f == 5 ? 9 : 2)" in src
+    # the same state on a device without the feature: blend ignored, closed-form kernel (Less + write = MIN_FIRST)
+    dev0, _ = adapter.request_device(api.CUDA_DEVICE_COMPILE_ONLY)
+    m0 = dev0.create_shader_module(shaders.wgsl("hello_mesh"))
+    p0 = dev0.create_render_pipeline(vertex_module=m0, fragment_module=m0, vertex_buffers=vbs, depth_stencil={"depth_compare": "less"},
+                                     targets=[{"format": "bgra8unorm-srgb", "blend": blend, "write_mask": 7}])
+    assert "#define WGB_RESOLVE 1" in p0.get_source()
+    pn = dev0.create_render_pipeline(vertex_module=m0, fragment_module=m0, vertex_buffers=vbs, targets=["rgba8unorm"],
+                                     depth_stencil={"depth_compare": "not-equal", "depth_write_enabled": True})
+    assert "#define WGB_RESOLVE 7" in pn.get_source()

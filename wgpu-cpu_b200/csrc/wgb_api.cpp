@@ -896,8 +896,10 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             dev->last_stats.tile_ms += t_ms;
             dev->last_stats.total_ms += g_ms + t_ms;
             if (dev->bin_cap_hint.size() > 4096) dev->bin_cap_hint.clear();
-            if (c.max_tile_pairs)
-                dev->bin_cap_hint[std::make_pair(np, band_tiles)] = (uint32_t)std::min<uint64_t>((uint64_t)c.max_tile_pairs * 5 / 4 + 64, 0xFFFFFF00ull);
+            if (c.max_tile_pairs) {     // never shrinks: draws of one shape whose fullest tile varies (a moving camera) must not alternate between overflow and replay
+                uint32_t& hint = dev->bin_cap_hint[std::make_pair(np, band_tiles)];
+                hint = std::max<uint32_t>(hint, (uint32_t)std::min<uint64_t>((uint64_t)c.max_tile_pairs * 5 / 4 + 64, 0xFFFFFF00ull));
+            }
             if (c.status & (WGB_STATUS_CLIP_OVERFLOW | WGB_STATUS_BIG_OVERFLOW | WGB_STATUS_BIN_OVERFLOW)) {
                 // the tile kernel saw the flag and left the attachments untouched: grow and replay
                 if (attempt >= 8) fail(WGB_ERROR_OUT_OF_MEMORY, "work buffers still too small after %d replays", attempt);
