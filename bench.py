@@ -246,8 +246,8 @@ def main():
             if acc is None:
                 acc = dict(st)
             else:
-                for k in ("primitives", "fragments", "shaded", "bin_pairs", "big_primitives", "clipped_primitives", "clip_records",
-                          "kernel_launches", "geometry_ms", "tile_ms", "total_ms"):
+                for k in ("primitives", "fragments", "shaded", "bin_pairs", "hiz_culled", "big_primitives", "clipped_primitives", "clip_records",
+                          "kernel_launches", "replays", "geometry_ms", "tile_ms", "total_ms"):
                     acc[k] += st[k]
         return acc
 
