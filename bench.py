@@ -55,40 +55,86 @@ def measured_peak_hbm():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  Samples through NVML every
+    few milliseconds from a thread (the timed region of a millisecond-frame benchmark is shorter than nvidia-smi's
+    start-up time); falls back to an `nvidia-smi -lms` subprocess when the NVML module is unavailable.  The sampler
+    runs from before the warm-up; `mark()` opens and `stop()` closes the window whose samples are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml = index, [], None, None     # rows: (time, sm_mhz, max_mhz, {reasons})
+        self.t_mark, self.running = None, False
 
     def start(self):
+        self.running = True
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index))
+            threading.Thread(target=self._poll_nvml, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            threading.Thread(target=self._read_smi, daemon=True).start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        nv, h = self.nvml
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while self.running:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((time.perf_counter(), sm, mx, {name for bit, name in self.REASONS if bits & bit}))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            r = [c.strip() for c in line.split(",")]
+            if len(r) >= 9 and r[1].replace(".", "").isdigit():
+                reasons = {name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9])
+                           if v.lower().startswith("active")}
+                self.rows.append((time.perf_counter(), float(r[1]), float(r[2]) if r[2].replace(".", "").isdigit() else None, reasons))
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        t_end = time.perf_counter()
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"], "samples": 0}
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+        self.running = False
+        t0 = self.t_mark if self.t_mark is not None else 0.0
+        inside = [r for r in self.rows if t0 <= r[0] <= t_end]
+        note = None
+        if not inside and self.rows:        # a window shorter than the sampling period: the samples next to it (still under load: warm-up precedes it)
+            inside = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t_end)))[:2]
+            note = "timed window shorter than the sampling period: nearest samples"
+        sm = [r[1] for r in inside]
+        mx = [r[2] for r in inside if r[2] is not None]
+        reasons = set().union(*[r[3] for r in inside]) if inside else set()
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+        if note:
+            out["note"] = note
+        return out
 
 
 def cpu_baseline(scene, budget_s: float = 25.0) -> dict:
@@ -251,15 +297,16 @@ def main():
                     acc[k] += st[k]
         return acc
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(warm):
         step()
     if cameras is None:
         recorded.extend(r.encode() for _ in range(args.steps))
 
     # ---- timed: K passes, inputs resident in HBM ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.mark()
     t0 = time.perf_counter()
     stats = []
     for _ in range(args.steps):
