@@ -1,0 +1,33 @@
+"""examples/hello_mesh (C++ host over the C ABI, the reference's hello_mesh.rs flow) renders the teapot bit-exactly:
+raw colour and depth against the CPU oracle, and the dumped PNG against the raw colour."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from wgpu_cpu_b200 import scenes as S
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_host_renders_hello_mesh(tmp_path):
+    from oracle import pyoracle
+    from tests.test_c_abi import _decode_png
+    scene = S.hello_mesh(256, 192)
+    ref = pyoracle.render(scene, want_coverage=False)
+    (tmp_path / "v.bin").write_bytes(scene.vertex_buffers[0].tobytes())
+    (tmp_path / "i.bin").write_bytes(scene.index_data.astype(np.uint32).tobytes())
+    (tmp_path / "u.bin").write_bytes(np.ascontiguousarray(scene.bindings[(0, 0)][1]).tobytes())
+    out = str(tmp_path / "frame")
+    p = subprocess.run([os.path.join(ROOT, "examples", "hello_mesh"), os.path.join(ROOT, "wgpu-cpu_b200", "shaders", "hello_mesh.wgsl"),
+                        str(tmp_path / "v.bin"), str(tmp_path / "i.bin"), str(tmp_path / "u.bin"), "256", "192", out],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert f"primitives {scene.num_primitives}" in p.stdout
+    color = np.fromfile(out + ".rgba", dtype=np.uint8).reshape(192, 256, 4)
+    depth = np.fromfile(out + ".depth", dtype=np.float32).reshape(192, 256)
+    assert np.array_equal(color, ref.color)
+    assert np.array_equal(depth.view(np.uint32), ref.depth.view(np.uint32))
+    assert np.array_equal(_decode_png(out + ".png"), color)
