@@ -327,6 +327,45 @@ WGB_LIFT2(wgb_min, i, i32) WGB_LIFT2(wgb_max, i, i32) WGB_LIFT2(wgb_min, u, u32)
     WGB_DEV vec3##S FN(vec3##S a, T b, T c) { return vec3##S(FN(a.x, b, c), FN(a.y, b, c), FN(a.z, b, c)); } \
     WGB_DEV vec4##S FN(vec4##S a, T b, T c) { return vec4##S(FN(a.x, b, c), FN(a.y, b, c), FN(a.z, b, c), FN(a.w, b, c)); }
 WGB_LIFT3(wgb_clamp, f, f32) WGB_LIFT3(wgb_clamp, i, i32) WGB_LIFT3(wgb_clamp, u, u32) WGB_LIFT3(wgb_fma, f, f32)
+// ---- integer bit builtins (WGSL 17.5.x; all `todo!()` in the reference with the rest of Math) ----
+WGB_DEV u32 wgb_countOneBits(u32 a) { return (u32)__popc(a); }
+WGB_DEV i32 wgb_countOneBits(i32 a) { return __popc((u32)a); }
+WGB_DEV u32 wgb_countLeadingZeros(u32 a) { return (u32)__clz((int)a); }
+WGB_DEV i32 wgb_countLeadingZeros(i32 a) { return __clz(a); }
+WGB_DEV u32 wgb_countTrailingZeros(u32 a) { return a == 0u ? 32u : (u32)(__ffs((int)a) - 1); }
+WGB_DEV i32 wgb_countTrailingZeros(i32 a) { return a == 0 ? 32 : __ffs(a) - 1; }
+WGB_DEV u32 wgb_firstLeadingBit(u32 a) { return a == 0u ? 0xFFFFFFFFu : 31u - (u32)__clz((int)a); }
+WGB_DEV i32 wgb_firstLeadingBit(i32 a) { return (a == 0 || a == -1) ? -1 : 31 - __clz(a < 0 ? ~a : a); }
+WGB_DEV u32 wgb_firstTrailingBit(u32 a) { return a == 0u ? 0xFFFFFFFFu : (u32)(__ffs((int)a) - 1); }
+WGB_DEV i32 wgb_firstTrailingBit(i32 a) { return a == 0 ? -1 : __ffs(a) - 1; }
+WGB_DEV u32 wgb_reverseBits(u32 a) { return __brev(a); }
+WGB_DEV i32 wgb_reverseBits(i32 a) { return (i32)__brev((u32)a); }
+WGB_DEV u32 wgb_extractBits(u32 e, u32 offset, u32 count) {
+    const u32 o = offset < 32u ? offset : 32u, c = count < 32u - o ? count : 32u - o;
+    return c == 0u ? 0u : (e >> o) & (c == 32u ? 0xFFFFFFFFu : (1u << c) - 1u);
+}
+WGB_DEV i32 wgb_extractBits(i32 e, u32 offset, u32 count) {
+    const u32 o = offset < 32u ? offset : 32u, c = count < 32u - o ? count : 32u - o;
+    return c == 0u ? 0 : ((i32)((u32)e << (32u - c - o))) >> (32u - c);          // sign-extends
+}
+WGB_DEV u32 wgb_insertBits(u32 e, u32 newbits, u32 offset, u32 count) {
+    const u32 o = offset < 32u ? offset : 32u, c = count < 32u - o ? count : 32u - o;
+    if (c == 0u) return e;
+    const u32 mask = (c == 32u ? 0xFFFFFFFFu : (1u << c) - 1u) << o;
+    return (e & ~mask) | ((newbits << o) & mask);
+}
+WGB_DEV i32 wgb_insertBits(i32 e, i32 newbits, u32 offset, u32 count) { return (i32)wgb_insertBits((u32)e, (u32)newbits, offset, count); }
+WGB_LIFT1(wgb_countOneBits, i) WGB_LIFT1(wgb_countOneBits, u) WGB_LIFT1(wgb_countLeadingZeros, i) WGB_LIFT1(wgb_countLeadingZeros, u)
+WGB_LIFT1(wgb_countTrailingZeros, i) WGB_LIFT1(wgb_countTrailingZeros, u) WGB_LIFT1(wgb_firstLeadingBit, i) WGB_LIFT1(wgb_firstLeadingBit, u)
+WGB_LIFT1(wgb_firstTrailingBit, i) WGB_LIFT1(wgb_firstTrailingBit, u) WGB_LIFT1(wgb_reverseBits, i) WGB_LIFT1(wgb_reverseBits, u)
+#define WGB_LIFT_BITS(S)                                                                            \
+    WGB_DEV vec2##S wgb_extractBits(vec2##S e, u32 o, u32 c) { return vec2##S(wgb_extractBits(e.x, o, c), wgb_extractBits(e.y, o, c)); } \
+    WGB_DEV vec3##S wgb_extractBits(vec3##S e, u32 o, u32 c) { return vec3##S(wgb_extractBits(e.x, o, c), wgb_extractBits(e.y, o, c), wgb_extractBits(e.z, o, c)); } \
+    WGB_DEV vec4##S wgb_extractBits(vec4##S e, u32 o, u32 c) { return vec4##S(wgb_extractBits(e.x, o, c), wgb_extractBits(e.y, o, c), wgb_extractBits(e.z, o, c), wgb_extractBits(e.w, o, c)); } \
+    WGB_DEV vec2##S wgb_insertBits(vec2##S e, vec2##S n, u32 o, u32 c) { return vec2##S(wgb_insertBits(e.x, n.x, o, c), wgb_insertBits(e.y, n.y, o, c)); } \
+    WGB_DEV vec3##S wgb_insertBits(vec3##S e, vec3##S n, u32 o, u32 c) { return vec3##S(wgb_insertBits(e.x, n.x, o, c), wgb_insertBits(e.y, n.y, o, c), wgb_insertBits(e.z, n.z, o, c)); } \
+    WGB_DEV vec4##S wgb_insertBits(vec4##S e, vec4##S n, u32 o, u32 c) { return vec4##S(wgb_insertBits(e.x, n.x, o, c), wgb_insertBits(e.y, n.y, o, c), wgb_insertBits(e.z, n.z, o, c), wgb_insertBits(e.w, n.w, o, c)); }
+WGB_LIFT_BITS(i) WGB_LIFT_BITS(u)
 WGB_DEV vec2f wgb_mix(vec2f a, vec2f b, vec2f t) { return vec2f(wgb_mix(a.x, b.x, t.x), wgb_mix(a.y, b.y, t.y)); }
 WGB_DEV vec3f wgb_mix(vec3f a, vec3f b, vec3f t) { return vec3f(wgb_mix(a.x, b.x, t.x), wgb_mix(a.y, b.y, t.y), wgb_mix(a.z, b.z, t.z)); }
 WGB_DEV vec4f wgb_mix(vec4f a, vec4f b, vec4f t) { return vec4f(wgb_mix(a.x, b.x, t.x), wgb_mix(a.y, b.y, t.y), wgb_mix(a.z, b.z, t.z), wgb_mix(a.w, b.w, t.w)); }

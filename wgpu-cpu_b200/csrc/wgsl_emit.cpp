@@ -1256,6 +1256,25 @@ struct Emitter {
             Val v; v.t = rt; v.s = "wgb_select(" + f.s + ", " + t.s + ", " + c.s + ")";
             return v;
         }
+        // integer bit builtins: same type in and out; offsets / counts are u32
+        {
+            static const char* bit1[] = {"countOneBits", "countLeadingZeros", "countTrailingZeros", "firstLeadingBit", "firstTrailingBit", "reverseBits"};
+            bool is_bit1 = false;
+            for (const char* b : bit1) is_bit1 = is_bit1 || name == b;
+            if (is_bit1 || name == "extractBits" || name == "insertBits") {
+                const size_t want_n = is_bit1 ? 1 : name == "extractBits" ? 3 : 4;
+                if (args.size() != want_n) err(line, name + " takes " + std::to_string(want_n) + " argument(s)");
+                Val e0 = concrete(args[0], line);
+                const Type::K sk = e0.t.scalar().k;
+                if (sk != Type::I32 && sk != Type::U32) err(line, name + " needs integer arguments");
+                std::string s = "wgb_" + name + "(" + e0.s;
+                size_t k = 1;
+                if (name == "insertBits") { s += ", " + coerce(args[1], e0.t, line).s; k = 2; }
+                for (; k < args.size(); k++) s += ", " + coerce(args[k], T(Type::U32), line).s;
+                Val v; v.t = e0.t; v.s = s + ")";
+                return v;
+            }
+        }
         // math builtins (all todo!() in the reference, expression/math.rs:23,29)
         struct B { const char* name; int nargs; int ret; };   // ret: 0 same as arg0, 1 scalar of arg0, 2 bool, 3 vec3
         static const B table[] = {
