@@ -23,6 +23,6 @@ def test_example_reports_the_missing_device():
     import torch
     if torch.cuda.is_available():
         pytest.skip("a CUDA device is present")
-    wgsl = os.path.join(ROOT, "wgpu-cpu_b200", "shaders", "hello_mesh.wgsl")
+    wgsl = os.path.join(ROOT, "wgpu-cpu_b200", "shaders", "mesh_vertex_color.wgsl")
     p = subprocess.run([EXAMPLE, wgsl, os.devnull, os.devnull, os.devnull, "64", "64", "/tmp/wgb_example"], capture_output=True, text=True)
     assert p.returncode == 1 and "no CPU fallback" in p.stderr

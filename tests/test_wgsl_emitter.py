@@ -16,7 +16,7 @@ def test_arithmetic_contract_in_emitted_text():
     """One IEEE operation per operator, never a*b+c: scalar float operators become wgb_* calls, and the
     camera transform is the prelude's column-accumulating operator* (binary.rs:297-323)."""
     vs = shaders.emitted("hello_mesh", "vs")
-    assert "wgb_load<mat4x4f>(wgb, 0, 0, 0u) * input.vertex_position" in vs
+    assert "wgb_load<mat4x4f>(wgb, 0, 0, 0u) * object_position" in vs
     fs = shaders.emitted("procedural", "fs")
     assert "wgb_add(wgb_sub(wgb_mul(zx, zx), wgb_mul(zy, zy)), cx)" in fs
     assert "wgb_add(wgb_mul(wgb_mul(2.0f, zx), zy), cy)" in fs

@@ -1,16 +1,14 @@
 // wgsl2cuda: stage=fragment entry=fs_main
 namespace wgb_fragment {
-struct VertexInput { vec4f vertex_position; vec4f vertex_color; };
-struct VertexOutput { vec4f position; vec4f color; };
 struct Camera { mat4x4f matrix; };
-struct FragmentOutput { f32 depth; vec4f color; };
+struct Interstage { vec4f clip; vec4f tint; };
+struct Shaded { f32 depth; vec4f tint; };
 struct WgbInvocation {
     bool killed = false;
 };
-WGB_DEV FragmentOutput fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, VertexOutput input);
-WGB_DEV FragmentOutput fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, VertexOutput input) {
-    const f32 depth = wgb_sub(1.0f, wgb_mul(input.position.z, input.color.x));
-    return FragmentOutput{depth, input.color};
+WGB_DEV Shaded fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, Interstage frag);
+WGB_DEV Shaded fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, Interstage frag) {
+    return Shaded{wgb_sub(1.0f, wgb_mul(frag.clip.z, frag.tint.x)), frag.tint};
 }
 }  // namespace wgb_fragment
 #define WGB_FS_COLOR_MASK 1
@@ -23,12 +21,12 @@ WGB_DEV constexpr int wgb_fs_interp(int slot) {
 }
 WGB_DEV bool wgb_fs_entry(const WgbDraw& wgb, const WgbFragIn& fi, const u32* vary, WgbFragOut& out) {
     wgb_fragment::WgbInvocation wgb_inv;
-    wgb_fragment::VertexOutput a0;
-    a0.position = fi.position;
-    a0.color = wgb_get<vec4f>(vary, WGB_VS_LOC0_SLOT);
-    const wgb_fragment::FragmentOutput r = wgb_fragment::fs_main(wgb, wgb_inv, a0);
+    wgb_fragment::Interstage a0;
+    a0.clip = fi.position;
+    a0.tint = wgb_get<vec4f>(vary, WGB_VS_LOC0_SLOT);
+    const wgb_fragment::Shaded r = wgb_fragment::fs_main(wgb, wgb_inv, a0);
     if (wgb_inv.killed) return false;
     out.frag_depth = r.depth;
-    out.color[0] = r.color;
+    out.color[0] = r.tint;
     return true;
 }

@@ -1,15 +1,13 @@
 // wgsl2cuda: stage=fragment entry=fs_main
 namespace wgb_fragment {
-struct VertexInput { u32 vertex_index; vec4f vertex_position; vec2f uv; };
-struct VertexOutput { vec4f position; vec2f uv; };
 struct Camera { mat4x4f matrix; };
+struct Interstage { vec4f clip; vec2f uv; };
 struct WgbInvocation {
     bool killed = false;
 };
-WGB_DEV vec4f fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, VertexOutput input);
-WGB_DEV vec4f fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, VertexOutput input) {
-    vec4f color = wgb_texture_sample(wgb, 1, 0, 1, 1, input.uv);
-    return color;
+WGB_DEV vec4f fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, Interstage frag);
+WGB_DEV vec4f fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, Interstage frag) {
+    return wgb_texture_sample(wgb, 1, 0, 1, 1, frag.uv);
 }
 }  // namespace wgb_fragment
 #define WGB_FS_COLOR_MASK 1
@@ -22,8 +20,8 @@ WGB_DEV constexpr int wgb_fs_interp(int slot) {
 }
 WGB_DEV bool wgb_fs_entry(const WgbDraw& wgb, const WgbFragIn& fi, const u32* vary, WgbFragOut& out) {
     wgb_fragment::WgbInvocation wgb_inv;
-    wgb_fragment::VertexOutput a0;
-    a0.position = fi.position;
+    wgb_fragment::Interstage a0;
+    a0.clip = fi.position;
     a0.uv = wgb_get<vec2f>(vary, WGB_VS_LOC0_SLOT);
     const vec4f r = wgb_fragment::fs_main(wgb, wgb_inv, a0);
     if (wgb_inv.killed) return false;

@@ -1,14 +1,13 @@
 // wgsl2cuda: stage=fragment entry=fs_main
 namespace wgb_fragment {
-struct VertexInput { u32 vertex_index; vec4f vertex_position; vec4f vertex_color; };
-struct VertexOutput { vec4f position; vec4f color; };
 struct Camera { mat4x4f matrix; };
+struct Interstage { vec4f clip; vec4f tint; };
 struct WgbInvocation {
     bool killed = false;
 };
-WGB_DEV vec4f fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, VertexOutput input);
-WGB_DEV vec4f fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, VertexOutput input) {
-    return input.color;
+WGB_DEV vec4f fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, Interstage frag);
+WGB_DEV vec4f fs_main(const WgbDraw& wgb, WgbInvocation& wgb_inv, Interstage frag) {
+    return frag.tint;
 }
 }  // namespace wgb_fragment
 #define WGB_FS_COLOR_MASK 1
@@ -21,9 +20,9 @@ WGB_DEV constexpr int wgb_fs_interp(int slot) {
 }
 WGB_DEV bool wgb_fs_entry(const WgbDraw& wgb, const WgbFragIn& fi, const u32* vary, WgbFragOut& out) {
     wgb_fragment::WgbInvocation wgb_inv;
-    wgb_fragment::VertexOutput a0;
-    a0.position = fi.position;
-    a0.color = wgb_get<vec4f>(vary, WGB_VS_LOC0_SLOT);
+    wgb_fragment::Interstage a0;
+    a0.clip = fi.position;
+    a0.tint = wgb_get<vec4f>(vary, WGB_VS_LOC0_SLOT);
     const vec4f r = wgb_fragment::fs_main(wgb, wgb_inv, a0);
     if (wgb_inv.killed) return false;
     out.color[0] = r;

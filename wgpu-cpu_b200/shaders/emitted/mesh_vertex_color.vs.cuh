@@ -2,7 +2,6 @@
 namespace wgb_vertex {
 struct Camera { mat4x4f matrix; };
 struct Interstage { vec4f clip; vec4f tint; };
-struct Shaded { f32 depth; vec4f tint; };
 struct WgbInvocation {
     bool killed = false;
 };
