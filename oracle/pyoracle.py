@@ -189,7 +189,10 @@ def render(scene, want_coverage: bool = True) -> Frame:
         rs.sc_x, rs.sc_y, rs.sc_w, rs.sc_h = scene.scissor
     rs.ext_features = getattr(scene, "features", 0) & 23       # depth range, write mask, sRGB encode, blend (oracle.h ORC_EXT_*)
     if getattr(scene, "blend", None):
-        from wgpu_cpu_b200.api import BLEND_FACTOR, BLEND_OPERATION
+        BLEND_FACTOR = {"zero": 0, "one": 1, "src": 2, "one-minus-src": 3, "src-alpha": 4, "one-minus-src-alpha": 5, "dst": 6,
+                        "one-minus-dst": 7, "dst-alpha": 8, "one-minus-dst-alpha": 9, "src-alpha-saturated": 10, "constant": 11,
+                        "one-minus-constant": 12}           # wgpu::BlendFactor, numbering of include/wgpu_b200.h
+        BLEND_OPERATION = {"add": 0, "subtract": 1, "reverse-subtract": 2, "min": 3, "max": 4}
         (cs, cd, co), (as_, ad, ao) = scene.blend["color"], scene.blend["alpha"]
         for k, v in enumerate([1, BLEND_FACTOR[cs], BLEND_FACTOR[cd], BLEND_OPERATION[co], BLEND_FACTOR[as_], BLEND_FACTOR[ad], BLEND_OPERATION[ao]]):
             rs.blend[0][k] = v
