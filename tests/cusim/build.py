@@ -1,0 +1,34 @@
+"""TEST INFRASTRUCTURE: builds tests/cusim/_build/libwgpu_b200_sim.so -- the host runtime source of the product
+(wgpu-cpu_b200/csrc/wgb_api.cpp, wgsl_emit.cpp, unchanged) compiled against the stand-in CUDA headers of
+tests/cusim/include and linked with cusim_host.cpp instead of the CUDA runtime.  See cusim_device.h."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "wgpu-cpu_b200", "csrc")
+OUT = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT, "libwgpu_b200_sim.so")
+
+
+def build(force: bool = False) -> str:
+    import importlib
+    import sys
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    product = importlib.import_module("wgpu_cpu_b200.build")
+    emb = product._embed()                                   # the device sources as text, exactly as the product embeds them
+    srcs = [os.path.join(CSRC, "wgb_api.cpp"), os.path.join(CSRC, "wgsl_emit.cpp"), emb, os.path.join(HERE, "cusim_host.cpp")]
+    deps = srcs + [os.path.join(HERE, "include", f) for f in os.listdir(os.path.join(HERE, "include"))] + [
+        os.path.join(CSRC, "wgb_shared.h"), os.path.join(ROOT, "include", "wgpu_b200.h"), os.path.abspath(__file__)]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+        return LIB
+    os.makedirs(OUT, exist_ok=True)
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-w", f"-I{os.path.join(HERE, 'include')}",
+           f'-DCUSIM_DIR="{HERE}"', *srcs, "-o", LIB, "-ldl", "-lpthread"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True))

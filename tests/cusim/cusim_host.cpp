@@ -1,0 +1,236 @@
+// TEST INFRASTRUCTURE (tests/cusim): host half of the software model of CUDA -- see cusim_device.h.  Implements the
+// subset of the CUDA runtime / driver / NVRTC entry points that wgpu-cpu_b200/csrc/wgb_api.cpp calls, on host memory.
+// "Device" allocations end at a PROT_NONE guard page, so a kernel that reads or writes past a buffer faults instead of
+// passing silently.  Every stream operation executes at issue.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+#undef dlopen
+#undef dlsym
+#include <dlfcn.h>
+#undef dlopen
+#undef dlsym
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#ifndef CUSIM_DIR
+#error "CUSIM_DIR (absolute path of tests/cusim) must be defined"
+#endif
+
+struct cusimStream { int unused; };
+struct cusimEvent { std::chrono::steady_clock::time_point t; bool recorded = false; };
+struct cusimModule { void* lib; void (*launch)(void*, const char*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void**); };
+struct cusimFunction { cusimModule* mod; void* fn; std::string name; };
+struct cusimProgram { std::string source, name, log, so_path; std::vector<std::pair<std::string, std::string>> headers; };
+struct CusimTexture { const void* ptr; unsigned long long bytes; };
+
+namespace {
+std::mutex g_mu;
+struct Alloc { void* base; size_t len; };
+std::map<void*, Alloc> g_allocs;
+thread_local cudaError_t g_last = cudaSuccess;
+const size_t PAGE = 4096;
+
+cudaError_t guarded_alloc(void** out, size_t size) {
+    const size_t body = (size + 15) & ~(size_t)15;
+    const size_t pages = (body + PAGE - 1) / PAGE + 1;
+    char* base = (char*)mmap(nullptr, pages * PAGE, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == MAP_FAILED) return g_last = cudaErrorMemoryAllocation;
+    mprotect(base + (pages - 1) * PAGE, PAGE, PROT_NONE);
+    char* p = base + (pages - 1) * PAGE - body;
+    memset(p, 0xCD, body);                      // fresh device memory is not zero
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_allocs[p] = Alloc{base, pages * PAGE};
+    *out = p;
+    return cudaSuccess;
+}
+cudaError_t guarded_free(void* p) {
+    if (!p) return cudaSuccess;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_allocs.find(p);
+    if (it == g_allocs.end()) return g_last = cudaErrorInvalidValue;
+    munmap(it->second.base, it->second.len);
+    g_allocs.erase(it);
+    return cudaSuccess;
+}
+unsigned long long fnv(const std::string& s, unsigned long long h) {
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+    return h;
+}
+std::string read_file(const std::string& path) {
+    std::string out;
+    if (FILE* f = fopen(path.c_str(), "rb")) { char buf[65536]; size_t n; while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n); fclose(f); }
+    return out;
+}
+bool write_file(const std::string& path, const std::string& text) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const bool ok = fwrite(text.data(), 1, text.size(), f) == text.size();
+    fclose(f);
+    return ok;
+}
+}  // namespace
+
+extern "C" {
+const char* cudaGetErrorString(cudaError_t e) {
+    switch (e) { case cudaSuccess: return "no error"; case cudaErrorInvalidValue: return "invalid argument"; case cudaErrorMemoryAllocation: return "out of memory";
+                 case cudaErrorNotSupported: return "operation not supported by the software model"; default: return "unknown error"; }
+}
+cudaError_t cudaGetLastError() { cudaError_t e = g_last; g_last = cudaSuccess; return e; }
+cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : (g_last = cudaErrorInvalidValue); }
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
+    memset(p, 0, sizeof *p);
+    snprintf(p->name, sizeof p->name, "cusim software model of sm_100a");
+    p->major = 10; p->minor = 0; p->multiProcessorCount = 148; p->totalGlobalMem = (size_t)8 << 30;
+    return cudaSuccess;
+}
+cudaError_t cudaMalloc(void** p, size_t n) { return guarded_alloc(p, n ? n : 1); }
+cudaError_t cudaFree(void* p) { return guarded_free(p); }
+cudaError_t cudaMallocHost(void** p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? cudaSuccess : (g_last = cudaErrorMemoryAllocation); }
+cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t) {
+    for (size_t r = 0; r < h; r++) memmove((char*)d + r * dp, (const char*)s + r * sp, w);
+    return cudaSuccess;
+}
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { if (n) memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new cusimStream(); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new cusimEvent(); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new cusimEvent(); return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); e->recorded = true; return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+    return cudaSuccess;
+}
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+    memset(a, 0, sizeof *a);
+    a->type = cudaMemoryTypeUnregistered; a->hostPointer = const_cast<void*>(p);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return g_last = cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return g_last = cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void*) { return g_last = cudaErrorNotSupported; }
+cudaError_t cudaCreateTextureObject(cudaTextureObject_t* out, const cudaResourceDesc* rd, const cudaTextureDesc*, const void*) {
+    if (rd->resType != cudaResourceTypeLinear) return g_last = cudaErrorNotSupported;
+    *out = (cudaTextureObject_t)(uintptr_t) new CusimTexture{rd->res.linear.devPtr, rd->res.linear.sizeInBytes};
+    return cudaSuccess;
+}
+cudaError_t cudaDestroyTextureObject(cudaTextureObject_t t) { delete (CusimTexture*)(uintptr_t)t; return cudaSuccess; }
+
+// ---- driver -----------------------------------------------------------------------------------------------
+CUresult cusim_cuModuleLoadData(CUmodule* out, const void* image) {
+    const char* path = (const char*)image;                       // the stand-in "cubin" is the path of the shared object
+    void* lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!lib) { fprintf(stderr, "cusim: dlopen(%s): %s\n", path, dlerror()); return CUDA_ERROR_INVALID_VALUE; }
+    auto launch = (decltype(cusimModule::launch))dlsym(lib, "cusim_launch");
+    if (!launch) { dlclose(lib); return CUDA_ERROR_NOT_FOUND; }
+    *out = new cusimModule{lib, launch};
+    return CUDA_SUCCESS;
+}
+CUresult cusim_cuModuleUnload(CUmodule m) { if (m) { dlclose(m->lib); delete m; } return CUDA_SUCCESS; }
+CUresult cusim_cuModuleGetFunction(CUfunction* out, CUmodule m, const char* name) {
+    void* fn = dlsym(m->lib, name);
+    if (!fn) return CUDA_ERROR_NOT_FOUND;
+    *out = new cusimFunction{m, fn, name};                       // lives as long as the process (a handful per pipeline)
+    return CUDA_SUCCESS;
+}
+CUresult cusim_cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz, unsigned, CUstream, void** params, void**) {
+    if (!f || !gx || !gy || !gz || !bx || !by || !bz || (unsigned long long)bx * by * bz > 1024ull) return CUDA_ERROR_INVALID_VALUE;
+    f->mod->launch(f->fn, f->name.c_str(), gx, gy, gz, bx, by, bz, params);
+    return CUDA_SUCCESS;
+}
+CUresult cusim_cuGetErrorString(CUresult r, const char** s) {
+    *s = r == CUDA_SUCCESS ? "no error" : r == CUDA_ERROR_NOT_FOUND ? "named symbol not found" : r == CUDA_ERROR_INVALID_VALUE ? "invalid value" : "unknown driver error";
+    return CUDA_SUCCESS;
+}
+cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q) {
+    *fn = nullptr;
+    if (!strcmp(name, "cuModuleLoadData")) *fn = (void*)&cusim_cuModuleLoadData;
+    else if (!strcmp(name, "cuModuleUnload")) *fn = (void*)&cusim_cuModuleUnload;
+    else if (!strcmp(name, "cuModuleGetFunction")) *fn = (void*)&cusim_cuModuleGetFunction;
+    else if (!strcmp(name, "cuLaunchKernel")) *fn = (void*)&cusim_cuLaunchKernel;
+    else if (!strcmp(name, "cuGetErrorString")) *fn = (void*)&cusim_cuGetErrorString;
+    if (q) *q = *fn ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
+    return cudaSuccess;
+}
+
+// ---- "NVRTC": g++ over the pipeline TU with the device half of the model force-included ---------------------------
+nvrtcResult nvrtcCreateProgram(nvrtcProgram* out, const char* src, const char* name, int nh, const char* const* headers, const char* const* names) {
+    auto* p = new cusimProgram();
+    p->source = src; p->name = name ? name : "program.cu";
+    for (int i = 0; i < nh; i++) p->headers.emplace_back(names[i], headers[i]);
+    *out = p;
+    return NVRTC_SUCCESS;
+}
+nvrtcResult nvrtcDestroyProgram(nvrtcProgram* p) { delete *p; *p = nullptr; return NVRTC_SUCCESS; }
+nvrtcResult nvrtcCompileProgram(nvrtcProgram p, int, const char* const*) {
+    const std::string dev = read_file(std::string(CUSIM_DIR) + "/cusim_device.h"), entry = read_file(std::string(CUSIM_DIR) + "/cusim_entry.h");
+    if (dev.empty() || entry.empty()) { p->log = "cusim: cannot read cusim_device.h / cusim_entry.h under " CUSIM_DIR; return NVRTC_ERROR_COMPILATION; }
+    const char* opt = getenv("CUSIM_OPT");
+    const std::string flags = std::string("-std=c++17 -fPIC -shared -g1 -w -ffp-contract=off -fno-strict-aliasing -fno-math-errno ") + (opt ? opt : "-O1");
+    unsigned long long h1 = fnv(p->source, 14695981039346656037ull), h2 = fnv(p->source, 0x9E3779B97F4A7C15ull);
+    for (auto& kv : p->headers) { h1 = fnv(kv.first, fnv(kv.second, h1)); h2 = fnv(kv.second, fnv(kv.first, h2)); }
+    h1 = fnv(flags, fnv(entry, fnv(dev, h1))); h2 = fnv(dev, fnv(entry, fnv(flags, h2)));
+    const char* cache_env = getenv("CUSIM_CACHE");
+    const std::string cache = cache_env ? cache_env : "/tmp/cusim_cache_" + std::to_string((unsigned)getuid());
+    mkdir(cache.c_str(), 0700);
+    char key[40];
+    snprintf(key, sizeof key, "%016llx%016llx", h1, h2);
+    const std::string so = cache + "/" + key + ".so";
+    if (access(so.c_str(), R_OK) != 0) {
+        const std::string dir = cache + "/" + key + "." + std::to_string((long)getpid());
+        mkdir(dir.c_str(), 0700);
+        bool ok = write_file(dir + "/cusim_device.h", dev) && write_file(dir + "/cusim_entry.h", entry) && write_file(dir + "/" + p->name, p->source);
+        for (auto& kv : p->headers) ok = ok && write_file(dir + "/" + kv.first, kv.second);
+        ok = ok && write_file(dir + "/tu.cpp", "#include \"cusim_device.h\"\n#include \"" + p->name + "\"\n#include \"cusim_entry.h\"\n");
+        if (!ok) { p->log = "cusim: cannot write " + dir; return NVRTC_ERROR_COMPILATION; }
+        const std::string cmd = "cd '" + dir + "' && g++ " + flags + " -I. tu.cpp -o out.so -lpthread > log.txt 2>&1";
+        const int rc = system(cmd.c_str());
+        p->log = read_file(dir + "/log.txt");
+        if (rc != 0) { if (p->log.size() > 20000) p->log.resize(20000); return NVRTC_ERROR_COMPILATION; }
+        if (rename((dir + "/out.so").c_str(), so.c_str()) != 0) { p->log = "cusim: rename failed"; return NVRTC_ERROR_COMPILATION; }
+        if (!getenv("CUSIM_KEEP")) { const std::string rm = "rm -rf '" + dir + "'"; if (system(rm.c_str())) {} }
+    }
+    p->so_path = so;
+    return NVRTC_SUCCESS;
+}
+nvrtcResult nvrtcGetCUBINSize(nvrtcProgram p, size_t* n) { *n = p->so_path.size() + 1; return NVRTC_SUCCESS; }
+nvrtcResult nvrtcGetCUBIN(nvrtcProgram p, char* out) { memcpy(out, p->so_path.c_str(), p->so_path.size() + 1); return NVRTC_SUCCESS; }
+nvrtcResult nvrtcGetProgramLogSize(nvrtcProgram p, size_t* n) { *n = p->log.size() + 1; return NVRTC_SUCCESS; }
+nvrtcResult nvrtcGetProgramLog(nvrtcProgram p, char* out) { memcpy(out, p->log.c_str(), p->log.size() + 1); return NVRTC_SUCCESS; }
+const char* nvrtcGetErrorString(nvrtcResult r) { return r == NVRTC_SUCCESS ? "NVRTC_SUCCESS" : "NVRTC_ERROR_COMPILATION"; }
+
+// ---- the two dlfcn calls wgb_api.cpp makes to find NVRTC ---------------------------------------------------------
+static int g_nvrtc_handle;
+void* cusim_dlopen(const char* name, int flags) {
+    if (name && strstr(name, "nvrtc")) return &g_nvrtc_handle;
+    return dlopen(name, flags);
+}
+void* cusim_dlsym(void* lib, const char* name) {
+    if (lib != &g_nvrtc_handle) return dlsym(lib, name);
+#define S(n) if (!strcmp(name, #n)) return (void*)&n;
+    S(nvrtcCreateProgram) S(nvrtcDestroyProgram) S(nvrtcCompileProgram) S(nvrtcGetCUBINSize) S(nvrtcGetCUBIN)
+    S(nvrtcGetProgramLogSize) S(nvrtcGetProgramLog) S(nvrtcGetErrorString)
+#undef S
+    return nullptr;
+}
+}  // extern "C"
