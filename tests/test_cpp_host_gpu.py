@@ -21,7 +21,11 @@ def test_cpp_host_renders_hello_mesh(tmp_path):
     (tmp_path / "i.bin").write_bytes(scene.index_data.astype(np.uint32).tobytes())
     (tmp_path / "u.bin").write_bytes(np.ascontiguousarray(scene.bindings[(0, 0)][1]).tobytes())
     out = str(tmp_path / "frame")
-    p = subprocess.run([os.path.join(ROOT, "examples", "hello_mesh"), os.path.join(ROOT, "wgpu-cpu_b200", "shaders", "mesh_vertex_color.wgsl"),
+    exe = os.path.join(ROOT, "examples", "hello_mesh")
+    if os.environ.get("WGB_CUSIM") == "1":          # the same example source linked against the software-model build
+        from tests.cusim import build as cusim_build
+        exe = cusim_build.build_example()
+    p = subprocess.run([exe, os.path.join(ROOT, "wgpu-cpu_b200", "shaders", "mesh_vertex_color.wgsl"),
                         str(tmp_path / "v.bin"), str(tmp_path / "i.bin"), str(tmp_path / "u.bin"), "256", "192", out],
                        capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stderr
