@@ -163,6 +163,17 @@ static void fs_frag_depth(const FsIn& in, FsOut& out, const Resources&, int*) {
     out.color[0] = color;
 }
 
+/* ---- early_force.wgsl / early_allow.wgsl (same stages; they differ in @early_depth_test) ---- */
+static void fs_early_depth(const FsIn& in, FsOut& out, const Resources&, int*) {
+    const Vec4 color = load_vec4(in.inter + 0);
+    if (color.y > 0.6f) { out.killed = true; return; }
+    out.has_frag_depth = true;
+    out.frag_depth = in.position.z * 0.5f;
+    out.num_color = 1;
+    out.color_location[0] = 0;
+    out.color[0] = color;
+}
+
 static const ShaderInfo SHADERS[ORC_SHADER_COUNT] = {
     /* colored_triangle */ {vs_colored_triangle, fs_passthrough_color, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
     /* hello_mesh */       {vs_hello_mesh, fs_passthrough_color, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
@@ -170,6 +181,8 @@ static const ShaderInfo SHADERS[ORC_SHADER_COUNT] = {
     /* procedural */       {vs_procedural, fs_procedural, 0, {}, 0},
     /* features */         {vs_features, fs_features, 2, {{0, 0, 4, VAR_F32, INTERP_LINEAR}, {1, 16, 1, VAR_U32, INTERP_FLAT}}, 0},
     /* frag_depth */       {vs_frag_depth, fs_frag_depth, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
+    /* early_force */      {vs_frag_depth, fs_early_depth, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 1},
+    /* early_allow */      {vs_frag_depth, fs_early_depth, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 2},
 };
 
 const ShaderInfo* shader_info(uint32_t shader) {

@@ -88,13 +88,11 @@ def test_unsupported_state_is_reported(offline):
     with pytest.raises(api.WgpuError) as e:      # state.rs:438-478 panics for PolygonMode::Line
         dev.create_render_pipeline(vertex_module=m, fragment_module=m, targets=["rgba8unorm"], polygon_mode=1)
     assert e.value.status == 2
-    # NotEqual + depth write has no closed form: it takes the ordered tile kernel, for triangles; lines are refused
-    dev.create_render_pipeline(vertex_module=m, fragment_module=m, targets=["rgba8unorm"],
-                               depth_stencil={"depth_compare": "not-equal", "depth_write_enabled": True})
-    with pytest.raises(api.WgpuError) as e:
-        dev.create_render_pipeline(vertex_module=m, fragment_module=m, targets=["rgba8unorm"], topology="line-list",
-                                   depth_stencil={"depth_compare": "not-equal", "depth_write_enabled": True})
-    assert e.value.status == 2 and "triangle" in str(e.value)
+    # NotEqual + depth write has no closed form: it takes the ordered tile kernel, which runs every topology
+    for topology in ("triangle-list", "line-list", "point-list"):
+        p = dev.create_render_pipeline(vertex_module=m, fragment_module=m, targets=["rgba8unorm"], topology=topology,
+                                       depth_stencil={"depth_compare": "not-equal", "depth_write_enabled": True})
+        assert "#define WGB_RESOLVE 7" in p.get_source()
     with pytest.raises(api.WgpuError):           # binding.rs:161 todo!()
         dev.create_sampler(address_mode_u="clamp-to-border")
     with pytest.raises(api.WgpuError):
@@ -231,3 +229,13 @@ def test_ordered_variants_compile_offline():
     pn = dev0.create_render_pipeline(vertex_module=m0, fragment_module=m0, vertex_buffers=vbs, targets=["rgba8unorm"],
                                      depth_stencil={"depth_compare": "not-equal", "depth_write_enabled": True})
     assert "#define WGB_RESOLVE 7" in pn.get_source()
+    # an early depth test ahead of discard / frag_depth, or followed by the late test (Allow), has no closed form either;
+    # compiled here for sm_100a for a triangle, a line and a point topology
+    for name, topology in (("early_force", "triangle-list"), ("early_allow", "line-strip"), ("early_force", "point-list")):
+        me = dev0.create_shader_module(shaders.wgsl(name))
+        pe = dev0.create_render_pipeline(vertex_module=me, fragment_module=me, vertex_buffers=vbs, targets=["rgba8unorm"], topology=topology,
+                                         depth_stencil={"depth_compare": "less", "depth_write_enabled": True})
+        assert "#define WGB_RESOLVE 7" in pe.get_source() and "#define WGB_FS_EARLY_DEPTH" in pe.get_source()
+    # without a depth test the attribute changes nothing: closed-form kernel
+    me = dev0.create_shader_module(shaders.wgsl("early_force"))
+    assert "#define WGB_RESOLVE 0" in dev0.create_render_pipeline(vertex_module=me, fragment_module=me, vertex_buffers=vbs, targets=["rgba8unorm"]).get_source()

@@ -40,7 +40,8 @@ def _compare(scene, gpu, use_emitted=False):
         msg.append(f"colour differs at {len(bad)} pixels, first (y,x)={bad[:5].tolist()} "
                    f"got={got.color[tuple(bad[0])].tolist()} ref={ref.color[tuple(bad[0])].tolist()}")
     assert not msg, f"{scene.name}: " + "; ".join(msg)
-    assert got.stats["fragments"] == ref.stats["fragments_shaded"] or scene.shader in ("features",), \
+    # (the oracle counts stage invocations: fewer than the rasterised fragments once an early depth test rejects some)
+    assert got.stats["fragments"] == ref.stats["fragments_shaded"] or scene.shader in ("features", "early_force", "early_allow"), \
         f"{scene.name}: fragment count {got.stats['fragments']} != {ref.stats['fragments_shaded']}"
     # the production configuration: no coverage capture, so the hierarchical depth test is active
     fast = render_scene(dev, queue, scene, want_coverage=False, use_emitted=use_emitted)
@@ -125,6 +126,28 @@ def test_features_instancing_flat_discard(gpu):
 
 def test_frag_depth(gpu):
     _compare(S.frag_depth(), gpu)
+
+
+@pytest.mark.parametrize("kind,compare,topology", [
+    ("force", "less", "triangle-list"), ("force", "greater-equal", "triangle-list"), ("force", "not-equal", "triangle-list"),
+    ("allow", "less", "triangle-list"), ("allow", "less-equal", "triangle-list"), ("allow", "greater-equal", "triangle-list"),
+    ("force", "less", "line-list"), ("allow", "less-equal", "line-strip"), ("force", "less-equal", "point-list")])
+def test_early_depth_test_before_discard_and_frag_depth(gpu, kind, compare, topology):
+    """fragment.rs:166-194: with @early_depth_test the rasteriser's depth is tested and written before the stage runs --
+    a fragment the stage then discards has already left its depth behind, the frag_depth it returns is ignored (force)
+    or tested once more against the depth just stored (allow).  The fold has no closed form:
+    these pipelines take the ordered tile kernel."""
+    got, ref = _compare(S.early_depth(kind, compare, topology=topology), gpu)
+    if compare != "not-equal":
+        assert ref.stats["fragments_shaded"] < got.stats["fragments"]          # the early test rejected fragments before the stage ran
+
+
+@pytest.mark.parametrize("topology", ["line-list", "line-strip", "point-list"])
+def test_not_equal_with_depth_write_on_lines_and_points(gpu, topology):
+    """The ordered kernel walks lines once per thread and treats points as single pixels."""
+    s = S.random_lines(200, 150, 90, 12, topology)
+    s.depth_compare, s.depth_write, s.clear_depth = "not-equal", True, 0.5
+    _compare(s, gpu)
 
 
 def test_viewport_and_scissor(gpu):

@@ -479,12 +479,22 @@ struct RenderPipeline : Object {
         }
     }
 
+    // value of a `#define NAME n` the emitter wrote into the fragment stage's text (0 if there is no fragment stage)
+    int fs_flag(const char* name) const {
+        if (!has_fragment) return 0;
+        const std::string key = std::string("#define ") + name + " ";
+        const size_t at = fs_text.find(key);
+        return at == std::string::npos ? 0 : atoi(fs_text.c_str() + at + key.size());
+    }
+
     std::string build_source(bool has_depth_attachment, bool separated) const {
         const bool test = has_depth_stencil && has_depth_attachment;
         int mode = resolve_mode(test, depth_compare, depth_write != 0);
         if (blends()) mode = 7;
-        if (mode == 7 && prim_size() != 3)
-            fail(WGB_ERROR_UNSUPPORTED, "blending and NotEqual depth tests with depth writes are supported for triangle topologies only");
+        // an early depth test (fragment.rs:166-194) is the late one in disguise unless the shader can discard or write
+        // frag_depth after it, or the late test runs as well (Allow): those take the ordered kernel too
+        const int early = fs_flag("WGB_FS_EARLY_DEPTH");
+        if (test && early != 0 && (early == 2 || fs_flag("WGB_FS_MAY_DISCARD") || fs_flag("WGB_FS_WRITES_FRAG_DEPTH"))) mode = 7;
         std::string s;
         char line[256];
         auto def = [&](const char* name, long long v) { snprintf(line, sizeof(line), "#define %s %lld\n", name, v); s += line; };
@@ -527,7 +537,6 @@ struct RenderPipeline : Object {
         else s += "#define WGB_FS_COLOR_MASK 0\n#define WGB_FS_WRITES_FRAG_DEPTH 0\n#define WGB_FS_MAY_DISCARD 0\n#define WGB_FS_EARLY_DEPTH 0\n"
                   "WGB_DEV constexpr int wgb_fs_interp(int) { return 0; }\n"
                   "WGB_DEV bool wgb_fs_entry(const WgbDraw&, const WgbFragIn&, const u32*, WgbFragOut&) { return true; }\n";
-        s += "\n#if WGB_FS_EARLY_DEPTH && WGB_FS_MAY_DISCARD\n#error \"early depth test combined with discard is not supported\"\n#endif\n";
         s += "#include \"wgb_raster.cuh\"\n";
         return s;
     }

@@ -427,6 +427,21 @@ def frag_depth(width=160, height=120) -> Scene:
     return s
 
 
+def early_depth(kind="force", compare="less", width=160, height=120, topology="triangle-list") -> Scene:
+    """@early_depth_test in front of a stage that discards and writes frag_depth (shaders/early_force.wgsl,
+    early_allow.wgsl; fragment.rs:166-194)."""
+    if topology == "triangle-list":
+        s = random_triangles(width, height, count=80, seed=33, spread=1.1, with_w=False)
+    else:
+        s = random_lines(width, height, 60, 34, topology)
+    s.name = f"early_{kind}_{compare}_{topology}"
+    s.shader = f"early_{kind}"
+    s.depth_compare = compare
+    s.depth_write = True
+    s.clear_depth = 0.5 if compare.startswith("greater") else 1.0
+    return s
+
+
 def multi_draw(width=192, height=128) -> Scene:
     """Several draws in one pass over the same attachments (later draws see earlier depth/colour), u16 indices with a
     base_vertex, a ragged index count (the incomplete tail primitive is dropped, util/mod.rs:58-76) and an empty draw."""
@@ -531,8 +546,6 @@ def fuzz(seed: int) -> Scene:
         draws.append(Draw(False, first, nverts - first, 0, 0, 1))
     compare = str(rng.choice(["less", "less", "less-equal", "greater", "greater-equal", "always", "never", "equal", "not-equal", "none"]))
     write = bool(rng.random() < 0.75)
-    if compare == "not-equal" and not topology.startswith("triangle"):
-        write = False       # NotEqual + write runs on the ordered kernel, which rasterises triangles only
     s = Scene(
         name=f"fuzz_{seed}", width=width, height=height, shader="hello_mesh", topology=topology, strip_index_format=strip_fmt,
         front_face=str(rng.choice(["ccw", "cw"])), cull_mode=rng.choice([None, None, "front", "back"]),
