@@ -406,6 +406,29 @@ def test_count_scan_fill_binning_matches_direct_binning(monkeypatch):
         assert a.stats["bin_pairs"] == b.stats["bin_pairs"] and a.stats["fragments"] == b.stats["fragments"]
 
 
+@pytest.mark.parametrize("compare", ["less", "not-equal"])
+def test_clip_record_and_big_list_overflow_replay(monkeypatch, compare):
+    """Clip records and the big list live in fixed buffers; when either overflows the tile kernel leaves the attachments
+    untouched and the host replays the draw with larger ones.  WGB_TEST_SMALL_WORK_BUFFERS=1 starts both at two entries, so
+    a scene with clipped and tile-spanning triangles overflows both, repeatedly (closed-form and ordered tile kernel)."""
+    from oracle import pyoracle
+    from wgpu_cpu_b200 import api
+    from wgpu_cpu_b200.render import SceneRenderer
+    monkeypatch.setenv("WGB_TEST_SMALL_WORK_BUFFERS", "1")
+    dev, queue = api.instance().request_adapter().request_device(0)
+    monkeypatch.delenv("WGB_TEST_SMALL_WORK_BUFFERS")
+    scene = S.huge_triangles()
+    scene.depth_compare, scene.depth_write = compare, True
+    ref = pyoracle.render(scene, want_coverage=False)
+    r = SceneRenderer(dev, queue, scene)
+    st = r.render()
+    assert st["replays"] >= 2 and st["big_primitives"] > 2 and st["clip_records"] > 2
+    f = r.read()
+    assert np.array_equal(f.color, ref.color) and np.array_equal(f.depth.view(np.uint32), ref.depth.view(np.uint32))
+    assert r.render()["replays"] == 0                       # the device keeps the capacities it learned
+    assert np.array_equal(r.read().color, ref.color)
+
+
 @pytest.mark.parametrize("order", ["front_to_back", "back_to_front"])
 def test_hierarchical_depth_test_drops_hidden_triangles_without_changing_the_frame(gpu, order):
     """Layered small triangles (the C3 structure): with the near layer drawn first most of the far layers is dropped

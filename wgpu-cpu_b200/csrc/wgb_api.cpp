@@ -314,6 +314,7 @@ struct Device : Object {
     // work buffers, grown on demand and reused across passes
     std::map<std::pair<uint32_t, uint32_t>, uint32_t> bin_cap_hint;   // (primitives, band tiles) of a draw -> slots per tile it needed
     bool no_direct_bins = false;
+    bool small_work_buffers = false;       // testing knob: start the clip-record and big lists at 2 entries so that both overflow-and-replay paths run
     DevBuf counters, prim_box, setup_cache, vcache_raster, vcache_ndc, vcache_flags, slow_list, clip_records, big_list, tile_count, tile_offset, tile_cursor, bins, coverage, strip_map, strip_count;
     WgbCounters* host_counters = nullptr;   // pinned
     uint32_t clip_capacity = 0, big_capacity = 0;
@@ -837,10 +838,10 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
         d.prim_base = (uint32_t)base;   // batches beyond 2^32 primitives are not addressable
         REQUIRE(base + np <= 0xFFFFFFFFull, "draw exceeds 2^32 primitives");
         d.num_prims = np;
-        if (dev->clip_capacity == 0) dev->clip_capacity = 65536;
+        if (dev->clip_capacity == 0) dev->clip_capacity = dev->small_work_buffers ? 2 : 65536;
         for (int attempt = 0;; attempt++) {
-            const uint32_t clip_cap = std::max<uint32_t>(dev->clip_capacity, np / 16);
-            const uint32_t big_cap = std::max<uint32_t>(dev->big_capacity, std::max<uint32_t>(65536, np / 8));
+            const uint32_t clip_cap = dev->small_work_buffers ? dev->clip_capacity : std::max<uint32_t>(dev->clip_capacity, np / 16);
+            const uint32_t big_cap = dev->small_work_buffers ? std::max<uint32_t>(dev->big_capacity, 2) : std::max<uint32_t>(dev->big_capacity, std::max<uint32_t>(65536, np / 8));
             dev->clip_capacity = clip_cap; dev->big_capacity = big_cap;
             // the counters and the per-tile pair counts share one buffer: one memset clears both
             dev->counters.ensure(sizeof(WgbCounters) + (size_t)(band_tiles + 1) * 4);
@@ -1249,6 +1250,7 @@ wgb_status wgb_adapter_request_device(wgb_adapter adapter, const wgb_device_desc
             CUDA_CHECK(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
             CUDA_CHECK(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
             dev->no_direct_bins = getenv("WGB_NO_DIRECT_BINS") != nullptr;      // testing knob: always count / scan / fill
+            dev->small_work_buffers = getenv("WGB_TEST_SMALL_WORK_BUFFERS") != nullptr;
             for (auto& e2 : dev->ev) CUDA_CHECK(cudaEventCreate(&e2));
             for (auto& e2 : dev->timer_ev) CUDA_CHECK(cudaEventCreate(&e2));
             CUDA_CHECK(cudaMallocHost((void**)&dev->host_counters, sizeof(WgbCounters)));
