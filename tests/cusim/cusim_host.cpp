@@ -14,6 +14,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -197,7 +198,8 @@ nvrtcResult nvrtcCompileProgram(nvrtcProgram p, int, const char* const*) {
     snprintf(key, sizeof key, "%016llx%016llx", h1, h2);
     const std::string so = cache + "/" + key + ".so";
     if (access(so.c_str(), R_OK) != 0) {
-        const std::string dir = cache + "/" + key + "." + std::to_string((long)getpid());
+        static std::atomic<unsigned> serial{0};
+        const std::string dir = cache + "/" + key + "." + std::to_string((long)getpid()) + "." + std::to_string(serial.fetch_add(1));
         mkdir(dir.c_str(), 0700);
         bool ok = write_file(dir + "/cusim_device.h", dev) && write_file(dir + "/cusim_entry.h", entry) && write_file(dir + "/" + p->name, p->source);
         for (auto& kv : p->headers) ok = ok && write_file(dir + "/" + kv.first, kv.second);

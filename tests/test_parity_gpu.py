@@ -406,6 +406,37 @@ def test_count_scan_fill_binning_matches_direct_binning(monkeypatch):
         assert a.stats["bin_pairs"] == b.stats["bin_pairs"] and a.stats["fragments"] == b.stats["fragments"]
 
 
+def test_concurrent_recording_and_submission_from_threads(gpu):
+    """Backend objects are Send + Sync and recording may happen on any thread (engine.rs:26-36 executes the
+    submissions one at a time in submission order).  Four threads share one device and queue; each creates its own
+    resources and pipeline, records, submits and reads back three times (ctypes drops the GIL around every C call)."""
+    import threading
+    from oracle import pyoracle
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    scn = [S.random_triangles(count=300, seed=40), S.hello_mesh(200, 150), S.random_lines(160, 120, 80, 7, "line-strip"), S.features()]
+    refs = [pyoracle.render(s, want_coverage=False) for s in scn]
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                r = SceneRenderer(dev, queue, scn[i])
+                r.render()
+                f = r.read()
+                if not np.array_equal(f.color, refs[i].color) or (refs[i].depth is not None and not np.array_equal(f.depth.view(np.uint32), refs[i].depth.view(np.uint32))):
+                    errors.append(f"{scn[i].name}: frame differs")
+        except Exception as e:      # noqa: BLE001 -- reported below, on the main thread
+            errors.append(f"{scn[i].name}: {e!r}")
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(scn))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 @pytest.mark.parametrize("compare", ["less", "not-equal"])
 def test_clip_record_and_big_list_overflow_replay(monkeypatch, compare):
     """Clip records and the big list live in fixed buffers; when either overflows the tile kernel leaves the attachments
