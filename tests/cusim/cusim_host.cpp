@@ -10,10 +10,12 @@
 #include <dlfcn.h>
 #undef dlopen
 #undef dlsym
+#include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -37,21 +39,34 @@ struct CusimTexture { const void* ptr; unsigned long long bytes; };
 
 namespace {
 std::mutex g_mu;
-struct Alloc { void* base; size_t len; };
+struct Alloc { void* base; size_t len; int fd; };
 std::map<void*, Alloc> g_allocs;
 thread_local cudaError_t g_last = cudaSuccess;
 const size_t PAGE = 4096;
 
+// CUSIM_IPC=1: allocations are backed by a memfd, so that cudaIpcGetMemHandle / cudaIpcOpenMemHandle can map them into
+// another process of the same user (the peer-memory presenter of the multi-GPU path, one process per "device")
+bool ipc_enabled() { static const bool on = getenv("CUSIM_IPC") != nullptr; return on; }
+int device_count() { static const int n = getenv("CUSIM_DEVICES") ? std::max(1, atoi(getenv("CUSIM_DEVICES"))) : 1; return n; }
+struct IpcHandle { unsigned magic; int pid, fd; unsigned long long offset, len; };
+static_assert(sizeof(IpcHandle) <= 64, "fits a cudaIpcMemHandle_t");
+
 cudaError_t guarded_alloc(void** out, size_t size) {
     const size_t body = (size + 15) & ~(size_t)15;
     const size_t pages = (body + PAGE - 1) / PAGE + 1;
-    char* base = (char*)mmap(nullptr, pages * PAGE, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-    if (base == MAP_FAILED) return g_last = cudaErrorMemoryAllocation;
+    int fd = -1;
+    char* base;
+    if (ipc_enabled()) {
+        fd = memfd_create("cusim", 0);
+        if (fd < 0 || ftruncate(fd, (off_t)(pages * PAGE)) != 0) { if (fd >= 0) close(fd); return g_last = cudaErrorMemoryAllocation; }
+        base = (char*)mmap(nullptr, pages * PAGE, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    } else base = (char*)mmap(nullptr, pages * PAGE, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == MAP_FAILED) { if (fd >= 0) close(fd); return g_last = cudaErrorMemoryAllocation; }
     mprotect(base + (pages - 1) * PAGE, PAGE, PROT_NONE);
     char* p = base + (pages - 1) * PAGE - body;
     memset(p, 0xCD, body);                      // fresh device memory is not zero
     std::lock_guard<std::mutex> lk(g_mu);
-    g_allocs[p] = Alloc{base, pages * PAGE};
+    g_allocs[p] = Alloc{base, pages * PAGE, fd};
     *out = p;
     return cudaSuccess;
 }
@@ -61,6 +76,7 @@ cudaError_t guarded_free(void* p) {
     auto it = g_allocs.find(p);
     if (it == g_allocs.end()) return g_last = cudaErrorInvalidValue;
     munmap(it->second.base, it->second.len);
+    if (it->second.fd >= 0) close(it->second.fd);
     g_allocs.erase(it);
     return cudaSuccess;
 }
@@ -88,9 +104,10 @@ const char* cudaGetErrorString(cudaError_t e) {
                  case cudaErrorNotSupported: return "operation not supported by the software model"; default: return "unknown error"; }
 }
 cudaError_t cudaGetLastError() { cudaError_t e = g_last; g_last = cudaSuccess; return e; }
-cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : (g_last = cudaErrorInvalidValue); }
+static thread_local int g_device = 0;
+cudaError_t cudaGetDeviceCount(int* n) { *n = device_count(); return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d) { *d = g_device; return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= device_count()) return g_last = cudaErrorInvalidValue; g_device = d; return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     memset(p, 0, sizeof *p);
     snprintf(p->name, sizeof p->name, "cusim software model of sm_100a");
@@ -127,9 +144,34 @@ cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
     a->type = cudaMemoryTypeUnregistered; a->hostPointer = const_cast<void*>(p);
     return cudaSuccess;
 }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return g_last = cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return g_last = cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void*) { return g_last = cudaErrorNotSupported; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* out, void* p) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_allocs.find(p);
+    if (it == g_allocs.end()) return g_last = cudaErrorInvalidValue;
+    if (it->second.fd < 0) return g_last = cudaErrorNotSupported;             // needs CUSIM_IPC=1
+    IpcHandle h{0x43534950u, (int)getpid(), it->second.fd, (unsigned long long)((char*)p - (char*)it->second.base), (unsigned long long)it->second.len};
+    memset(out, 0, sizeof *out);
+    memcpy(out, &h, sizeof h);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** out, cudaIpcMemHandle_t handle, unsigned) {
+    IpcHandle h;
+    memcpy(&h, &handle, sizeof h);
+    if (h.magic != 0x43534950u) return g_last = cudaErrorInvalidValue;
+    char path[64];
+    snprintf(path, sizeof path, "/proc/%d/fd/%d", h.pid, h.fd);
+    const int fd = open(path, O_RDWR);
+    if (fd < 0) return g_last = cudaErrorInvalidValue;
+    char* base = (char*)mmap(nullptr, h.len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (base == MAP_FAILED) return g_last = cudaErrorMemoryAllocation;
+    mprotect(base + h.len - PAGE, PAGE, PROT_NONE);
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_allocs[base + h.offset] = Alloc{base, (size_t)h.len, -1};
+    *out = base + h.offset;
+    return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void* p) { return guarded_free(p); }
 cudaError_t cudaCreateTextureObject(cudaTextureObject_t* out, const cudaResourceDesc* rd, const cudaTextureDesc*, const void*) {
     if (rd->resType != cudaResourceTypeLinear) return g_last = cudaErrorNotSupported;
     *out = (cudaTextureObject_t)(uintptr_t) new CusimTexture{rd->res.linear.devPtr, rd->res.linear.sizeInBytes};
