@@ -406,6 +406,27 @@ def test_count_scan_fill_binning_matches_direct_binning(monkeypatch):
         assert a.stats["bin_pairs"] == b.stats["bin_pairs"] and a.stats["fragments"] == b.stats["fragments"]
 
 
+def test_wgb_log_prints_the_pass_timer_and_counters():
+    """The reference's only instrumentation is `tracing::debug!(?elapsed, "render pass time")` and its per-draw counters
+    (render_pass/mod.rs:346,392-393; state.rs:516-517,592).  WGB_LOG=debug prints the same per pass, WGB_LOG=trace per
+    draw as well (read once per process, hence the child process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys; sys.path.insert(0, %r)\n"
+            "if os.environ.get('WGB_CUSIM') == '1':\n    from tests import conftest; conftest.use_cusim()\n"
+            "from wgpu_cpu_b200 import api, scenes\nfrom wgpu_cpu_b200.render import render_scene\n"
+            "dev, q = api.instance().request_adapter().request_device(0)\nrender_scene(dev, q, scenes.multi_draw())\n") % root
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, WGB_LOG="trace"), capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    lines = [ln for ln in p.stderr.splitlines() if ln.startswith("wgpu-b200 ")]
+    assert any("DEBUG render pass time:" in ln and "primitives_drawn=89" in ln and "draws=3" in ln for ln in lines), p.stderr
+    assert sum("TRACE draw" in ln for ln in lines) >= 3
+    quiet = subprocess.run([sys.executable, "-c", code], env={k: v for k, v in os.environ.items() if k != "WGB_LOG"}, capture_output=True, text=True, timeout=600)
+    assert quiet.returncode == 0 and "wgpu-b200 " not in quiet.stderr
+
+
 def test_concurrent_recording_and_submission_from_threads(gpu):
     """Backend objects are Send + Sync and recording may happen on any thread (engine.rs:26-36 executes the
     submissions one at a time in submission order).  Four threads share one device and queue; each creates its own

@@ -13,6 +13,12 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nvrtc.h>
+#if defined(__has_include)
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+#define WGB_HAVE_NVTX 1
+#endif
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -938,7 +944,42 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
     dev->last_stats.draws++;
 }
 
+// Tracing: the reference logs `render pass time` and its per-draw counters at debug level through the
+// `tracing` crate (render_pass/mod.rs:346,392-393, state.rs:516-517,592; RUST_LOG selects the level).  Here WGB_LOG=debug
+// prints one line per executed pass to stderr, WGB_LOG=trace one more per draw, and every pass / draw is an NVTX range
+// for nsys / ncu when the toolkit's header is there.
+int log_level() {
+    static const int level = [] {
+        const char* e = getenv("WGB_LOG");
+        return !e ? 0 : !strcmp(e, "trace") ? 2 : (!strcmp(e, "debug") || !strcmp(e, "1")) ? 1 : 0;
+    }();
+    return level;
+}
+struct TraceRange {
+#ifdef WGB_HAVE_NVTX
+    explicit TraceRange(const char* name) { nvtxRangePushA(name); }
+    ~TraceRange() { nvtxRangePop(); }
+#else
+    explicit TraceRange(const char*) {}
+#endif
+};
+
+void execute_pass_body(Device* dev, const PassCommand& pass);
 void execute_pass(Device* dev, const PassCommand& pass) {
+    TraceRange range("wgb::render_pass");
+    const auto t0 = std::chrono::steady_clock::now();
+    execute_pass_body(dev, pass);
+    if (log_level() >= 1) {
+        const wgb_pass_stats& s = dev->last_stats;
+        const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "wgpu-b200 DEBUG render pass time: %.3f ms on the device (geometry %.3f, tile %.3f), %.3f ms on the host; draws=%u "
+                        "primitives_drawn=%llu fragments=%llu shaded=%llu bin_pairs=%llu big=%llu clipped=%llu hiz_culled=%llu launches=%u replays=%u\n",
+                s.total_ms, s.geometry_ms, s.tile_ms, host_ms, s.draws, (unsigned long long)s.primitives, (unsigned long long)s.fragments,
+                (unsigned long long)s.shaded, (unsigned long long)s.bin_pairs, (unsigned long long)s.big_primitives,
+                (unsigned long long)s.clipped_primitives, (unsigned long long)s.hiz_culled, s.kernel_launches, s.replays);
+    }
+}
+void execute_pass_body(Device* dev, const PassCommand& pass) {
     dev->last_stats = wgb_pass_stats{};
     PassTargets tg;
     bool have_size = false;
@@ -1005,7 +1046,17 @@ void execute_pass(Device* dev, const PassCommand& pass) {
             case SubCommand::SetScissor: memcpy(st.sc, sc.sc, sizeof(st.sc)); break;
             case SubCommand::SetBlendConstant: memcpy(st.blend_constant, sc.blend_constant, sizeof(st.blend_constant)); break;   // used by WGB_FEATURE_BLEND only
             case SubCommand::SetStencilReference: break;   // stored, unused (state.rs:207-221)
-            case SubCommand::Draw: case SubCommand::DrawIndexed: execute_draw(dev, st, tg, sc); break;
+            case SubCommand::Draw: case SubCommand::DrawIndexed: {
+                TraceRange draw_range(sc.kind == SubCommand::Draw ? "wgb::draw" : "wgb::draw_indexed");
+                const wgb_pass_stats before = dev->last_stats;
+                execute_draw(dev, st, tg, sc);
+                if (log_level() >= 2)
+                    fprintf(stderr, "wgpu-b200 TRACE %s: primitives=%llu fragments=%llu geometry %.3f ms tile %.3f ms replays=%u\n",
+                            sc.kind == SubCommand::Draw ? "draw" : "draw_indexed", (unsigned long long)(dev->last_stats.primitives - before.primitives),
+                            (unsigned long long)(dev->last_stats.fragments - before.fragments), dev->last_stats.geometry_ms - before.geometry_ms,
+                            dev->last_stats.tile_ms - before.tile_ms, dev->last_stats.replays - before.replays);
+                break;
+            }
         }
     }
     // LoadOp::Clear of a pass whose draws never reached the tile kernel (State::load, state.rs:135-145)
