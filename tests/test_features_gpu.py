@@ -154,22 +154,6 @@ def test_blending(ext, name, depth):
     assert not np.array_equal(pyoracle.render(scene, want_coverage=False).color, ref.color)
 
 
-@pytest.mark.parametrize("topology", ["line-list", "line-strip", "point-list"])
-def test_blending_lines_and_points(ext, topology):
-    """Blended lines and points: the ordered kernel runs every topology (one Bresenham walk per thread for a line)."""
-    from wgpu_cpu_b200 import api
-    scene = S.random_lines(200, 150, 120, 17, topology)
-    scene.color_format = "rgba8unorm"
-    _translucent(scene, 4)
-    scene.features = api.FEATURE["BLEND"]
-    scene.blend = BLENDS["alpha"]
-    scene.clear_color = (0.1, 0.3, 0.2, 0.5)
-    got, ref = _render_both(scene, ext)
-    assert np.array_equal(got.color, ref.color)
-    scene.features = 0
-    from oracle import pyoracle
-    assert not np.array_equal(pyoracle.render(scene, want_coverage=False).color, ref.color)
-
 
 def test_blending_with_srgb_target_mask_and_indexed_mesh(ext):
     from wgpu_cpu_b200 import api

@@ -1,0 +1,126 @@
+"""GPU tests written after round 1's GPU minutes were spent: they pass on the software model of tests/cusim (the CPU
+tier runs them there) and their kernels compile for sm_100a, but they have not run on a B200 yet.  The file sorts last so
+that on the hardware they run after every test that has.  (Same helpers and bar as tests/test_parity_gpu.py: coverage,
+depth bits and colour bytes equal to the oracle's.)"""
+import numpy as np
+import pytest
+
+from tests.test_features_gpu import BLENDS, _render_both, _translucent, ext  # noqa: F401  (ext is a fixture)
+from tests.test_parity_gpu import _compare, gpu  # noqa: F401  (gpu is a fixture)
+from wgpu_cpu_b200 import scenes as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kind,compare,topology", [
+    ("force", "less", "triangle-list"), ("force", "greater-equal", "triangle-list"), ("force", "not-equal", "triangle-list"),
+    ("allow", "less", "triangle-list"), ("allow", "less-equal", "triangle-list"), ("allow", "greater-equal", "triangle-list"),
+    ("force", "less", "line-list"), ("allow", "less-equal", "line-strip"), ("force", "less-equal", "point-list")])
+def test_early_depth_test_before_discard_and_frag_depth(gpu, kind, compare, topology):
+    """fragment.rs:166-194: with @early_depth_test the rasteriser's depth is tested and written before the stage runs --
+    a fragment the stage then discards has already left its depth behind, the frag_depth it returns is ignored (force)
+    or tested once more against the depth just stored (allow).  The fold has no closed form:
+    these pipelines take the ordered tile kernel."""
+    got, ref = _compare(S.early_depth(kind, compare, topology=topology), gpu)
+    if compare != "not-equal":
+        assert ref.stats["fragments_shaded"] < got.stats["fragments"]          # the early test rejected fragments before the stage ran
+
+
+@pytest.mark.parametrize("topology", ["line-list", "line-strip", "point-list"])
+def test_not_equal_with_depth_write_on_lines_and_points(gpu, topology):
+    """The ordered kernel walks lines once per thread and treats points as single pixels."""
+    s = S.random_lines(200, 150, 90, 12, topology)
+    s.depth_compare, s.depth_write, s.clear_depth = "not-equal", True, 0.5
+    _compare(s, gpu)
+
+
+def test_wgb_log_prints_the_pass_timer_and_counters():
+    """The reference's only instrumentation is `tracing::debug!(?elapsed, "render pass time")` and its per-draw counters
+    (render_pass/mod.rs:346,392-393; state.rs:516-517,592).  WGB_LOG=debug prints the same per pass, WGB_LOG=trace per
+    draw as well (read once per process, hence the child process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys; sys.path.insert(0, %r)\n"
+            "if os.environ.get('WGB_CUSIM') == '1':\n    from tests import conftest; conftest.use_cusim()\n"
+            "from wgpu_cpu_b200 import api, scenes\nfrom wgpu_cpu_b200.render import render_scene\n"
+            "dev, q = api.instance().request_adapter().request_device(0)\nrender_scene(dev, q, scenes.multi_draw())\n") % root
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, WGB_LOG="trace"), capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    lines = [ln for ln in p.stderr.splitlines() if ln.startswith("wgpu-b200 ")]
+    assert any("DEBUG render pass time:" in ln and "primitives_drawn=89" in ln and "draws=3" in ln for ln in lines), p.stderr
+    assert sum("TRACE draw" in ln for ln in lines) >= 3
+    quiet = subprocess.run([sys.executable, "-c", code], env={k: v for k, v in os.environ.items() if k != "WGB_LOG"}, capture_output=True, text=True, timeout=600)
+    assert quiet.returncode == 0 and "wgpu-b200 " not in quiet.stderr
+
+
+def test_concurrent_recording_and_submission_from_threads(gpu):
+    """Backend objects are Send + Sync and recording may happen on any thread (engine.rs:26-36 executes the
+    submissions one at a time in submission order).  Four threads share one device and queue; each creates its own
+    resources and pipeline, records, submits and reads back three times (ctypes drops the GIL around every C call)."""
+    import threading
+    from oracle import pyoracle
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    scn = [S.random_triangles(count=300, seed=40), S.hello_mesh(200, 150), S.random_lines(160, 120, 80, 7, "line-strip"), S.features()]
+    refs = [pyoracle.render(s, want_coverage=False) for s in scn]
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                r = SceneRenderer(dev, queue, scn[i])
+                r.render()
+                f = r.read()
+                if not np.array_equal(f.color, refs[i].color) or (refs[i].depth is not None and not np.array_equal(f.depth.view(np.uint32), refs[i].depth.view(np.uint32))):
+                    errors.append(f"{scn[i].name}: frame differs")
+        except Exception as e:      # noqa: BLE001 -- reported below, on the main thread
+            errors.append(f"{scn[i].name}: {e!r}")
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(scn))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
+@pytest.mark.parametrize("compare", ["less", "not-equal"])
+def test_clip_record_and_big_list_overflow_replay(monkeypatch, compare):
+    """Clip records and the big list live in fixed buffers; when either overflows the tile kernel leaves the attachments
+    untouched and the host replays the draw with larger ones.  WGB_TEST_SMALL_WORK_BUFFERS=1 starts both at two entries, so
+    a scene with clipped and tile-spanning triangles overflows both, repeatedly (closed-form and ordered tile kernel)."""
+    from oracle import pyoracle
+    from wgpu_cpu_b200 import api
+    from wgpu_cpu_b200.render import SceneRenderer
+    monkeypatch.setenv("WGB_TEST_SMALL_WORK_BUFFERS", "1")
+    dev, queue = api.instance().request_adapter().request_device(0)
+    monkeypatch.delenv("WGB_TEST_SMALL_WORK_BUFFERS")
+    scene = S.huge_triangles()
+    scene.depth_compare, scene.depth_write = compare, True
+    ref = pyoracle.render(scene, want_coverage=False)
+    r = SceneRenderer(dev, queue, scene)
+    st = r.render()
+    assert st["replays"] >= 2 and st["big_primitives"] > 2 and st["clip_records"] > 2
+    f = r.read()
+    assert np.array_equal(f.color, ref.color) and np.array_equal(f.depth.view(np.uint32), ref.depth.view(np.uint32))
+    assert r.render()["replays"] == 0                       # the device keeps the capacities it learned
+    assert np.array_equal(r.read().color, ref.color)
+
+
+@pytest.mark.parametrize("topology", ["line-list", "line-strip", "point-list"])
+def test_blending_lines_and_points(ext, topology):
+    """Blended lines and points: the ordered kernel runs every topology (one Bresenham walk per thread for a line)."""
+    from wgpu_cpu_b200 import api
+    scene = S.random_lines(200, 150, 120, 17, topology)
+    scene.color_format = "rgba8unorm"
+    _translucent(scene, 4)
+    scene.features = api.FEATURE["BLEND"]
+    scene.blend = BLENDS["alpha"]
+    scene.clear_color = (0.1, 0.3, 0.2, 0.5)
+    got, ref = _render_both(scene, ext)
+    assert np.array_equal(got.color, ref.color)
+    scene.features = 0
+    from oracle import pyoracle
+    assert not np.array_equal(pyoracle.render(scene, want_coverage=False).color, ref.color)
