@@ -124,3 +124,26 @@ def test_blending_lines_and_points(ext, topology):
     scene.features = 0
     from oracle import pyoracle
     assert not np.array_equal(pyoracle.render(scene, want_coverage=False).color, ref.color)
+
+
+@pytest.mark.parametrize("config", ["c1", "c2", "c3", "c4", "c5_frame_17"])
+def test_baseline_configs_at_full_size(gpu, config):
+    """BASELINE.json's configurations at their full sizes, bit-exact against the oracle (colour bytes and depth bits of
+    every pixel): C1 teapot 512x512, C2 bunny 1920x1080 textured, C3 9 999 392 triangles at 3840x2160, C4 the 64-iteration
+    fragment shader at 7680x4320, and one frame (yaw 17/64 of a turn) of C5's bunny at 3840x2160.  The oracle needs a few
+    seconds for each; the production configuration is what is measured (no coverage capture, hierarchical depth test on)."""
+    import math
+    from oracle import pyoracle
+    from wgpu_cpu_b200.render import render_scene
+    dev, queue = gpu
+    scene = {"c1": lambda: S.hello_mesh(512, 512), "c2": lambda: S.hello_texture(1920, 1080), "c3": lambda: S.synthetic_grid(),
+             "c4": lambda: S.procedural(7680, 4320),
+             "c5_frame_17": lambda: S.hello_texture(3840, 2160, yaw=17 * 2.0 * math.pi / 64)}[config]()
+    ref = pyoracle.render(scene, want_coverage=False)
+    got = render_scene(dev, queue, scene, want_coverage=False)
+    assert np.array_equal(got.color, ref.color), f"{scene.name}: colour differs at {int((got.color != ref.color).any(axis=2).sum())} pixels"
+    if ref.depth is not None:
+        assert np.array_equal(got.depth.view(np.uint32), ref.depth.view(np.uint32)), f"{scene.name}: depth differs"
+    assert got.stats["primitives"] == scene.num_primitives
+    if config == "c3":
+        assert got.stats["primitives"] == 9999392 and got.stats["bin_pairs"] == 11952651      # the figures of profiles/r01_summary.md
