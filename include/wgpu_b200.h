@@ -78,7 +78,9 @@ enum { WGB_ADDRESS_MODE_CLAMP_TO_EDGE = 0, WGB_ADDRESS_MODE_REPEAT = 1, WGB_ADDR
 enum { WGB_FILTER_MODE_NEAREST = 0, WGB_FILTER_MODE_LINEAR = 1 };
 enum { WGB_VERTEX_STEP_MODE_VERTEX = 0, WGB_VERTEX_STEP_MODE_INSTANCE = 1 };
 enum { WGB_VERTEX_FORMAT_FLOAT32 = 0, WGB_VERTEX_FORMAT_FLOAT32X2 = 1, WGB_VERTEX_FORMAT_FLOAT32X3 = 2,
-       WGB_VERTEX_FORMAT_FLOAT32X4 = 3, WGB_VERTEX_FORMAT_UINT32 = 4, WGB_VERTEX_FORMAT_SINT32 = 5 };
+       WGB_VERTEX_FORMAT_FLOAT32X4 = 3, WGB_VERTEX_FORMAT_UINT32 = 4, WGB_VERTEX_FORMAT_SINT32 = 5,
+       WGB_VERTEX_FORMAT_UINT32X2 = 6, WGB_VERTEX_FORMAT_UINT32X3 = 7, WGB_VERTEX_FORMAT_UINT32X4 = 8,
+       WGB_VERTEX_FORMAT_SINT32X2 = 9, WGB_VERTEX_FORMAT_SINT32X3 = 10, WGB_VERTEX_FORMAT_SINT32X4 = 11 };
 enum { WGB_LOAD_OP_CLEAR = 0, WGB_LOAD_OP_LOAD = 1 };
 enum { WGB_STORE_OP_STORE = 0, WGB_STORE_OP_DISCARD = 1 };
 enum { WGB_SHADER_STAGE_VERTEX = 1, WGB_SHADER_STAGE_FRAGMENT = 2 };

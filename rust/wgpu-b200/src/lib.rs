@@ -316,6 +316,12 @@ mod convert {
             V::Float32x4 => sys::WGB_VERTEX_FORMAT_FLOAT32X4,
             V::Uint32 => sys::WGB_VERTEX_FORMAT_UINT32,
             V::Sint32 => sys::WGB_VERTEX_FORMAT_SINT32,
+            V::Uint32x2 => sys::WGB_VERTEX_FORMAT_UINT32X2,
+            V::Uint32x3 => sys::WGB_VERTEX_FORMAT_UINT32X3,
+            V::Uint32x4 => sys::WGB_VERTEX_FORMAT_UINT32X4,
+            V::Sint32x2 => sys::WGB_VERTEX_FORMAT_SINT32X2,
+            V::Sint32x3 => sys::WGB_VERTEX_FORMAT_SINT32X3,
+            V::Sint32x4 => sys::WGB_VERTEX_FORMAT_SINT32X4,
             other => panic!("wgpu-b200: vertex format {other:?} is not supported"),
         }
     }

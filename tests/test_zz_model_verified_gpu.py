@@ -147,3 +147,46 @@ def test_baseline_configs_at_full_size(gpu, config):
     assert got.stats["primitives"] == scene.num_primitives
     if config == "c3":
         assert got.stats["primitives"] == 9999392 and got.stats["bin_pairs"] == 11952651      # the figures of profiles/r01_summary.md
+
+
+def test_integer_vector_vertex_formats(gpu):
+    """Uint32x2..x4 / Sint32x2..x4 attributes: the vertex stage receives the attribute's raw bytes as its declared type
+    (vertex.rs:128-156 copies `format.size()` bytes), integers travel to the fragment stage as flat varyings."""
+    from wgpu_cpu_b200 import api
+    dev, queue = gpu
+    wgsl = """
+struct VOut { @builtin(position) p: vec4f, @location(0) @interpolate(flat) packed: vec4u, @location(1) @interpolate(flat) s: vec2i, }
+struct FOut { @builtin(frag_depth) depth: f32, @location(0) color: vec4f, }
+@vertex fn vs_main(@builtin(vertex_index) i: u32, @location(0) a: vec4u, @location(1) b: vec2i, @location(2) c: vec3u) -> VOut {
+    let x = f32(i32(i & 1u) * 4 - 1);
+    let y = f32(i32(i >> 1u) * 4 - 1);
+    return VOut(vec4f(x, y, 0.5, 1.0), vec4u(a.x + c.x, a.y + c.y, a.z + c.z, a.w), b);
+}
+@fragment fn fs_main(v: VOut) -> FOut {
+    let sum = f32(v.packed.x) + f32(v.packed.y) * 10.0 + f32(v.packed.z) * 100.0 + f32(v.packed.w) * 1000.0 + f32(v.s.x * v.s.y);
+    return FOut(sum / 65536.0, vec4f(1.0, 0.0, 0.0, 1.0));
+}"""
+    module = dev.create_shader_module(wgsl)
+    # one 48-byte vertex, three copies: a = (1,2,3,4) @0, b = (-3, 5) @16, c = (4,3,2) @24
+    vertex = np.zeros(12, dtype=np.uint32)
+    vertex[0:4] = [1, 2, 3, 4]
+    vertex[4:6] = np.array([-3, 5], dtype=np.int32).view(np.uint32)
+    vertex[6:9] = [4, 3, 2]
+    vb = dev.create_buffer_init(np.tile(vertex, 3), api.BUFFER_USAGE["VERTEX"])
+    pipe = dev.create_render_pipeline(
+        vertex_module=module, fragment_module=module, targets=["rgba8unorm"],
+        vertex_buffers=[{"array_stride": 48, "attributes": [("uint32x4", 0, 0), ("sint32x2", 16, 1), ("uint32x3", 24, 2)]}],
+        depth_stencil={"depth_compare": "always", "depth_write_enabled": True})
+    color = dev.create_texture(8, 8, "rgba8unorm")
+    depth = dev.create_texture(8, 8, "depth32float")
+    enc = dev.create_command_encoder()
+    with enc.begin_render_pass([{"view": color.create_view(), "load": ("clear", (0, 0, 0, 0))}],
+                               {"view": depth.create_view(), "depth_load": ("clear", 0.0)}) as rp:
+        rp.set_pipeline(pipe)
+        rp.set_vertex_buffer(0, vb)
+        rp.draw(range(0, 3))
+    dev.poll(True, queue.submit([enc.finish()]))
+    d = depth.read()
+    assert (color.read()[..., 0] == 255).all()
+    want = np.float32((5 + 5 * 10 + 5 * 100 + 4 * 1000 - 15) / 65536.0)
+    assert (d == want).all(), (d[0, 0], want)

@@ -32,7 +32,8 @@ BYTES_PER_TEXEL = {0: 4, 1: 4, 2: 4, 3: 4, 4: 1, 5: 2, 6: 4, 7: 4}
 ADDRESS_MODE = {"clamp-to-edge": 0, "repeat": 1, "mirror-repeat": 2, "clamp-to-border": 3}
 FILTER_MODE = {"nearest": 0, "linear": 1}
 STEP_MODE = {"vertex": 0, "instance": 1}
-VERTEX_FORMAT = {"float32": 0, "float32x2": 1, "float32x3": 2, "float32x4": 3, "uint32": 4, "sint32": 5}
+VERTEX_FORMAT = {"float32": 0, "float32x2": 1, "float32x3": 2, "float32x4": 3, "uint32": 4, "sint32": 5,
+                 "uint32x2": 6, "uint32x3": 7, "uint32x4": 8, "sint32x2": 9, "sint32x3": 10, "sint32x4": 11}
 STAGE_VERTEX, STAGE_FRAGMENT = 1, 2
 BUFFER_USAGE = {"MAP_READ": 1, "MAP_WRITE": 2, "COPY_SRC": 4, "COPY_DST": 8, "INDEX": 16, "VERTEX": 32, "UNIFORM": 64,
                 "STORAGE": 128}

@@ -267,9 +267,9 @@ uint32_t encode_color(const double c[4], uint32_t format, bool srgb_encode = fal
 uint32_t vertex_format_size(uint32_t f) {
     switch (f) {
         case WGB_VERTEX_FORMAT_FLOAT32: case WGB_VERTEX_FORMAT_UINT32: case WGB_VERTEX_FORMAT_SINT32: return 4;
-        case WGB_VERTEX_FORMAT_FLOAT32X2: return 8;
-        case WGB_VERTEX_FORMAT_FLOAT32X3: return 12;
-        case WGB_VERTEX_FORMAT_FLOAT32X4: return 16;
+        case WGB_VERTEX_FORMAT_FLOAT32X2: case WGB_VERTEX_FORMAT_UINT32X2: case WGB_VERTEX_FORMAT_SINT32X2: return 8;
+        case WGB_VERTEX_FORMAT_FLOAT32X3: case WGB_VERTEX_FORMAT_UINT32X3: case WGB_VERTEX_FORMAT_SINT32X3: return 12;
+        case WGB_VERTEX_FORMAT_FLOAT32X4: case WGB_VERTEX_FORMAT_UINT32X4: case WGB_VERTEX_FORMAT_SINT32X4: return 16;
         default: return 0;
     }
 }
