@@ -190,3 +190,40 @@ struct FOut { @builtin(frag_depth) depth: f32, @location(0) color: vec4f, }
     assert (color.read()[..., 0] == 255).all()
     want = np.float32((5 + 5 * 10 + 5 * 100 + 4 * 1000 - 15) / 65536.0)
     assert (d == want).all(), (d[0, 0], want)
+
+
+def test_explicit_layouts_and_stream_handle(gpu):
+    """hello_mesh.rs:126-142,174-180 creates a bind group layout and a pipeline layout and hands them to the pipeline and
+    the bind group; the frame is the same as with the layouts left out.  The device's render stream is exposed for
+    interop (NCCL presenter, CUDA-event timing)."""
+    from oracle import pyoracle
+    from wgpu_cpu_b200 import api, shaders
+    dev, queue = gpu
+    scene = S.hello_mesh(96, 64)
+    ref = pyoracle.render(scene, want_coverage=False)
+    module = dev.create_shader_module(shaders.wgsl("hello_mesh"))
+    bgl = dev.create_bind_group_layout([(0, 1, 1, 0)])                       # binding 0, vertex stage, buffer, no dynamic offset
+    layout = dev.create_pipeline_layout([bgl])
+    pipe = dev.create_render_pipeline(
+        vertex_module=module, fragment_module=module, layout=layout, front_face=scene.front_face, cull_mode=scene.cull_mode,
+        vertex_buffers=[{"array_stride": 32, "attributes": [("float32x4", 0, 0), ("float32x4", 16, 1)]}],
+        depth_stencil={"depth_compare": "less", "depth_write_enabled": True}, targets=[scene.color_format])
+    vb = dev.create_buffer_init(scene.vertex_buffers[0], api.BUFFER_USAGE["VERTEX"])
+    ib = dev.create_buffer_init(scene.index_data, api.BUFFER_USAGE["INDEX"])
+    ub = dev.create_buffer_init(scene.bindings[(0, 0)][1], api.BUFFER_USAGE["UNIFORM"])
+    group = dev.create_bind_group(bgl, [{"binding": 0, "buffer": ub}])
+    color = dev.create_texture(scene.width, scene.height, scene.color_format)
+    depth = dev.create_texture(scene.width, scene.height, "depth32float")
+    enc = dev.create_command_encoder()
+    with enc.begin_render_pass([{"view": color.create_view(), "load": ("clear", scene.clear_color)}],
+                               {"view": depth.create_view(), "depth_load": ("clear", scene.clear_depth)}) as rp:
+        rp.set_pipeline(pipe)
+        rp.set_bind_group(0, group)
+        rp.set_vertex_buffer(0, vb)
+        rp.set_index_buffer(ib, "uint32")
+        d = scene.draws[0]
+        rp.draw_indexed(range(d.first, d.first + d.count), d.base_vertex, range(d.first_instance, d.first_instance + d.instance_count))
+    dev.poll(True, queue.submit([enc.finish()]))
+    assert np.array_equal(color.read(), ref.color)
+    assert np.array_equal(depth.read().view(np.uint32), ref.depth.view(np.uint32))
+    assert dev.stream() != 0
