@@ -174,6 +174,15 @@ static void fs_early_depth(const FsIn& in, FsOut& out, const Resources&, int*) {
     out.color[0] = color;
 }
 
+/* ---- mrt.wgsl: outputs in declaration order (locations 0, 2, 1) ---- */
+static void fs_mrt(const FsIn& in, FsOut& out, const Resources&, int*) {
+    const Vec4 tint = load_vec4(in.inter + 0);
+    out.num_color = 3;
+    out.color_location[0] = 0; out.color[0] = tint;
+    out.color_location[1] = 2; out.color[1] = {in.position.z, tint.x * tint.y, 0.25f, 1.0f};
+    out.color_location[2] = 1; out.color[2] = {tint.z, tint.y, tint.x, 0.5f};
+}
+
 static const ShaderInfo SHADERS[ORC_SHADER_COUNT] = {
     /* colored_triangle */ {vs_colored_triangle, fs_passthrough_color, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
     /* hello_mesh */       {vs_hello_mesh, fs_passthrough_color, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
@@ -183,6 +192,7 @@ static const ShaderInfo SHADERS[ORC_SHADER_COUNT] = {
     /* frag_depth */       {vs_frag_depth, fs_frag_depth, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
     /* early_force */      {vs_frag_depth, fs_early_depth, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 1},
     /* early_allow */      {vs_frag_depth, fs_early_depth, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 2},
+    /* mrt */              {vs_frag_depth, fs_mrt, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
 };
 
 const ShaderInfo* shader_info(uint32_t shader) {

@@ -28,7 +28,7 @@ FORMAT = {"rgba8unorm": 0, "rgba8unorm-srgb": 1, "bgra8unorm": 2, "bgra8unorm-sr
 ADDRESS = {"clamp-to-edge": 0, "repeat": 1, "mirror-repeat": 2}
 STEP = {"vertex": 0, "instance": 1}
 SHADER = {"colored_triangle": 0, "hello_shader": 0, "hello_mesh": 1, "hello_texture": 2, "procedural": 3,
-          "features": 4, "frag_depth": 5, "early_force": 6, "early_allow": 7}
+          "features": 4, "frag_depth": 5, "early_force": 6, "early_allow": 7, "mrt": 8}
 ATTR_SIZE = {"float32": 4, "float32x2": 8, "float32x3": 12, "float32x4": 16, "uint32": 4, "sint32": 4}
 
 
@@ -132,6 +132,7 @@ class Frame:
     depth: np.ndarray | None   # H x W float32
     coverage: np.ndarray | None  # H x W uint32: fragments that reached the fragment stage
     stats: dict
+    extra_colors: list = None  # further colour attachments, in location order
 
 
 def render(scene, want_coverage: bool = True) -> Frame:
@@ -155,6 +156,17 @@ def render(scene, want_coverage: bool = True) -> Frame:
     if scene.clear_color is not None:
         for k in range(4):
             p.clear_color[0][k] = float(scene.clear_color[k])
+    extra_colors = []
+    for k, (xfmt, xclear) in enumerate(getattr(scene, "extra_targets", None) or [], start=1):
+        xf = FORMAT[xfmt]
+        arr = np.zeros((H, W, {4: 1, 5: 2}.get(xf, 4)), dtype=np.uint8)
+        extra_colors.append(arr)
+        p.color[k] = Texture(_ptr(arr), W, H, xf)
+        p.color_clear[k] = 1 if xclear is not None else 0
+        if xclear is not None:
+            for c in range(4):
+                p.clear_color[k][c] = float(xclear[c])
+        p.num_color = k + 1
     p.ext_features = getattr(scene, "features", 0) & 23
     p.has_depth = 1 if scene.has_depth else 0
     if scene.has_depth:
@@ -199,6 +211,8 @@ def render(scene, want_coverage: bool = True) -> Frame:
         for k in range(4):
             rs.blend_constant[k] = float(scene.blend_constant[k])
     rs.color_write_mask[0] = getattr(scene, "color_write_mask", 15)
+    for k in range(1, 4):
+        rs.color_write_mask[k] = 15
     dyn = {}
     if getattr(scene, "features", 0) & 8 and scene.dynamic_offsets:       # dynamic offsets: the k-th offset moves the k-th dynamic binding
         for g, offs in scene.dynamic_offsets.items():
@@ -247,4 +261,4 @@ def render(scene, want_coverage: bool = True) -> Frame:
                                _ptr(coverage) if coverage is not None else None)
         if e:
             raise RuntimeError(f"orc_draw_execute failed: {e}")
-    return Frame(color, depth, coverage, {f[0]: int(getattr(stats, f[0])) for f in Stats._fields_})
+    return Frame(color, depth, coverage, {f[0]: int(getattr(stats, f[0])) for f in Stats._fields_}, extra_colors)

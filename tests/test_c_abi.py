@@ -239,3 +239,15 @@ def test_ordered_variants_compile_offline():
     # without a depth test the attribute changes nothing: closed-form kernel
     me = dev0.create_shader_module(shaders.wgsl("early_force"))
     assert "#define WGB_RESOLVE 0" in dev0.create_render_pipeline(vertex_module=me, fragment_module=me, vertex_buffers=vbs, targets=["rgba8unorm"]).get_source()
+
+
+def test_multiple_colour_targets_compile_offline(offline):
+    """Three colour attachments: the closed-form and the ordered tile kernel compile for sm_100a with WGB_NUM_COLOR 3."""
+    dev, _ = offline
+    m = dev.create_shader_module(shaders.wgsl("mrt"))
+    vbs = [{"array_stride": 32, "attributes": [("float32x4", 0, 0), ("float32x4", 16, 1)]}]
+    for compare, resolve in (("less", 1), ("not-equal", 7)):
+        p = dev.create_render_pipeline(vertex_module=m, fragment_module=m, vertex_buffers=vbs, targets=["rgba8unorm", "bgra8unorm", "rg8unorm"],
+                                       depth_stencil={"depth_compare": compare, "depth_write_enabled": True})
+        src = p.get_source()
+        assert "#define WGB_NUM_COLOR 3" in src and f"#define WGB_RESOLVE {resolve}" in src and "#define WGB_FS_COLOR_MASK 7" in src

@@ -227,3 +227,24 @@ def test_explicit_layouts_and_stream_handle(gpu):
     assert np.array_equal(color.read(), ref.color)
     assert np.array_equal(depth.read().view(np.uint32), ref.depth.view(np.uint32))
     assert dev.stream() != 0
+
+
+@pytest.mark.parametrize("compare,second_load", [("less", False), ("greater-equal", False), ("less", True), ("not-equal", False)])
+def test_multiple_colour_targets(gpu, compare, second_load):
+    """Three colour attachments (rgba8unorm, bgra8unorm, rg8unorm) written by one fragment stage whose outputs are
+    declared out of location order (fragment.rs:457-488): every attachment bit-exact, with a cleared and a loaded second
+    attachment, through the closed-form tile kernel and (NotEqual + write) the ordered one."""
+    from oracle import pyoracle
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    scene = S.multiple_targets(compare=compare, second_load=second_load)
+    ref = pyoracle.render(scene, want_coverage=False)
+    r = SceneRenderer(dev, queue, scene)
+    r.render()
+    got = r.read()
+    assert np.array_equal(got.color, ref.color)
+    assert np.array_equal(got.depth.view(np.uint32), ref.depth.view(np.uint32))
+    assert len(got.extra_colors) == 2
+    for k, (g, e) in enumerate(zip(got.extra_colors, ref.extra_colors), start=1):
+        assert g.shape == e.shape and np.array_equal(g, e), f"colour attachment {k} differs at {int((g != e).any(axis=2).sum())} pixels"
+    assert ref.extra_colors[0].any() and ref.extra_colors[1][..., 1].any()

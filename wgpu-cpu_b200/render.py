@@ -19,6 +19,7 @@ class Frame:
     depth: Optional[np.ndarray]
     coverage: Optional[np.ndarray]
     stats: dict
+    extra_colors: Optional[list] = None     # further colour attachments, in location order
 
 
 class SceneRenderer:
@@ -77,7 +78,10 @@ class SceneRenderer:
             topology=s.topology, strip_index_format=s.strip_index_format, front_face=s.front_face, cull_mode=s.cull_mode,
             depth_stencil=depth_state,
             targets=[s.color_format if s.color_write_mask == 15 and not s.blend
-                     else {"format": s.color_format, "write_mask": s.color_write_mask, "blend": s.blend}])
+                     else {"format": s.color_format, "write_mask": s.color_write_mask, "blend": s.blend}] +
+                    [fmt for fmt, _ in (s.extra_targets or [])])
+        self.extra_targets = [device.create_texture(s.width, s.height, fmt) for fmt, _ in (s.extra_targets or [])]
+        self.extra_views = [t.create_view() for t in self.extra_targets]
         self.target = target if target is not None else device.create_texture(s.width, s.height, s.color_format)
         self.target_view = self.target.create_view()
         self.depth_texture = self.depth_view = None
@@ -97,7 +101,9 @@ class SceneRenderer:
         if s.has_depth:
             depth = {"view": self.depth_view, "depth_load": ("clear", s.clear_depth) if s.clear_depth is not None else "load",
                      "depth_store": "discard"}
-        with enc.begin_render_pass([color], depth) as rp:
+        colors = [color] + [{"view": v, "load": ("clear", clear) if clear is not None else "load"}
+                            for v, (_, clear) in zip(self.extra_views, s.extra_targets or [])]
+        with enc.begin_render_pass(colors, depth) as rp:
             rp.set_pipeline(self.pipeline)
             for g, bg in self.bind_groups.items():
                 rp.set_bind_group(g, bg, (s.dynamic_offsets or {}).get(g, ()))
@@ -134,7 +140,7 @@ class SceneRenderer:
         color = self.target.read()
         depth = self.depth_texture.read() if self.depth_texture is not None else None
         cov = self.device.read_coverage(s.width, s.height) if want_coverage else None
-        return Frame(color, depth, cov, self.device.last_pass_stats())
+        return Frame(color, depth, cov, self.device.last_pass_stats(), [t.read() for t in self.extra_targets])
 
 
 def render_scene(device: api.Device, queue: api.Queue, scene: Scene, want_coverage: bool = True,

@@ -81,6 +81,7 @@ class Scene:
     blend: Optional[dict] = None                     # {"color": (src, dst, op), "alpha": (src, dst, op)}, FEATURE["BLEND"]
     blend_constant: Tuple[float, float, float, float] = (0.0, 0.0, 0.0, 0.0)
     initial_color: Optional[np.ndarray] = None  # for LoadOp::Load passes
+    extra_targets: Optional[list] = None        # further colour attachments (@location(1..)): [(format, clear colour | None)]
     initial_depth: Optional[np.ndarray] = None
 
     @property
@@ -439,6 +440,20 @@ def early_depth(kind="force", compare="less", width=160, height=120, topology="t
     s.depth_compare = compare
     s.depth_write = True
     s.clear_depth = 0.5 if compare.startswith("greater") else 1.0
+    return s
+
+
+def multiple_targets(width=180, height=130, compare="less", second_load=False) -> Scene:
+    """Three colour attachments of different texel sizes written by one fragment stage whose outputs are declared out
+    of location order (shaders/mrt.wgsl; fragment.rs:457-488 visits them in declaration order and runs the late depth
+    test once, at the first)."""
+    s = random_triangles(width, height, count=120, seed=44, spread=1.1, with_w=False)
+    s.name = f"multiple_targets_{compare}" + ("_load" if second_load else "")
+    s.shader = "mrt"
+    s.color_format = "rgba8unorm"
+    s.depth_compare, s.depth_write = compare, True
+    s.clear_depth = 0.5 if compare.startswith("greater") else 1.0
+    s.extra_targets = [("bgra8unorm", None if second_load else (0.25, 0.5, 0.75, 1.0)), ("rg8unorm", (0.5, 0.125, 0.0, 0.0))]
     return s
 
 
