@@ -248,3 +248,76 @@ def test_multiple_colour_targets(gpu, compare, second_load):
     for k, (g, e) in enumerate(zip(got.extra_colors, ref.extra_colors), start=1):
         assert g.shape == e.shape and np.array_equal(g, e), f"colour attachment {k} differs at {int((g != e).any(axis=2).sum())} pixels"
     assert ref.extra_colors[0].any() and ref.extra_colors[1][..., 1].any()
+
+
+def test_negative_base_vertex_and_first_instance(gpu):
+    """index.rs:45-62: vertex = index + base_vertex with a signed base (indices shifted up by 100, base_vertex = -100), and
+    a draw whose instance range starts at 2 (instance_index reaches the vertex stage as first_instance + k)."""
+    s = S.features()
+    base = s.vertex_buffers[0]
+    s.index_data = (np.arange(180, dtype=np.uint32) + 100)
+    s.draws = [S.Draw(True, 0, 180, -100, 2, 2)]
+    _compare(s, gpu)
+    s.draws = [S.Draw(True, 0, 180, -101, 0, 1)]          # index 100 - 101 underflows: strict_add_signed panics in the reference
+    from wgpu_cpu_b200 import api
+    from wgpu_cpu_b200.render import render_scene
+    with pytest.raises(api.WgpuError):
+        render_scene(gpu[0], gpu[1], s)
+    assert base is s.vertex_buffers[0]
+
+
+def test_bindings_in_higher_groups_and_array_layers(gpu):
+    """Resources in bind groups 1 and 2 (binding.rs:22-52 flattens (group, binding)), and a render pass into array layer 1
+    of a two-layer texture through a view with base_array_layer = 1: layer 0 keeps its bytes."""
+    from wgpu_cpu_b200 import api
+    dev, queue = gpu
+    wgsl = """
+struct A { scale: vec4f, }
+struct B { bias: vec4f, }
+@group(1) @binding(3) var<uniform> a: A;
+@group(2) @binding(0) var<uniform> b: B;
+@vertex fn vs_main(@builtin(vertex_index) i: u32) -> @builtin(position) vec4f {
+    return vec4f(f32(i32(i & 1u) * 4 - 1), f32(i32(i >> 1u) * 4 - 1), 0.5, 1.0);
+}
+@fragment fn fs_main() -> @location(0) vec4f {
+    return vec4f(a.scale.x * b.bias.x, a.scale.y + b.bias.y, a.scale.z - b.bias.z, 1.0);
+}"""
+    m = dev.create_shader_module(wgsl)
+    pipe = dev.create_render_pipeline(vertex_module=m, fragment_module=m, targets=["rgba8unorm"])
+    ua = dev.create_buffer_init(np.array([0.5, 0.25, 0.75, 0.0], dtype=np.float32), api.BUFFER_USAGE["UNIFORM"])
+    ub = dev.create_buffer_init(np.array([0.5, 0.5, 0.25, 0.0], dtype=np.float32), api.BUFFER_USAGE["UNIFORM"])
+    g1 = dev.create_bind_group(None, [{"binding": 3, "buffer": ua}])
+    g2 = dev.create_bind_group(None, [{"binding": 0, "buffer": ub}])
+    tex = dev.create_texture(40, 24, "rgba8unorm", layers=2)
+    enc = dev.create_command_encoder()
+    with enc.begin_render_pass([{"view": tex.create_view(base_array_layer=1), "load": ("clear", (0, 0, 0, 0))}], None) as rp:
+        rp.set_pipeline(pipe)
+        rp.set_bind_group(1, g1)
+        rp.set_bind_group(2, g2)
+        rp.draw(range(0, 3))
+    dev.poll(True, queue.submit([enc.finish()]))
+    texels = tex.read()
+    assert texels.shape == (2, 24, 40, 4)
+    assert not texels[0].any()
+    want = [int(np.float32(0.25) * np.float32(255.0)), int(np.float32(0.75) * np.float32(255.0)), int(np.float32(0.5) * np.float32(255.0)), 255]
+    assert (texels[1] == np.array(want, dtype=np.uint8)).all(), texels[1][0, 0]
+
+
+def test_several_command_buffers_and_submissions_without_waiting(gpu):
+    """Submissions execute in submission order (engine.rs:26-36) whether or not the application waits in between: three
+    scenes submitted back to back (two command buffers in one submit, one in the next), one poll(Wait) at the end."""
+    from oracle import pyoracle
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    scn = [S.random_triangles(count=150, seed=51), S.random_lines(160, 120, 50, 52, "line-list"), S.hello_mesh(120, 90)]
+    rs = [SceneRenderer(dev, queue, s) for s in scn]
+    first = queue.submit([rs[0].encode(), rs[1].encode()])
+    second = queue.submit([rs[2].encode()])
+    assert second == first + 1                                  # device.rs:443-444: monotonically increasing
+    dev.poll(True, second)
+    for r, s in zip(rs, scn):
+        ref = pyoracle.render(s, want_coverage=False)
+        f = r.read()
+        assert np.array_equal(f.color, ref.color), s.name
+        if ref.depth is not None:
+            assert np.array_equal(f.depth.view(np.uint32), ref.depth.view(np.uint32)), s.name

@@ -288,8 +288,8 @@ class Texture(_Handle):
             out = out.reshape(shape)
         _check(_lib.wgb_texture_read(self._h, out.ctypes.data_as(C.c_void_p), C.c_uint64(out.nbytes)))
         if self.format == "depth32float":
-            return out.view(np.float32).reshape(self.layers, self.height, self.width)[0]
-        return out[0]
+            out = out.view(np.float32).reshape(self.layers, self.height, self.width)
+        return out if self.layers > 1 else out[0]      # array textures come back with the layer axis first
 
     def dump_png(self, path: str):
         """wgpu_cpu::dump_texture (lib.rs:111-158)."""
