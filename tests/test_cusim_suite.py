@@ -34,6 +34,6 @@ def test_gpu_suite_on_the_software_model(tmp_path):
     # once more under a shuffled schedule (random start thread, direction and hold-backs per scheduler pass): the frame
     # must not depend on the order in which the threads of a CTA reach their barriers and collectives
     env["CUSIM_SCHED_SEED"] = "7"
-    p = subprocess.run(cmd + [], cwd=ROOT, env=env, capture_output=True, text=True, timeout=3000)
+    p = subprocess.run(cmd + ["-k", "not full_size"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=3000)   # (the 4K / 8K frames ran above)
     tail = "\n".join(p.stdout.splitlines()[-40:])
     assert p.returncode == 0, f"GPU suite failed on the software model under a shuffled schedule:\n{tail}\n{p.stderr[-2000:]}"
