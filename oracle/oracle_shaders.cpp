@@ -183,6 +183,17 @@ static void fs_mrt(const FsIn& in, FsOut& out, const Resources&, int*) {
     out.color_location[2] = 1; out.color[2] = {tint.z, tint.y, tint.x, 0.5f};
 }
 
+/* ---- depth_only.wgsl: no inter-stage values, no outputs ---- */
+static void vs_depth_only(const VsIn& in, VsOut& out, const Resources& res, int* err) {
+    const uint8_t* cam = res.buffer(0, 0, 64, err);
+    const uint8_t* p = need_attr(in, 0, 16, err);
+    if (*err) return;
+    float m[16];
+    std::memcpy(m, cam, 64);
+    out.position = mat4_mul_vec4(m, load_vec4(p));
+}
+static void fs_depth_only(const FsIn&, FsOut& out, const Resources&, int*) { out.num_color = 0; }
+
 static const ShaderInfo SHADERS[ORC_SHADER_COUNT] = {
     /* colored_triangle */ {vs_colored_triangle, fs_passthrough_color, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
     /* hello_mesh */       {vs_hello_mesh, fs_passthrough_color, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
@@ -193,6 +204,7 @@ static const ShaderInfo SHADERS[ORC_SHADER_COUNT] = {
     /* early_force */      {vs_frag_depth, fs_early_depth, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 1},
     /* early_allow */      {vs_frag_depth, fs_early_depth, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 2},
     /* mrt */              {vs_frag_depth, fs_mrt, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
+    /* depth_only */       {vs_depth_only, fs_depth_only, 0, {}, 1},
 };
 
 const ShaderInfo* shader_info(uint32_t shader) {

@@ -41,7 +41,7 @@ def _compare(scene, gpu, use_emitted=False):
                    f"got={got.color[tuple(bad[0])].tolist()} ref={ref.color[tuple(bad[0])].tolist()}")
     assert not msg, f"{scene.name}: " + "; ".join(msg)
     # (the oracle counts stage invocations: fewer than the rasterised fragments once an early depth test rejects some)
-    assert got.stats["fragments"] == ref.stats["fragments_shaded"] or scene.shader in ("features", "early_force", "early_allow"), \
+    assert got.stats["fragments"] == ref.stats["fragments_shaded"] or scene.shader in ("features", "early_force", "early_allow", "depth_only"), \
         f"{scene.name}: fragment count {got.stats['fragments']} != {ref.stats['fragments_shaded']}"
     # the production configuration: no coverage capture, so the hierarchical depth test is active
     fast = render_scene(dev, queue, scene, want_coverage=False, use_emitted=use_emitted)

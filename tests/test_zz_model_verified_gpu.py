@@ -321,3 +321,36 @@ def test_several_command_buffers_and_submissions_without_waiting(gpu):
         assert np.array_equal(f.color, ref.color), s.name
         if ref.depth is not None:
             assert np.array_equal(f.depth.view(np.uint32), ref.depth.view(np.uint32)), s.name
+
+
+@pytest.mark.parametrize("compare", ["less", "greater"])
+def test_depth_only_pass(gpu, compare):
+    """A fragment stage without outputs never reaches the late depth test (it runs at the first @location output,
+    fragment.rs:457-488); with @early_depth_test(force) the early test (fragment.rs:166-194) tests and writes depth.
+    Rendered once next to an (untouched) colour attachment and once as a true depth-only pass."""
+    from oracle import pyoracle
+    from wgpu_cpu_b200 import api, shaders
+    dev, queue = gpu
+    scene = S.random_triangles(200, 140, count=150, seed=71, spread=1.1, with_w=False)
+    scene.name, scene.shader = f"depth_only_{compare}", "depth_only"
+    scene.depth_compare, scene.depth_write, scene.clear_depth = compare, True, (1.0 if compare == "less" else 0.25)
+    got, ref = _compare(scene, gpu)
+    assert (ref.color == ref.color[0, 0]).all() and (ref.depth != scene.clear_depth).any()
+    # no colour attachment at all
+    module = dev.create_shader_module(shaders.wgsl("depth_only"))
+    pipe = dev.create_render_pipeline(
+        vertex_module=module, fragment_module=module, targets=[], front_face=scene.front_face, cull_mode=scene.cull_mode,
+        vertex_buffers=[{"array_stride": 32, "attributes": [("float32x4", 0, 0), ("float32x4", 16, 1)]}],
+        depth_stencil={"depth_compare": compare, "depth_write_enabled": True})
+    vb = dev.create_buffer_init(scene.vertex_buffers[0], api.BUFFER_USAGE["VERTEX"])
+    ub = dev.create_buffer_init(scene.bindings[(0, 0)][1], api.BUFFER_USAGE["UNIFORM"])
+    depth = dev.create_texture(scene.width, scene.height, "depth32float")
+    enc = dev.create_command_encoder()
+    with enc.begin_render_pass([], {"view": depth.create_view(), "depth_load": ("clear", scene.clear_depth)}) as rp:
+        rp.set_pipeline(pipe)
+        rp.set_bind_group(0, dev.create_bind_group(None, [{"binding": 0, "buffer": ub}]))
+        rp.set_vertex_buffer(0, vb)
+        d = scene.draws[0]
+        rp.draw(range(d.first, d.first + d.count))
+    dev.poll(True, queue.submit([enc.finish()]))
+    assert np.array_equal(depth.read().view(np.uint32), ref.depth.view(np.uint32))

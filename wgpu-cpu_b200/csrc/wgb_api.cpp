@@ -502,6 +502,9 @@ struct RenderPipeline : Object {
         // frag_depth after it, or the late test runs as well (Allow): those take the ordered kernel too
         const int early = fs_flag("WGB_FS_EARLY_DEPTH");
         if (test && early != 0 && (early == 2 || fs_flag("WGB_FS_MAY_DISCARD") || fs_flag("WGB_FS_WRITES_FRAG_DEPTH"))) mode = 7;
+        // ... and a stage without colour outputs never reaches the late test (it runs at the first @location output,
+        // fragment.rs:457-488): its early test is then the only one that writes depth (a depth-only pass)
+        if (test && early != 0 && fs_flag("WGB_FS_COLOR_MASK") == 0) mode = 7;
         std::string s;
         char line[256];
         auto def = [&](const char* name, long long v) { snprintf(line, sizeof(line), "#define %s %lld\n", name, v); s += line; };
