@@ -194,6 +194,15 @@ static void vs_depth_only(const VsIn& in, VsOut& out, const Resources& res, int*
 }
 static void fs_depth_only(const FsIn&, FsOut& out, const Resources&, int*) { out.num_color = 0; }
 
+/* ---- prim_index.wgsl ---- */
+static void fs_prim_index(const FsIn& in, FsOut& out, const Resources&, int*) {
+    const float low = (float)(in.primitive_index & 255u) / 255.0f;
+    const float high = (float)((in.primitive_index >> 8) & 255u) / 255.0f;
+    out.num_color = 1;
+    out.color_location[0] = 0;
+    out.color[0] = {low, high, (float)in.sample_index + (float)(in.sample_mask & 1u) * 0.5f, 1.0f};
+}
+
 static const ShaderInfo SHADERS[ORC_SHADER_COUNT] = {
     /* colored_triangle */ {vs_colored_triangle, fs_passthrough_color, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
     /* hello_mesh */       {vs_hello_mesh, fs_passthrough_color, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
@@ -205,6 +214,7 @@ static const ShaderInfo SHADERS[ORC_SHADER_COUNT] = {
     /* early_allow */      {vs_frag_depth, fs_early_depth, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 2},
     /* mrt */              {vs_frag_depth, fs_mrt, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
     /* depth_only */       {vs_depth_only, fs_depth_only, 0, {}, 1},
+    /* prim_index */       {vs_depth_only, fs_prim_index, 0, {}, 0},
 };
 
 const ShaderInfo* shader_info(uint32_t shader) {

@@ -354,3 +354,27 @@ def test_depth_only_pass(gpu, compare):
         rp.draw(range(d.first, d.first + d.count))
     dev.poll(True, queue.submit([enc.finish()]))
     assert np.array_equal(depth.read().view(np.uint32), ref.depth.view(np.uint32))
+
+
+@pytest.mark.parametrize("kind", ["list_culled_clipped_instanced", "strip_with_restart", "lines", "not_equal_ordered"])
+def test_primitive_index_sample_index_and_mask(gpu, kind):
+    """@builtin(primitive_index) is the primitive's position in its instance's assembly order, counted before culling and
+    clipping and restarting with every instance (state.rs:519-541); sample_index is 0 and sample_mask all ones."""
+    if kind == "list_culled_clipped_instanced" or kind == "not_equal_ordered":
+        s = S.random_triangles(220, 160, count=400, seed=81, spread=1.4)
+        s.cull_mode, s.front_face = "back", "ccw"
+        s.draws = [S.Draw(False, 0, 1200, 0, 0, 2)]
+        if kind == "not_equal_ordered":
+            s.depth_compare, s.depth_write, s.clear_depth = "not-equal", True, 0.5
+    elif kind == "lines":
+        s = S.random_lines(200, 150, 300, 82, "line-strip")
+    elif kind == "strip_with_restart":
+        rng = np.random.default_rng(83)
+        s = S.random_triangles(220, 160, count=200, seed=83, spread=1.2, with_w=False)
+        idx = rng.integers(0, 600, 900).astype(np.uint16)
+        idx[rng.random(900) < 0.1] = 0xFFFF
+        s.topology, s.strip_index_format, s.index_data = "triangle-strip", "uint16", idx
+        s.draws = [S.Draw(True, 0, 900, 0, 0, 1)]
+    s.name, s.shader = f"prim_index_{kind}", "prim_index"
+    got, ref = _compare(s, gpu)
+    assert len(np.unique(ref.color[..., 0])) > 20 and (ref.color[..., 2] == 127).any()
