@@ -545,7 +545,7 @@ static bool process_vertex(DrawCtx& cx, uint32_t instance_index, uint32_t vertex
 
 /* fragment.rs:319-377 interpolate_user + util/interpolation.rs:149-163.
  * `coeff` has n entries; n == 1 selects vertex 0 without arithmetic (NoInterpolation). */
-static bool build_varyings(DrawCtx& cx, int n, const float* coeff, const VertexOut* const* vin, uint8_t out[64]) {
+static bool build_varyings(DrawCtx& cx, int n, const float* coeff, const float* frag_w, const VertexOut* const* vin, uint8_t out[64]) {
     std::memset(out, 0, 64);
     for (int l = 0; l < cx.sh->num_varyings; l++) {
         const VaryingLayout& vl = cx.sh->varyings[l];
@@ -554,7 +554,26 @@ static bool build_varyings(DrawCtx& cx, int n, const float* coeff, const VertexO
             std::memcpy(out + vl.offset, vin[0]->inter + vl.offset, 4 * vl.ncomp);       /* FlatSampling: vertex 0 */
             continue;
         }
-        if (vl.interp == INTERP_PERSPECTIVE) { cx.err = ORC_ERR_UNSUPPORTED; return false; }   /* fragment.rs:343-345 todo!() */
+        if (vl.interp == INTERP_PERSPECTIVE) {
+            /* NOT IN THE REFERENCE (fragment.rs:343-345 is todo!()): WebGPU's perspective-correct interpolation,
+             * sum(v_k B_k w_k) / sum(B_k w_k) with w_k = 1 / clip.w of the rasterised vertices (the fourth component of
+             * to_raster's fragment, raster.rs:156) -- every product and sum a separate f32 operation, left to right */
+            float bw[3] = {0.0f, 0.0f, 0.0f};
+            for (int k = 0; k < n; k++) bw[k] = coeff[k] * frag_w[k];
+            for (uint32_t c = 0; c < vl.ncomp; c++) {
+                float p[3];
+                for (int k = 0; k < n; k++) std::memcpy(&p[k], vin[k]->inter + vl.offset + 4 * c, 4);
+                float value;
+                if (n == 1) value = p[0];
+                else {
+                    float num = p[0] * bw[0], den = 1.0f * bw[0];
+                    for (int k = 1; k < n; k++) { num = num + p[k] * bw[k]; den = den + 1.0f * bw[k]; }
+                    value = num / den;
+                }
+                std::memcpy(out + vl.offset + 4 * c, &value, 4);
+            }
+            continue;
+        }
         for (uint32_t c = 0; c < vl.ncomp; c++) {
             float p[3];
             for (int k = 0; k < n; k++) std::memcpy(&p[k], vin[k]->inter + vl.offset + 4 * c, 4);
@@ -588,7 +607,7 @@ static bool depth_test(DrawCtx& cx, uint32_t x, uint32_t y, float frag_depth) {
 
 /* FragmentProcessingState::process (fragment.rs:127-214) */
 static void process_fragment(DrawCtx& cx, int n, const VertexOut* const* unclipped, bool front_facing,
-                             uint32_t primitive_index, uint32_t fx, uint32_t fy, Vec4 fragment, const float* coeff) {
+                             uint32_t primitive_index, uint32_t fx, uint32_t fy, Vec4 fragment, const float* coeff, const float* frag_w) {
     if (cx.err) return;
     for (uint32_t c = 0; c < cx.pass->num_color; c++)
         if (fx >= cx.pass->color[c].width || fy >= cx.pass->color[c].height) { cx.err = ORC_ERR_OUT_OF_BOUNDS; return; }
@@ -601,7 +620,7 @@ static void process_fragment(DrawCtx& cx, int n, const VertexOut* const* unclipp
     in.primitive_index = primitive_index;
     in.sample_index = 0;
     in.sample_mask = ~0u;
-    if (!build_varyings(cx, n, coeff, unclipped, in.inter)) return;
+    if (!build_varyings(cx, n, coeff, frag_w, unclipped, in.inter)) return;
 
     float frag_depth = fragment.z;
     bool have_result = false, result = false;
@@ -701,7 +720,8 @@ static void rasterize_tri(DrawCtx& cx, const ClipTri& tri, const VertexOut* cons
             Vec4 f = v4_scale(frag[0], B.c[0]);
             f = v4_add(f, v4_scale(frag[1], B.c[1]));
             f = v4_add(f, v4_scale(frag[2], B.c[2]));
-            process_fragment(cx, 3, unclipped, front_facing, primitive_index, x, y, f, B.c);
+            const float fw[3] = {frag[0].w, frag[1].w, frag[2].w};
+            process_fragment(cx, 3, unclipped, front_facing, primitive_index, x, y, f, B.c, fw);
         }
     });
 }
@@ -722,7 +742,8 @@ static void rasterize_line(DrawCtx& cx, const Vec4 clipped[2], const float alpha
         const float tt = alphas[0] * (1.0f - t) + alphas[1] * t;
         const float c[2] = {1.0f - tt, tt};
         const Vec4 f = v4_add(v4_scale(fs, c[0]), v4_scale(fe, c[1]));
-        process_fragment(cx, 2, unclipped, true, primitive_index, pt[0], pt[1], f, c);
+        const float fw[2] = {fs.w, fe.w};
+        process_fragment(cx, 2, unclipped, true, primitive_index, pt[0], pt[1], f, c, fw);
     }
 }
 
@@ -733,7 +754,8 @@ static void rasterize_point(DrawCtx& cx, const VertexOut* const* unclipped, uint
     if (!cx.target.to_raster(unclipped[0]->clip, p, f)) { cx.err = ORC_ERR_W_ZERO; return; }
     if (!cx.target.in_scissor(p[0], p[1])) return;
     const float c[1] = {1.0f};
-    process_fragment(cx, 1, unclipped, true, primitive_index, p[0], p[1], f, c);
+    const float fw[1] = {f.w};
+    process_fragment(cx, 1, unclipped, true, primitive_index, p[0], p[1], f, c, fw);
 }
 
 struct Item { bool separator; VertexOut v; };

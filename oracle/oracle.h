@@ -58,7 +58,8 @@ enum { ORC_SHADER_COLORED_TRIANGLE = 0, /* colored_triangle.wgsl == hello_shader
        ORC_SHADER_MRT = 8,              /* wgpu_b200/shaders/mrt.wgsl: three colour attachments */
        ORC_SHADER_DEPTH_ONLY = 9,       /* wgpu_b200/shaders/depth_only.wgsl: no fragment outputs, @early_depth_test(force) */
        ORC_SHADER_PRIM_INDEX = 10,      /* wgpu_b200/shaders/prim_index.wgsl: primitive_index, sample_index, sample_mask */
-       ORC_SHADER_COUNT = 11 };
+       ORC_SHADER_PERSPECTIVE = 11,     /* wgpu_b200/shaders/perspective.wgsl: default (perspective-correct) interpolation -- not in the reference */
+       ORC_SHADER_COUNT = 12 };
 
 enum { ORC_OK = 0, ORC_ERR_INVALID = 1, ORC_ERR_OUT_OF_BOUNDS = 2, ORC_ERR_UNSUPPORTED = 3,
        ORC_ERR_W_ZERO = 4 };

@@ -203,6 +203,32 @@ static void fs_prim_index(const FsIn& in, FsOut& out, const Resources&, int*) {
     out.color[0] = {low, high, (float)in.sample_index + (float)(in.sample_mask & 1u) * 0.5f, 1.0f};
 }
 
+/* ---- perspective.wgsl: inter-stage layout vec4 @0, vec2 @16, f32 @24 (bindings.rs:307-346) ---- */
+static void vs_perspective(const VsIn& in, VsOut& out, const Resources& res, int* err) {
+    const uint8_t* cam = res.buffer(0, 0, 64, err);
+    const uint8_t* p = need_attr(in, 0, 16, err);
+    const uint8_t* c = need_attr(in, 1, 16, err);
+    if (*err) return;
+    float m[16];
+    std::memcpy(m, cam, 64);
+    out.position = mat4_mul_vec4(m, load_vec4(p));
+    const Vec4 tint = load_vec4(c);
+    store_vec4(out.inter + 0, tint);
+    std::memcpy(out.inter + 16, &tint.x, 4);
+    std::memcpy(out.inter + 20, &tint.y, 4);
+    std::memcpy(out.inter + 24, &tint.z, 4);
+}
+static void fs_perspective(const FsIn& in, FsOut& out, const Resources&, int*) {
+    const Vec4 corrected = load_vec4(in.inter + 0);
+    float sx, sy, flat;
+    std::memcpy(&sx, in.inter + 16, 4);
+    std::memcpy(&sy, in.inter + 20, 4);
+    std::memcpy(&flat, in.inter + 24, 4);
+    out.num_color = 1;
+    out.color_location[0] = 0;
+    out.color[0] = {corrected.x, corrected.y * 0.5f + sy * 0.5f, sx, flat};
+}
+
 static const ShaderInfo SHADERS[ORC_SHADER_COUNT] = {
     /* colored_triangle */ {vs_colored_triangle, fs_passthrough_color, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
     /* hello_mesh */       {vs_hello_mesh, fs_passthrough_color, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
@@ -215,6 +241,8 @@ static const ShaderInfo SHADERS[ORC_SHADER_COUNT] = {
     /* mrt */              {vs_frag_depth, fs_mrt, 1, {{0, 0, 4, VAR_F32, INTERP_LINEAR}}, 0},
     /* depth_only */       {vs_depth_only, fs_depth_only, 0, {}, 1},
     /* prim_index */       {vs_depth_only, fs_prim_index, 0, {}, 0},
+    /* perspective */      {vs_perspective, fs_perspective, 3, {{0, 0, 4, VAR_F32, INTERP_PERSPECTIVE}, {1, 16, 2, VAR_F32, INTERP_LINEAR},
+                                                                 {2, 24, 1, VAR_F32, INTERP_FLAT}}, 0},
 };
 
 const ShaderInfo* shader_info(uint32_t shader) {

@@ -28,7 +28,7 @@ FORMAT = {"rgba8unorm": 0, "rgba8unorm-srgb": 1, "bgra8unorm": 2, "bgra8unorm-sr
 ADDRESS = {"clamp-to-edge": 0, "repeat": 1, "mirror-repeat": 2}
 STEP = {"vertex": 0, "instance": 1}
 SHADER = {"colored_triangle": 0, "hello_shader": 0, "hello_mesh": 1, "hello_texture": 2, "procedural": 3,
-          "features": 4, "frag_depth": 5, "early_force": 6, "early_allow": 7, "mrt": 8, "depth_only": 9, "prim_index": 10}
+          "features": 4, "frag_depth": 5, "early_force": 6, "early_allow": 7, "mrt": 8, "depth_only": 9, "prim_index": 10, "perspective": 11}
 ATTR_SIZE = {"float32": 4, "float32x2": 8, "float32x3": 12, "float32x4": 16, "uint32": 4, "sint32": 4}
 
 

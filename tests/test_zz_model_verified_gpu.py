@@ -378,3 +378,19 @@ def test_primitive_index_sample_index_and_mask(gpu, kind):
     s.name, s.shader = f"prim_index_{kind}", "prim_index"
     got, ref = _compare(s, gpu)
     assert len(np.unique(ref.color[..., 0])) > 20 and (ref.color[..., 2] == 127).any()
+
+
+@pytest.mark.parametrize("topology", ["triangle-list", "line-list", "point-list"])
+def test_perspective_correct_interpolation(gpu, topology):
+    """WGSL's default interpolation is perspective-correct; the reference panics on it (fragment.rs:343-345 todo!()), so the
+    oracle restates WebGPU's formula -- sum(v_k B_k / w_k) / sum(B_k / w_k) -- and the frame must match it bit for bit,
+    clipped primitives included.  A linear and a flat varying ride along; the corrected one must differ from the linear."""
+    if topology == "triangle-list":
+        s = S.random_triangles(220, 160, count=160, seed=91, spread=1.3, with_w=True)
+    else:
+        s = S.random_lines(220, 160, 120, 92, topology)
+    s.name, s.shader = f"perspective_{topology}", "perspective"
+    got, ref = _compare(s, gpu)
+    if topology != "point-list":
+        # red = perspective-corrected tint.x, blue = the same value interpolated linearly in screen space
+        assert (ref.color[..., 0].astype(int) != ref.color[..., 2].astype(int)).sum() > 200

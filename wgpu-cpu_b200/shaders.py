@@ -6,7 +6,7 @@ from __future__ import annotations
 import os
 
 _DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shaders")
-NAMES = ("index_triangle", "mesh_vertex_color", "mesh_textured", "procedural", "features", "frag_depth", "early_force", "early_allow", "mrt", "depth_only", "prim_index")
+NAMES = ("index_triangle", "mesh_vertex_color", "mesh_textured", "procedural", "features", "frag_depth", "early_force", "early_allow", "mrt", "depth_only", "prim_index", "perspective")
 # the scenes keep the names of the reference programs they restate (scenes.py, oracle shader ids)
 ALIASES = {"colored_triangle": "index_triangle", "hello_shader": "index_triangle", "hello_mesh": "mesh_vertex_color",
            "hello_texture": "mesh_textured"}
