@@ -394,3 +394,50 @@ def test_perspective_correct_interpolation(gpu, topology):
     if topology != "point-list":
         # red = perspective-corrected tint.x, blue = the same value interpolated linearly in screen space
         assert (ref.color[..., 0].astype(int) != ref.color[..., 2].astype(int)).sum() > 200
+
+
+@pytest.mark.parametrize("name,blend", [
+    ("src_factors", {"color": ("src", "one-minus-src", "add"), "alpha": ("one-minus-dst-alpha", "one-minus-dst", "add")}),
+    ("dst_factors", {"color": ("one-minus-dst", "src", "subtract"), "alpha": ("one-minus-src", "one-minus-dst-alpha", "reverse-subtract")})])
+def test_blend_factors_not_covered_elsewhere(ext, name, blend):
+    """Src, OneMinusSrc, OneMinusDst and OneMinusDstAlpha (the kernel-coverage run of tests/cusim showed that no other
+    blending case selects them)."""
+    from wgpu_cpu_b200 import api
+    scene = S.random_triangles(count=200, seed=6, color_format="bgra8unorm", depth_compare=None, depth_write=False)
+    _translucent(scene, 10)
+    scene.features = api.FEATURE["BLEND"]
+    scene.blend = blend
+    scene.clear_color = (0.2, 0.6, 0.4, 0.7)
+    got, ref = _render_both(scene, ext)
+    assert np.array_equal(got.color, ref.color)
+
+
+def test_clear_only_pass_and_ordered_kernel_with_exact_bins(gpu, monkeypatch):
+    """A render pass without a draw still applies its LoadOp::Clear (State::load, state.rs:135-145): that is the clear
+    kernel, which nothing else reaches.  And the ordered tile kernel over exact-size bins (count / scan / fill instead of
+    direct binning, WGB_NO_DIRECT_BINS=1)."""
+    from oracle import pyoracle
+    from wgpu_cpu_b200 import api
+    from wgpu_cpu_b200.render import render_scene
+    dev, queue = gpu
+    for w, h in ((70, 45), (64, 64)):
+        color = dev.create_texture(w, h, "bgra8unorm")
+        extra = dev.create_texture(w, h, "rg8unorm")
+        depth = dev.create_texture(w, h, "depth32float")
+        enc = dev.create_command_encoder()
+        with enc.begin_render_pass([{"view": color.create_view(), "load": ("clear", (0.25, 0.5, 1.0, 0.0))},
+                                    {"view": extra.create_view(), "load": ("clear", (1.0, 0.5, 0.0, 0.0))}],
+                                   {"view": depth.create_view(), "depth_load": ("clear", 0.375)}):
+            pass
+        dev.poll(True, queue.submit([enc.finish()]))
+        assert (color.read() == np.array([255, 127, 63, 0], dtype=np.uint8)).all()          # B G R A
+        assert (extra.read() == np.array([255, 127], dtype=np.uint8)).all()
+        assert (depth.read() == np.float32(0.375)).all()
+    monkeypatch.setenv("WGB_NO_DIRECT_BINS", "1")
+    dev2, queue2 = api.instance().request_adapter().request_device(0)
+    monkeypatch.delenv("WGB_NO_DIRECT_BINS")
+    scene = S.random_triangles(count=250, seed=77, clear_depth=0.5)
+    scene.depth_compare, scene.depth_write = "not-equal", True
+    ref = pyoracle.render(scene, want_coverage=False)
+    got = render_scene(dev2, queue2, scene, want_coverage=False)
+    assert np.array_equal(got.color, ref.color) and np.array_equal(got.depth.view(np.uint32), ref.depth.view(np.uint32))

@@ -118,6 +118,7 @@ CASES = [
     ("int_div_zero_defined", "", "var a: i32 = 9; var z: i32 = 0;", "f32(a / z) + f32(a % z)", 9.0),
     ("bits_count", "", "var a: u32 = 0xF0u; var b: i32 = 8;", "f32(countOneBits(a) + firstLeadingBit(16u)) + 10.0 * f32(countTrailingZeros(b)) + 100.0 * f32(countLeadingZeros(a))", 8.0 + 30.0 + 2400.0),
     ("bits_extract", "", "var a: u32 = 0xABCDu; var n: i32 = -16;", "f32(extractBits(a, 4u, 8u)) + f32(extractBits(n, 2u, 4u))", 188.0 - 4.0),
+    ("bits_insert_none", "", "var e: u32 = 0xF0F0u; let w = insertBits(e, 0xFFFFu, 40u, 3u); let v = insertBits(e, 0xFFFFu, 4u, 0u);", "f32(w) + f32(v)", float(0xF0F0 * 2)),
     ("bits_insert_vec", "", "var e = vec2i(0, -1); let w = insertBits(e, vec2i(5, 0), 4u, 3u);", "f32(w.x) + f32(w.y)", 80.0 - 113.0),
     ("bits_reverse_first", "", "var a: u32 = 1u; var z: u32 = 0u; var m: i32 = -1;", "f32(reverseBits(a) >> 31u) + f32(firstTrailingBit(12u)) + f32(firstLeadingBit(m)) + f32(firstTrailingBit(z) == 0xFFFFFFFFu)", 1.0 + 2.0 - 1.0 + 1.0),
     ("bitcast", "", "var a: f32 = 1.0;", "f32(bitcast<u32>(a) >> 23u)", 127.0),
