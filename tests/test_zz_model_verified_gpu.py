@@ -441,3 +441,16 @@ def test_clear_only_pass_and_ordered_kernel_with_exact_bins(gpu, monkeypatch):
     ref = pyoracle.render(scene, want_coverage=False)
     got = render_scene(dev2, queue2, scene, want_coverage=False)
     assert np.array_equal(got.color, ref.color) and np.array_equal(got.depth.view(np.uint32), ref.depth.view(np.uint32))
+
+
+def test_vertex_attributes_that_are_only_four_byte_aligned(gpu):
+    """A 28-byte vertex (position, one pad word, uv) leaves the float32x2 attribute on 4-byte boundaries and the float32x4
+    one on 4- or 8-byte ones for most vertices: the scalar fetch paths behind the 128-bit / 64-bit ones."""
+    s = S.hello_texture(200, 150)
+    v = s.vertex_buffers[0].view(np.float32).reshape(-1, 6)
+    padded = np.zeros((v.shape[0], 7), dtype=np.float32)
+    padded[:, 0:4], padded[:, 5:7] = v[:, 0:4], v[:, 4:6]
+    s.vertex_buffers = [padded.view(np.uint8).reshape(-1)]
+    s.vertex_layouts = [S.VertexBufferLayout(28, "vertex", [S.VertexAttribute(0, "float32x4", 0), S.VertexAttribute(1, "float32x2", 20)])]
+    s.name = "hello_texture_unaligned_attributes"
+    _compare(s, gpu)
