@@ -12,8 +12,12 @@ LIB = os.path.join(OUT, "libwgpu_b200_sim.so")
 
 
 def build(force: bool = False) -> str:
+    """CUSIM_HOST_COVERAGE=1: an -O0 --coverage build (libwgpu_b200_sim_cov.so; the .gcno / .gcda files land in _build/),
+    for measuring which lines of the host runtime and the WGSL emitter the tests execute."""
     import importlib
     import sys
+    coverage = os.environ.get("CUSIM_HOST_COVERAGE") == "1"
+    lib = os.path.join(OUT, "libwgpu_b200_sim_cov.so") if coverage else LIB
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     product = importlib.import_module("wgpu_cpu_b200.build")
@@ -21,13 +25,13 @@ def build(force: bool = False) -> str:
     srcs = [os.path.join(CSRC, "wgb_api.cpp"), os.path.join(CSRC, "wgsl_emit.cpp"), emb, os.path.join(HERE, "cusim_host.cpp")]
     deps = srcs + [os.path.join(HERE, "include", f) for f in os.listdir(os.path.join(HERE, "include"))] + [
         os.path.join(CSRC, "wgb_shared.h"), os.path.join(ROOT, "include", "wgpu_b200.h"), os.path.abspath(__file__)]
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
-        return LIB
+    if not force and os.path.exists(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps):
+        return lib
     os.makedirs(OUT, exist_ok=True)
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-w", f"-I{os.path.join(HERE, 'include')}",
-           f'-DCUSIM_DIR="{HERE}"', *srcs, "-o", LIB, "-ldl", "-lpthread"]
-    subprocess.check_call(cmd)
-    return LIB
+    cmd = ["g++", *(["-O0", "--coverage"] if coverage else ["-O1"]), "-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-w",
+           f"-I{os.path.join(HERE, 'include')}", f'-DCUSIM_DIR="{HERE}"', *srcs, "-o", lib, "-ldl", "-lpthread"]
+    subprocess.check_call(cmd, cwd=OUT)
+    return lib
 
 
 def build_example() -> str:

@@ -454,3 +454,45 @@ def test_vertex_attributes_that_are_only_four_byte_aligned(gpu):
     s.vertex_layouts = [S.VertexBufferLayout(28, "vertex", [S.VertexAttribute(0, "float32x4", 0), S.VertexAttribute(1, "float32x2", 20)])]
     s.name = "hello_texture_unaligned_attributes"
     _compare(s, gpu)
+
+
+@pytest.mark.parametrize("name", ["hello_mesh", "hello_texture", "features", "frag_depth"])
+def test_pre_emitted_shader_modules(gpu, name):
+    """wgb_shader_module_descriptor.emitted: a host that runs its own WGSL / naga-IR front end hands the CUDA C++ of each
+    entry point to the library instead of WGSL.  The golden emitter output of the built-in shaders,
+    fed back this way, renders the same frame."""
+    scene = {"hello_mesh": lambda: S.hello_mesh(128, 96), "hello_texture": lambda: S.hello_texture(160, 100),
+             "features": S.features, "frag_depth": S.frag_depth}[name]()
+    _compare(scene, gpu, use_emitted=True)
+
+
+def test_queue_write_buffer_ranges_timer_and_device_pointer(gpu, tmp_path):
+    """Queue::write_buffer with an offset updates that range only (the reference's copy_from_slice on the whole buffer
+    only works for whole-buffer writes, device.rs:341-343 / buffer.rs:297-309 -- the intended semantics are implemented);
+    a frame rendered after the update sees it.  Also: the CUDA-event timer around submissions, the texel storage's
+    device pointer, and dump_texture of a BGRA target."""
+    from oracle import pyoracle
+    from tests.test_c_abi import _decode_png
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    scene = S.random_triangles(160, 120, count=120, seed=95, color_format="bgra8unorm")
+    r = SceneRenderer(dev, queue, scene)
+    dev.timer_begin()
+    r.render()
+    assert dev.timer_end() > 0.0
+    before = r.read().color
+    assert np.array_equal(before, pyoracle.render(scene, want_coverage=False).color)
+    # move the second half of the vertices: 60 triangles x 3 vertices x 32 bytes, written at their byte offset
+    v = scene.vertex_buffers[0].view(np.float32).reshape(-1, 8).copy()
+    v[180:, 0] = -v[180:, 0]
+    queue.write_buffer(r.vertex_buffers[0], 180 * 32, v[180:])
+    scene.vertex_buffers[0] = v.view(np.uint8).reshape(-1)
+    r.render()
+    after = r.read().color
+    assert np.array_equal(after, pyoracle.render(scene, want_coverage=False).color) and not np.array_equal(after, before)
+    ptr, nbytes = r.target.device_pointer()
+    assert ptr != 0 and nbytes == 160 * 120 * 4
+    r.target.dump_png(str(tmp_path / "bgra.png"))
+    assert np.array_equal(_decode_png(str(tmp_path / "bgra.png")), after[..., [2, 1, 0, 3]])      # PNGs are RGBA
+    with pytest.raises(Exception):
+        queue.write_buffer(r.vertex_buffers[0], scene.vertex_buffers[0].nbytes - 16, np.zeros(32, dtype=np.uint8))   # past the end
