@@ -113,3 +113,24 @@ struct Tail { head: vec4f, items: array<vec3f>, }
     import pytest
     with pytest.raises(api.WgpuError):
         api.translate_wgsl(src.replace("arrayLength(&tail.items)", "arrayLength(&tail.head)"), api.STAGE_VERTEX, "main")
+
+
+def test_only_the_entry_points_call_graph_is_emitted():
+    """A module shared by both stages may hold helpers that are valid in one stage only: a helper that discards must not
+    stop the vertex stage of the same module from translating (it is outside that entry point's call graph), while a
+    vertex entry point that does call it is an error."""
+    src = """
+fn cut(x: f32) -> f32 { if (x > 3.0) { discard; } return x; }
+fn unused_everywhere() -> f32 { return 1.0; }
+fn shared_helper(x: f32) -> f32 { return x * 2.0; }
+@vertex fn vs_main(@location(0) a: vec4f) -> @builtin(position) vec4f { return vec4f(shared_helper(a.x), a.y, a.z, a.w); }
+@fragment fn fs_main(@builtin(position) p: vec4f) -> @location(0) vec4f { return vec4f(cut(shared_helper(p.x))); }
+"""
+    vs = api.translate_wgsl(src, api.STAGE_VERTEX, "vs_main")
+    assert "shared_helper(" in vs and "cut(" not in vs and "unused_everywhere" not in vs
+    fs = api.translate_wgsl(src, api.STAGE_FRAGMENT, "fs_main")
+    assert "cut(" in fs and "shared_helper(" in fs and "unused_everywhere" not in fs and "#define WGB_FS_MAY_DISCARD 1" in fs
+    bad = src.replace("vec4f(shared_helper(a.x), a.y", "vec4f(cut(a.x), a.y")
+    with pytest.raises(api.WgpuError) as e:
+        api.translate_wgsl(bad, api.STAGE_VERTEX, "vs_main")
+    assert "discard" in str(e.value)

@@ -66,3 +66,29 @@ def test_array_length_of_storage_bindings(gpu):
             "f32(n) + 1000.0 * f32(m) + 0.25 * tail.items[1].y + 0.125 * f32(what_len_is_this_array[2])", 0.0)
     got = evaluate(dev, queue, module_for(case), [{"binding": 0, "buffer": a}, {"binding": 1, "buffer": b}])
     assert got == np.float32(123 + 9000 + 1.25 + 0.875)
+
+
+def test_texture_queries_loads_and_whole_value_uniform_loads(gpu):
+    """textureDimensions / textureLoad (image.rs:107,119 are todo!() in the reference) and loads of a whole struct and a
+    whole array out of a uniform buffer (each member / element fetched at its layout offset)."""
+    from wgpu_cpu_b200 import api
+    dev, queue = gpu
+    img = np.zeros((3, 5, 4), dtype=np.uint8)               # 5 wide, 3 high
+    img[2, 4] = [255, 51, 102, 255]
+    tex = dev.create_texture_with_data(queue, 5, 3, "rgba8unorm", img)
+    data = np.zeros(4 + 4 * 2 + 4 * 3, dtype=np.float32)    # m: vec4f | lights: 2 x {dir vec3f, power f32} | table: array<vec4f, 3>
+    data[0:4] = [1.0, 2.0, 3.0, 4.0]
+    data[4:8] = [0.5, 0.25, 0.125, 7.0]
+    data[8:12] = [9.0, 8.0, 7.0, 11.0]
+    data[12:24] = np.arange(12, dtype=np.float32)
+    ub = dev.create_buffer_init(data, api.BUFFER_USAGE["UNIFORM"])
+    case = ("texture_and_whole_loads",
+            "struct Light { dir: vec3f, power: f32, }\nstruct U { m: vec4f, lights: array<Light, 2>, table: array<vec4f, 3>, }\n"
+            "@group(0) @binding(0) var<uniform> u: U;\n@group(0) @binding(1) var t: texture_2d<f32>;",
+            "let d = textureDimensions(t); let px = textureLoad(t, vec2i(4, 2), 0); let light = u.lights[1]; let table = u.table; var k = 2;",
+            "f32(d.x) * 1000.0 + f32(d.y) * 100.0 + px.x + px.y * 5.0 + light.dir.y + light.power + table[k].w + table[0].y", 0.0)
+    got = evaluate(dev, queue, module_for(case), [{"binding": 0, "buffer": ub}, {"binding": 1, "texture_view": tex.create_view()}])
+    want = np.float32(5000.0 + 300.0)
+    for term in (1.0, np.float32(np.float32(51.0 / 255.0) * np.float32(5.0)), 8.0, 11.0, 11.0, 1.0):
+        want = np.float32(want + np.float32(term))
+    assert got == want, (got, want)

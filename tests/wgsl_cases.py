@@ -123,6 +123,17 @@ CASES = [
     ("bits_reverse_first", "", "var a: u32 = 1u; var z: u32 = 0u; var m: i32 = -1;", "f32(reverseBits(a) >> 31u) + f32(firstTrailingBit(12u)) + f32(firstLeadingBit(m)) + f32(firstTrailingBit(z) == 0xFFFFFFFFu)", 1.0 + 2.0 - 1.0 + 1.0),
     ("bitcast", "", "var a: f32 = 1.0;", "f32(bitcast<u32>(a) >> 23u)", 127.0),
     ("let_shadowing", "", "let a = 1.0; var b = a; { let a = 5.0; b = b + a; }", "a + b", 7.0),
+    # syntax and constructor forms no other case reaches (found by the emitter-coverage run over tests/cusim)
+    ("block_comments", "/* outer /* nested */ still a comment */ const K = 7;", "/* in a body */", "f32(K)", 7.0),
+    ("exponent_literals", "", "let a = 1.5e2; let b = 2E-1f; let c = 1e+1;", "(a + b) + c", float(__import__("numpy").float32(__import__("numpy").float32(150.0) + __import__("numpy").float32(0.2)) + __import__("numpy").float32(10.0))),
+    ("template_types", "", "let m = mat3x3<f32>(vec3<f32>(1.0, 2.0, 3.0), vec3<f32>(4.0, 5.0, 6.0), vec3<f32>(7.0, 8.0, 9.0)); let v = m * vec3<f32>(1.0, 0.0, 1.0); var w: vec2<f32>= vec2<f32>(1.0, 2.0);", "v.x + v.y + v.z + w.y", 32.0),
+    ("mat_from_scalars", "", "let m = mat2x2f(1.0, 2.0, 3.0, 4.0); let v = m * vec2f(1.0, 1.0);", "v.x * 10.0 + v.y", 46.0),
+    ("array_named_size", "const N = 3;\nvar<private> arr: array<f32, N>;", "arr[0] = 1.0; arr[2] = 5.0;", "arr[0] + arr[1] + arr[2]", 6.0),
+    ("array_inferred", "", "let a = array(1.0, 2.5, 4.0); var i = 2;", "a[i] + a[0]", 5.0),
+    ("vector_conversions", "", "let f = vec3f(1.7, -2.7, 3.2); let i = vec3i(f); let u = vec2u(vec2f(3.9, 4.1));", "f32(i.x + i.y + i.z) + f32(u.x + u.y)", 9.0),
+    ("const_comparisons_and_casts", "const A = 3;\nconst B = A < 4;\nconst C = A == 3;\nconst Z = i32(3.9);\nconst Y = bool(2);", "", "f32(B) + f32(C) + f32(Z) + f32(Y)", 6.0),
+    ("vector_dynamic_index", "", "var v = vec4f(1.0, 2.0, 3.0, 4.0); var i = 2; var j = 9;", "v[i] + v[j]", 7.0),
+    ("call_result_after_discard_check", "fn pick(x: f32) -> f32 { if (x > 100.0) { discard; } return x * 2.0; }\nfn twice(x: f32) -> f32 { return pick(x) + pick(x + 1.0); }", "let y = twice(3.0);", "y", 14.0),
     ("compound_assign", "", "var a: f32 = 8.0; a /= 2.0; a -= 1.0; a *= 3.0; var i: i32 = 5; i %= 3; i <<= 2u;", "a + f32(i)", 17.0),
 ]
 

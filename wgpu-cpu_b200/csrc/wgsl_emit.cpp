@@ -1538,6 +1538,19 @@ struct Emitter {
         }
         return false;
     }
+    // does the block call one of `names`? (the walk of stmt_discards without the discard statement itself)
+    bool stmt_calls(const std::vector<StmtP>& b, const std::set<std::string>& names) const {
+        for (auto& s : b) {
+            if (!s) continue;
+            auto ec = [&](const ExprP& e) { return e && expr_calls(e, names); };
+            if (ec(s->a) || ec(s->b)) return true;
+            if (s->init && stmt_calls({s->init}, names)) return true;
+            if (s->update && stmt_calls({s->update}, names)) return true;
+            if (stmt_calls(s->body, names) || stmt_calls(s->else_body, names) || stmt_calls(s->continuing, names)) return true;
+            for (auto& c : s->cases) if (stmt_calls(c.body, names)) return true;
+        }
+        return false;
+    }
     bool expr_calls(const ExprP& e, const std::set<std::string>& names) const {
         if (e->k == Expr::Call && names.count(e->name)) return true;
         for (auto& a : e->args) if (a && expr_calls(a, names)) return true;
@@ -1565,6 +1578,17 @@ struct Emitter {
                 if (!discarding.count(f->name) && stmt_discards(f->body, discarding)) { discarding.insert(f->name); f->may_discard = true; changed = true; }
         }
         for (auto& g : m.globals) if (g.space == "private") has_private = true;
+        // only the entry point's call graph is emitted: a module shared by both stages may hold helpers that are valid in
+        // one of them only (a function that discards must not stop the vertex stage of the same module from translating)
+        std::set<std::string> reachable = {ep->name};
+        for (bool changed = true; changed;) {
+            changed = false;
+            for (auto& f : m.functions) {
+                if (reachable.count(f->name) || f->stage()) continue;
+                for (auto& g : m.functions)
+                    if (reachable.count(g->name) && stmt_calls(g->body, {f->name})) { reachable.insert(f->name); changed = true; break; }
+            }
+        }
 
         out += "// wgsl2cuda: stage=" + std::string(stage == 1 ? "vertex" : "fragment") + " entry=" + entry + "\n";
         out += "namespace " + ns + " {\n";
@@ -1610,6 +1634,7 @@ struct Emitter {
         std::string protos, bodies;
         for (auto& f : m.functions) {
             if (f->stage() && f.get() != ep) continue;
+            if (!reachable.count(f->name)) continue;
             cur_fn = f.get();
             std::string sig = "WGB_DEV " + cuda_type(f->ret, f->line) + " " + f->name + "(const WgbDraw& wgb, WgbInvocation& wgb_inv";
             push();
