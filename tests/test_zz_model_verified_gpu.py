@@ -496,3 +496,23 @@ def test_queue_write_buffer_ranges_timer_and_device_pointer(gpu, tmp_path):
     assert np.array_equal(_decode_png(str(tmp_path / "bgra.png")), after[..., [2, 1, 0, 3]])      # PNGs are RGBA
     with pytest.raises(Exception):
         queue.write_buffer(r.vertex_buffers[0], scene.vertex_buffers[0].nbytes - 16, np.zeros(32, dtype=np.uint8))   # past the end
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_fuzz_with_the_other_shaders(gpu, seed):
+    """scenes.fuzz_shaders: the random state x geometry of the fuzz test drawn with the other parity programs (instancing +
+    flat varyings + discard, frag_depth, the early-depth-test programs on every topology, three colour attachments,
+    perspective-correct varyings, primitive_index, a depth-only stage).  400 further seeds were run once on the model."""
+    from oracle import pyoracle
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    scene = S.fuzz_shaders(seed)
+    ref = pyoracle.render(scene, want_coverage=False)
+    r = SceneRenderer(dev, queue, scene)
+    r.render()
+    got = r.read()
+    assert np.array_equal(got.color, ref.color), scene.name
+    if ref.depth is not None:
+        assert np.array_equal(got.depth.view(np.uint32), ref.depth.view(np.uint32)), scene.name
+    for k, (g, e) in enumerate(zip(got.extra_colors, ref.extra_colors), start=1):
+        assert np.array_equal(g, e), f"{scene.name}: colour attachment {k}"

@@ -586,3 +586,27 @@ def fuzz(seed: int) -> Scene:
             s.clear_depth = None
             s.initial_depth = rng.random((height, width), dtype=np.float32)
     return s
+
+
+def fuzz_shaders(seed: int) -> Scene:
+    """The state x geometry of fuzz(seed), drawn with one of the other parity shaders: instancing + flat varyings + discard,
+    frag_depth, the early-depth-test programs (with depth writes, so that every topology reaches the ordered kernel),
+    three colour attachments, perspective-correct varyings, primitive_index."""
+    rng = np.random.default_rng(50000 + seed)
+    s = fuzz(seed)
+    shader = str(rng.choice(["features", "frag_depth", "early_force", "early_allow", "mrt", "perspective", "prim_index", "depth_only"]))
+    s.name, s.shader = f"fuzz_{shader}_{seed}", shader
+    s.color_format = "rgba8unorm"
+    if s.initial_color is not None:                     # LoadOp::Load targets start from these bytes
+        s.initial_color = np.ascontiguousarray(s.initial_color)
+    if shader == "features":
+        params = np.zeros(20, dtype=np.float32)
+        params[:16] = np.eye(4, dtype=np.float32).reshape(-1)
+        params[16:20] = [float(rng.random() * 0.3 - 0.15), float(rng.random() * 0.3 - 0.15), float(rng.random() * 0.1), 0.0]
+        s.bindings = {(0, 0): ("buffer", params.view(np.uint8).reshape(-1).copy())}
+        s.draws = [Draw(d.indexed, d.first, d.count, d.base_vertex, int(rng.integers(0, 3)), int(rng.integers(1, 4))) for d in s.draws]
+    if shader in ("early_force", "early_allow", "depth_only") and s.depth_compare is not None:
+        s.depth_write = True
+    if shader == "mrt":
+        s.extra_targets = [("bgra8unorm", (0.25, 0.5, 0.75, 1.0) if rng.random() < 0.7 else None), ("rg8unorm", (0.5, 0.125, 0.0, 0.0))]
+    return s
