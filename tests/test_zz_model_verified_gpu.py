@@ -516,3 +516,15 @@ def test_fuzz_with_the_other_shaders(gpu, seed):
         assert np.array_equal(got.depth.view(np.uint32), ref.depth.view(np.uint32)), scene.name
     for k, (g, e) in enumerate(zip(got.extra_colors, ref.extra_colors), start=1):
         assert np.array_equal(g, e), f"{scene.name}: colour attachment {k}"
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_with_the_opt_in_features(ext, seed):
+    """scenes.fuzz_features: the fuzz test's state x geometry on devices with random sets of the opt-in features -- random
+    blend states (all thirteen factors, five operations, lines and points included), colour write masks, viewport depth
+    ranges -- against the oracle's restatement of them.  300 further seeds were run once on the model."""
+    scene = S.fuzz_features(seed)
+    got, ref = _render_both(scene, ext)
+    assert np.array_equal(got.color, ref.color), (scene.name, scene.features, scene.blend, scene.color_write_mask)
+    if ref.depth is not None:
+        assert np.array_equal(got.depth.view(np.uint32), ref.depth.view(np.uint32)), scene.name

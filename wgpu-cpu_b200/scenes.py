@@ -610,3 +610,38 @@ def fuzz_shaders(seed: int) -> Scene:
     if shader == "mrt":
         s.extra_targets = [("bgra8unorm", (0.25, 0.5, 0.75, 1.0) if rng.random() < 0.7 else None), ("rg8unorm", (0.5, 0.125, 0.0, 0.0))]
     return s
+
+
+_BLEND_FACTORS = ["zero", "one", "src", "one-minus-src", "src-alpha", "one-minus-src-alpha", "dst", "one-minus-dst", "dst-alpha",
+                  "one-minus-dst-alpha", "src-alpha-saturated", "constant", "one-minus-constant"]
+
+
+def fuzz_features(seed: int) -> Scene:
+    """fuzz(seed) on a device with a random set of the opt-in features (viewport depth range, colour write mask, blending
+    with a random blend state) over a random non-sRGB colour format.  The sRGB encode is left out: it goes through powf on
+    both sides and is held to a tolerance, not to equality (tests/test_features_gpu.py)."""
+    rng = np.random.default_rng(70000 + seed)
+    s = fuzz(seed)
+    s.name = f"fuzz_features_{seed}"
+    s.color_format = str(rng.choice(["rgba8unorm", "bgra8unorm"]))
+    v = s.vertex_buffers[0].view(np.float32).reshape(-1, 8).copy()
+    v[:, 7] = rng.random(v.shape[0], dtype=np.float32)                  # translucent vertices
+    s.vertex_buffers[0] = v.view(np.uint8).reshape(-1)
+    s.features = 0
+    if rng.random() < 0.6:
+        s.features |= 16                                                # WGB_FEATURE_BLEND
+        ops = ["add", "subtract", "reverse-subtract", "min", "max"]
+        pick = lambda: (str(rng.choice(_BLEND_FACTORS)), str(rng.choice(_BLEND_FACTORS)), str(rng.choice(ops)))
+        s.blend = {"color": pick(), "alpha": pick()}
+        s.blend_constant = tuple(float(x) for x in rng.random(4))
+    if rng.random() < 0.5:
+        s.features |= 2                                                 # WGB_FEATURE_COLOR_WRITE_MASK
+        s.color_write_mask = int(rng.integers(0, 16))
+    if rng.random() < 0.4:
+        s.features |= 1                                                 # WGB_FEATURE_VIEWPORT_DEPTH_RANGE
+        lo = float(rng.random() * 0.5)
+        vp = s.viewport or (0.0, 0.0, float(s.width), float(s.height), 0.0, 1.0)
+        s.viewport = (vp[0], vp[1], vp[2], vp[3], lo, lo + float(rng.random() * 0.5))
+    if s.clear_color is not None:
+        s.clear_color = tuple(float(x) for x in rng.random(4))
+    return s
