@@ -528,3 +528,20 @@ def test_fuzz_with_the_opt_in_features(ext, seed):
     assert np.array_equal(got.color, ref.color), (scene.name, scene.features, scene.blend, scene.color_write_mask)
     if ref.depth is not None:
         assert np.array_equal(got.depth.view(np.uint32), ref.depth.view(np.uint32)), scene.name
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_fuzz_texture_sampling(gpu, seed):
+    """scenes.fuzz_textured: texture coordinates far outside [0, 1] and exactly on texel boundaries, every address mode
+    per axis, 1 x 1 to odd non-square textures, both sampled formats (binding.rs:93-164).  400 further seeds were run
+    once on the model."""
+    _compare(S.fuzz_textured(seed), gpu)
+
+
+@pytest.mark.parametrize("size", [(16384, 40), (40, 16384), (16384, 1)])
+def test_maximum_texture_extent(gpu, size):
+    """Attachments at the 16384-texel limit: tile column / row 511, the last one the direct bins address."""
+    from wgpu_cpu_b200 import api
+    _compare(S.random_triangles(size[0], size[1], count=400, seed=5, spread=1.05), gpu)
+    with pytest.raises(api.WgpuError):
+        gpu[0].create_texture(16385, 8, "rgba8unorm")

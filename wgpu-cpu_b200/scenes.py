@@ -645,3 +645,37 @@ def fuzz_features(seed: int) -> Scene:
     if s.clear_color is not None:
         s.clear_color = tuple(float(x) for x in rng.random(4))
     return s
+
+
+def fuzz_textured(seed: int) -> Scene:
+    """Random textured triangles for the sampling path (binding.rs:93-164): texture coordinates from far outside [0, 1] to
+    exactly on texel boundaries, every address mode per axis, texture sizes from 1 x 1 over odd and non-square ones,
+    both sampled formats, perspective division (w != 1) in the positions."""
+    rng = np.random.default_rng(90000 + seed)
+    width, height = int(rng.integers(8, 200)), int(rng.integers(8, 150))
+    count = int(rng.integers(1, 120))
+    u = rng.random((count * 3, 6), dtype=np.float32)
+    v = np.ones((count * 3, 6), dtype=np.float32)
+    spread = np.float32(rng.choice([0.7, 1.0, 1.5]))
+    v[:, 0] = (u[:, 0] * 2 - 1) * spread
+    v[:, 1] = (u[:, 1] * 2 - 1) * spread
+    v[:, 2] = u[:, 2]
+    if rng.random() < 0.5:
+        v[:, 3] = np.float32(0.4) + u[:, 3] * np.float32(1.2)
+    scale = np.float32(rng.choice([1.0, 1.0, 3.0, 17.0]))
+    v[:, 4:6] = (u[:, 4:6] * 2 - np.float32(rng.choice([0.0, 1.0]))) * scale
+    tw, th = int(rng.choice([1, 2, 3, 7, 16, 33, 64])), int(rng.choice([1, 2, 5, 8, 31, 64]))
+    if rng.random() < 0.3:       # coordinates that land exactly on texel centres and edges of the texture
+        v[:, 4] = np.round(v[:, 4] * np.float32(2 * max(tw - 1, 1))) / np.float32(2 * max(tw - 1, 1))
+        v[:, 5] = np.round(v[:, 5] * np.float32(2 * max(th - 1, 1))) / np.float32(2 * max(th - 1, 1))
+    image = rng.integers(0, 256, (th, tw, 4), dtype=np.uint8)
+    modes = ["clamp-to-edge", "repeat", "mirror-repeat"]
+    return Scene(
+        name=f"fuzz_textured_{seed}", width=width, height=height, shader="hello_texture", color_format=str(rng.choice(["rgba8unorm", "rgba8unorm-srgb"])),
+        front_face="ccw", cull_mode=None, depth_compare=str(rng.choice(["less", "always", "greater-equal"])), depth_write=True,
+        clear_depth=float(rng.choice([1.0, 0.5])),
+        vertex_layouts=[_POS_UV_LAYOUT], vertex_buffers=[np.ascontiguousarray(v).view(np.uint8).reshape(-1)],
+        bindings={(0, 0): ("buffer", identity_matrix_bytes()), (1, 0): ("texture", image, str(rng.choice(["rgba8unorm", "rgba8unorm-srgb"]))),
+                  (1, 1): ("sampler", str(rng.choice(modes)), str(rng.choice(modes)))},
+        draws=[Draw(False, 0, count * 3)],
+    )
