@@ -545,3 +545,46 @@ def test_maximum_texture_extent(gpu, size):
     _compare(S.random_triangles(size[0], size[1], count=400, seed=5, spread=1.05), gpu)
     with pytest.raises(api.WgpuError):
         gpu[0].create_texture(16385, 8, "rgba8unorm")
+
+
+def test_several_pipelines_in_one_pass(gpu):
+    """A render pass that switches pipelines, bindings, topologies, viewports and scissors between draws (the reference
+    replays the sub-commands in order on one State, render_pass/mod.rs:351-388): depth-tested triangles, then lines, then
+    an instanced draw that discards, then textured triangles under a scissor -- later draws see the depth and colour of
+    earlier ones.  The oracle renders them one after the other, each loading what the previous left."""
+    import copy
+    from oracle import pyoracle
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    W, H = 200, 150
+    tri = S.random_triangles(W, H, count=120, seed=61, color_format="rgba8unorm")
+    lines = S.random_lines(W, H, 80, 62, "line-strip")
+    inst = S.features(W, H, instances=2)
+    tex = S.fuzz_textured(3)
+    tex.width, tex.height, tex.scissor = W, H, (20, 10, 150, 120)
+    tex.viewport = (10.0, 5.0, 180.0, 140.0, 0.0, 1.0)
+    for s in (lines, inst, tex):
+        s.color_format = "rgba8unorm"
+    lines.depth_compare, lines.depth_write = "less-equal", False
+    scenes = [tri, lines, inst, tex]
+    # the oracle: one scene after the other, loading the previous result
+    ref = pyoracle.render(scenes[0], want_coverage=False)
+    for s in scenes[1:]:
+        step = copy.copy(s)
+        step.clear_color, step.initial_color = None, ref.color
+        step.clear_depth, step.initial_depth = None, ref.depth
+        ref = pyoracle.render(step, want_coverage=False)
+    # the device: one pass
+    rs = [SceneRenderer(dev, queue, s) for s in scenes]
+    enc = dev.create_command_encoder()
+    with enc.begin_render_pass([{"view": rs[0].target_view, "load": ("clear", tri.clear_color)}],
+                               {"view": rs[0].depth_view, "depth_load": ("clear", tri.clear_depth)}) as rp:
+        for r in rs:
+            r.record_into(rp)
+            if r.scene.viewport is None:
+                rp.set_viewport(0.0, 0.0, float(W), float(H))          # pass state persists: undo the previous scene's
+            if r.scene.scissor is None:
+                rp.set_scissor_rect(0, 0, W, H)
+    dev.poll(True, queue.submit([enc.finish()]))
+    assert np.array_equal(rs[0].target.read(), ref.color)
+    assert np.array_equal(rs[0].depth_texture.read().view(np.uint32), ref.depth.view(np.uint32))

@@ -104,26 +104,31 @@ class SceneRenderer:
         colors = [color] + [{"view": v, "load": ("clear", clear) if clear is not None else "load"}
                             for v, (_, clear) in zip(self.extra_views, s.extra_targets or [])]
         with enc.begin_render_pass(colors, depth) as rp:
-            rp.set_pipeline(self.pipeline)
-            for g, bg in self.bind_groups.items():
-                rp.set_bind_group(g, bg, (s.dynamic_offsets or {}).get(g, ()))
-            if self.index_buffer is not None:
-                rp.set_index_buffer(self.index_buffer, self.index_format)
-            for i, vb in enumerate(self.vertex_buffers):
-                rp.set_vertex_buffer(i, vb)
-            if s.blend:
-                rp.set_blend_constant(s.blend_constant)
-            if s.viewport is not None:
-                rp.set_viewport(*s.viewport)
-            if s.scissor is not None:
-                rp.set_scissor_rect(*s.scissor)
-            for d in s.draws:
-                if d.indexed:
-                    rp.draw_indexed(range(d.first, d.first + d.count), d.base_vertex,
-                                    range(d.first_instance, d.first_instance + d.instance_count))
-                else:
-                    rp.draw(range(d.first, d.first + d.count), range(d.first_instance, d.first_instance + d.instance_count))
+            self.record_into(rp)
         return enc.finish()
+
+    def record_into(self, rp) -> None:
+        """This scene's pipeline, bindings, state and draws into an open render pass (several scenes can share one)."""
+        s = self.scene
+        rp.set_pipeline(self.pipeline)
+        for g, bg in self.bind_groups.items():
+            rp.set_bind_group(g, bg, (s.dynamic_offsets or {}).get(g, ()))
+        if self.index_buffer is not None:
+            rp.set_index_buffer(self.index_buffer, self.index_format)
+        for i, vb in enumerate(self.vertex_buffers):
+            rp.set_vertex_buffer(i, vb)
+        if s.blend:
+            rp.set_blend_constant(s.blend_constant)
+        if s.viewport is not None:
+            rp.set_viewport(*s.viewport)
+        if s.scissor is not None:
+            rp.set_scissor_rect(*s.scissor)
+        for d in s.draws:
+            if d.indexed:
+                rp.draw_indexed(range(d.first, d.first + d.count), d.base_vertex,
+                                range(d.first_instance, d.first_instance + d.instance_count))
+            else:
+                rp.draw(range(d.first, d.first + d.count), range(d.first_instance, d.first_instance + d.instance_count))
 
     def submit(self, command_buffer: Optional[api.CommandBuffer] = None) -> int:
         idx = self.queue.submit([command_buffer if command_buffer is not None else self.encode()])
