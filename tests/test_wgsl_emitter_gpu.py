@@ -40,11 +40,60 @@ def evaluate(dev, queue, wgsl: str, bind_group_entries=None) -> float:
     return float(d[0, 0])
 
 
-@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_wgsl_case(gpu, case):
+def evaluate_batch(dev, queue, cases) -> dict:
+    """All cases of a group in one module and one draw: column k of a (len x 4) target holds case k's value."""
+    from tests.wgsl_cases import module_for_batch
+    module = dev.create_shader_module(module_for_batch(cases))
+    pipe = dev.create_render_pipeline(vertex_module=module, fragment_module=module,
+                                      depth_stencil={"depth_compare": "always", "depth_write_enabled": True},
+                                      targets=["rgba8unorm"])
+    w, h = len(cases), 4
+    color = dev.create_texture(w, h, "rgba8unorm")
+    depth = dev.create_texture(w, h, "depth32float")
+    enc = dev.create_command_encoder()
+    with enc.begin_render_pass([{"view": color.create_view(), "load": ("clear", (0, 0, 0, 0))}],
+                               {"view": depth.create_view(), "depth_load": ("clear", 0.0)}) as rp:
+        rp.set_pipeline(pipe)
+        rp.draw(range(0, 6))
+    dev.poll(True, queue.submit([enc.finish()]))
+    d = depth.read()
+    assert (color.read()[..., 0] == 255).all(), "the two triangles must cover the target"
+    assert (d == d[0:1, :]).all(), "every row evaluates the same cases"
+    return {c[0]: float(d[0, k]) for k, c in enumerate(cases)}
+
+
+@pytest.fixture(scope="module")
+def case_values(gpu):
+    """name -> value for every case, one shader module per group of non-colliding cases (4 NVRTC compilations instead of
+    one per case); a group that fails as a whole is re-run case by case so that the failure names its case."""
+    from tests.wgsl_cases import batches
     dev, queue = gpu
-    got = evaluate(dev, queue, module_for(case))
+    values = {}
+    for group in batches():
+        try:
+            values.update(evaluate_batch(dev, queue, group))
+        except Exception:      # noqa: BLE001 -- fall back to one module per case
+            for case in group:
+                try:
+                    values[case[0]] = evaluate(dev, queue, module_for(case))
+                except Exception as e:      # noqa: BLE001
+                    values[case[0]] = e
+    return values
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_wgsl_case(case_values, case):
+    got = case_values[case[0]]
+    if isinstance(got, Exception):
+        raise got
     assert got == np.float32(case[4]), f"{case[0]}: got {got!r}, expected {case[4]!r}"
+
+
+def test_a_case_on_its_own_module(gpu):
+    """The one-module-per-case harness the batches replace (kept for the fall-back path): same value."""
+    dev, queue = gpu
+    case = next(c for c in CASES if c[0] == "for_factorial")
+    assert evaluate(dev, queue, module_for(case)) == np.float32(case[4])
 
 
 def test_array_length_of_storage_bindings(gpu):

@@ -498,7 +498,7 @@ def test_queue_write_buffer_ranges_timer_and_device_pointer(gpu, tmp_path):
         queue.write_buffer(r.vertex_buffers[0], scene.vertex_buffers[0].nbytes - 16, np.zeros(32, dtype=np.uint8))   # past the end
 
 
-@pytest.mark.parametrize("seed", range(32))
+@pytest.mark.parametrize("seed", range(16))
 def test_fuzz_with_the_other_shaders(gpu, seed):
     """scenes.fuzz_shaders: the random state x geometry of the fuzz test drawn with the other parity programs (instancing +
     flat varyings + discard, frag_depth, the early-depth-test programs on every topology, three colour attachments,
@@ -518,7 +518,7 @@ def test_fuzz_with_the_other_shaders(gpu, seed):
         assert np.array_equal(g, e), f"{scene.name}: colour attachment {k}"
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(12))
 def test_fuzz_with_the_opt_in_features(ext, seed):
     """scenes.fuzz_features: the fuzz test's state x geometry on devices with random sets of the opt-in features -- random
     blend states (all thirteen factors, five operations, lines and points included), colour write masks, viewport depth
@@ -530,7 +530,7 @@ def test_fuzz_with_the_opt_in_features(ext, seed):
         assert np.array_equal(got.depth.view(np.uint32), ref.depth.view(np.uint32)), scene.name
 
 
-@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("seed", range(8))
 def test_fuzz_texture_sampling(gpu, seed):
     """scenes.fuzz_textured: texture coordinates far outside [0, 1] and exactly on texel boundaries, every address mode
     per axis, 1 x 1 to odd non-square textures, both sampled formats (binding.rs:93-164).  400 further seeds were run

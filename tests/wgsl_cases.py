@@ -165,3 +165,61 @@ fn fs_main() -> FragmentOutput {{
     return FragmentOutput(compute(), vec4f(1.0, 0.0, 0.0, 1.0));
 }}
 """
+
+
+def batches(cases=None, limit=64):
+    """Groups of cases whose module-scope declarations do not collide, so that one shader module (one NVRTC compilation on
+    the hardware instead of one per case) can hold a whole group; a case whose code can discard stays alone, because a
+    stage that may discard takes another path through the tile kernel."""
+    import re
+    groups = []
+    for c in (cases if cases is not None else CASES):
+        ids = {x for t in re.findall(r"\b(?:const|fn|struct|alias)\s+(\w+)|var<[^>]*>\s+(\w+)", c[1]) for x in t if x}
+        alone = "discard" in c[1] + c[2]
+        for g in groups:
+            if not alone and not g["alone"] and not (g["ids"] & ids) and len(g["cases"]) < limit:
+                g["cases"].append(c)
+                g["ids"] |= ids
+                break
+        else:
+            groups.append({"cases": [c], "ids": set(ids), "alone": alone})
+    return [g["cases"] for g in groups]
+
+
+def module_for_batch(cases) -> str:
+    """One module for a group of cases: case k is evaluated by the fragments of pixel column k (the value leaves through
+    frag_depth, as in module_for)."""
+    decls = "\n".join(c[1] for c in cases if c[1])
+    fns = "\n".join(f"fn compute_{k}() -> f32 {{\n    {c[2]}\n    return {c[3]};\n}}" for k, c in enumerate(cases))
+    arms = "\n".join(f"        case {k}u: {{ d = compute_{k}(); }}" for k in range(len(cases)))
+    return f"""
+{decls}
+
+struct FragmentOutput {{
+    @builtin(frag_depth) depth: f32,
+    @location(0) color: vec4f,
+}}
+
+// two triangles that cover the target exactly: nothing is clipped, so the interpolated position is the pixel's (the
+// position of a clipped triangle's fragments is not -- raster.rs:345-346 interpolates the clipped vertices with the
+// unclipped triangle's coefficients)
+@vertex
+fn vs_main(@builtin(vertex_index) vertex_index: u32) -> @builtin(position) vec4f {{
+    let x = f32(i32((0x1Au >> vertex_index) & 1u) * 2 - 1);
+    let y = f32(i32((0x34u >> vertex_index) & 1u) * 2 - 1);
+    return vec4f(x, y, 0.5, 1.0);
+}}
+
+{fns}
+
+@fragment
+fn fs_main(@builtin(position) p: vec4f) -> FragmentOutput {{
+    let column = u32(p.x + 0.5);
+    var d: f32 = -1.0;
+    switch (column) {{
+{arms}
+        default: {{ }}
+    }}
+    return FragmentOutput(d, vec4f(1.0, 0.0, 0.0, 1.0));
+}}
+"""
