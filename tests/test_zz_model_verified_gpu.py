@@ -588,3 +588,25 @@ def test_several_pipelines_in_one_pass(gpu):
     dev.poll(True, queue.submit([enc.finish()]))
     assert np.array_equal(rs[0].target.read(), ref.color)
     assert np.array_equal(rs[0].depth_texture.read().view(np.uint32), ref.depth.view(np.uint32))
+
+
+def test_recorded_commands_keep_their_resources_alive(gpu):
+    """Backend objects are reference counted like the reference's Arc clones (buffer.rs:22-29, command.rs:10-13): a recorded
+    pass keeps the pipeline, bind groups, buffers and views it names alive, so the application may drop its handles before
+    it submits."""
+    import gc
+    from oracle import pyoracle
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    scene = S.hello_texture(160, 110)
+    ref = pyoracle.render(scene, want_coverage=False)
+    r = SceneRenderer(dev, queue, scene)
+    cb = r.encode()
+    target, depth = r.target, r.depth_texture
+    del r                      # pipeline, module, bind groups, sampler, sampled texture + view, vertex / index / uniform buffers
+    gc.collect()
+    junk = [dev.create_buffer(1 << 16, mapped_at_creation=False) for _ in range(8)]      # churn the allocator
+    dev.poll(True, queue.submit([cb]))
+    del junk
+    assert np.array_equal(target.read(), ref.color)
+    assert np.array_equal(depth.read().view(np.uint32), ref.depth.view(np.uint32))

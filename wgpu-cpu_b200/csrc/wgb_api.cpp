@@ -2014,6 +2014,10 @@ wgb_status wgb_queue_submit(wgb_queue queue, const wgb_command_buffer* command_b
             }
             std::sort(used.begin(), used.end());
             used.erase(std::unique(used.begin(), used.end()), used.end());
+            // the recorded commands may hold the last reference to a buffer (the application is free to drop its handle
+            // once the pass is recorded) and are cleared below, before this scope ends: keep the buffers alive until the
+            // end-of-scope bookkeeping has run
+            std::vector<Ref<Buffer>> keep_alive(used.begin(), used.end());
             for (Buffer* b : used) b->acquire_on(dev->stream);
             struct MarkUsed {
                 std::vector<Buffer*>& v; cudaStream_t s;
