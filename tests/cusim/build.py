@@ -17,7 +17,12 @@ def build(force: bool = False) -> str:
     import importlib
     import sys
     coverage = os.environ.get("CUSIM_HOST_COVERAGE") == "1"
-    lib = os.path.join(OUT, "libwgpu_b200_sim_cov.so") if coverage else LIB
+    # CUSIM_ASAN=1: the host runtime under AddressSanitizer (the fibers of the device half are not instrumented).  Python
+    # is not, so the sanitizer runtime has to be preloaded together with libstdc++ (for its __cxa_throw interceptor):
+    #   CUSIM_ASAN=1 WGB_CUSIM=1 ASAN_OPTIONS=detect_leaks=0 \
+    #   LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libstdc++.so.6)" python -m pytest tests -m gpu -q
+    asan = os.environ.get("CUSIM_ASAN") == "1"
+    lib = os.path.join(OUT, "libwgpu_b200_sim_cov.so") if coverage else os.path.join(OUT, "libwgpu_b200_sim_asan.so") if asan else LIB
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     product = importlib.import_module("wgpu_cpu_b200.build")
@@ -28,7 +33,7 @@ def build(force: bool = False) -> str:
     if not force and os.path.exists(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps):
         return lib
     os.makedirs(OUT, exist_ok=True)
-    cmd = ["g++", *(["-O0", "--coverage"] if coverage else ["-O1"]), "-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-w",
+    cmd = ["g++", *(["-O0", "--coverage"] if coverage else ["-O1", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else ["-O1"]), "-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-w",
            f"-I{os.path.join(HERE, 'include')}", f'-DCUSIM_DIR="{HERE}"', *srcs, "-o", lib, "-ldl", "-lpthread"]
     subprocess.check_call(cmd, cwd=OUT)
     return lib
