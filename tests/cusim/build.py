@@ -39,11 +39,11 @@ def build(force: bool = False) -> str:
     return lib
 
 
-def build_example() -> str:
-    """examples/hello_mesh.cpp (the C++ host over the C ABI) linked against the model build of the library."""
+def build_example(name: str = "hello_mesh") -> str:
+    """examples/<name>.cpp (the C++ host over the C ABI) linked against the model build of the library."""
     lib = build()
-    src = os.path.join(ROOT, "examples", "hello_mesh.cpp")
-    exe = os.path.join(OUT, "hello_mesh")
+    src = os.path.join(ROOT, "examples", name + ".cpp")
+    exe = os.path.join(OUT, name)
     if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(lib)):
         subprocess.check_call(["g++", "-std=c++17", "-O1", f"-I{os.path.join(ROOT, 'include')}", src, "-o", exe,
                                f"-L{OUT}", "-lwgpu_b200_sim", f"-Wl,-rpath,{OUT}"])

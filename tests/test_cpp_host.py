@@ -14,9 +14,10 @@ def test_example_builds_and_links():
     sys.path.insert(0, ROOT)
     from wgpu_cpu_b200 import build
     build.build()
-    assert os.path.exists(EXAMPLE)
-    p = subprocess.run([EXAMPLE], capture_output=True, text=True)
-    assert p.returncode == 2 and "usage" in p.stderr
+    for exe in (EXAMPLE, os.path.join(ROOT, "examples", "hello_texture")):
+        assert os.path.exists(exe)
+        p = subprocess.run([exe], capture_output=True, text=True)
+        assert p.returncode == 2 and "usage" in p.stderr
 
 
 def test_example_reports_the_missing_device():

@@ -35,3 +35,32 @@ def test_cpp_host_renders_hello_mesh(tmp_path):
     assert np.array_equal(color, ref.color)
     assert np.array_equal(depth.view(np.uint32), ref.depth.view(np.uint32))
     assert np.array_equal(_decode_png(out + ".png"), color)
+
+
+def test_cpp_host_renders_hello_texture(tmp_path):
+    """examples/hello_texture (the reference's hello_texture.rs flow: texture from image bytes, Repeat / Nearest sampler, a
+    second bind group) renders the textured bunny bit-exactly."""
+    from oracle import pyoracle
+    from tests.test_c_abi import _decode_png
+    scene = S.hello_texture(240, 160)
+    ref = pyoracle.render(scene, want_coverage=False)
+    image = np.ascontiguousarray(scene.bindings[(1, 0)][1])
+    (tmp_path / "v.bin").write_bytes(scene.vertex_buffers[0].tobytes())
+    (tmp_path / "i.bin").write_bytes(scene.index_data.astype(np.uint32).tobytes())
+    (tmp_path / "u.bin").write_bytes(np.ascontiguousarray(scene.bindings[(0, 0)][1]).tobytes())
+    (tmp_path / "t.rgba").write_bytes(image.tobytes())
+    out = str(tmp_path / "frame")
+    exe = os.path.join(ROOT, "examples", "hello_texture")
+    if os.environ.get("WGB_CUSIM") == "1":
+        from tests.cusim import build as cusim_build
+        exe = cusim_build.build_example("hello_texture")
+    p = subprocess.run([exe, os.path.join(ROOT, "wgpu-cpu_b200", "shaders", "mesh_textured.wgsl"), str(tmp_path / "v.bin"), str(tmp_path / "i.bin"),
+                        str(tmp_path / "u.bin"), str(tmp_path / "t.rgba"), str(image.shape[1]), str(image.shape[0]), "240", "160", out],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert f"primitives {scene.num_primitives}" in p.stdout
+    color = np.fromfile(out + ".rgba", dtype=np.uint8).reshape(160, 240, 4)
+    depth = np.fromfile(out + ".depth", dtype=np.float32).reshape(160, 240)
+    assert np.array_equal(color, ref.color)
+    assert np.array_equal(depth.view(np.uint32), ref.depth.view(np.uint32))
+    assert np.array_equal(_decode_png(out + ".png"), color)
