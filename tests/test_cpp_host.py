@@ -14,7 +14,7 @@ def test_example_builds_and_links():
     sys.path.insert(0, ROOT)
     from wgpu_cpu_b200 import build
     build.build()
-    for exe in (EXAMPLE, os.path.join(ROOT, "examples", "hello_texture")):
+    for exe in (EXAMPLE, os.path.join(ROOT, "examples", "hello_texture"), os.path.join(ROOT, "examples", "hello_shader")):
         assert os.path.exists(exe)
         p = subprocess.run([exe], capture_output=True, text=True)
         assert p.returncode == 2 and "usage" in p.stderr

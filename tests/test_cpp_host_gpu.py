@@ -64,3 +64,27 @@ def test_cpp_host_renders_hello_texture(tmp_path):
     assert np.array_equal(color, ref.color)
     assert np.array_equal(depth.view(np.uint32), ref.depth.view(np.uint32))
     assert np.array_equal(_decode_png(out + ".png"), color)
+
+
+def test_cpp_host_renders_hello_shader(tmp_path):
+    """examples/hello_shader (hello_shader.rs: no vertex buffers, position and colour from vertex_index) renders the
+    reference's test triangle bit-exactly, colour and depth; the depth dump is the 8-bit grey of lib.rs:129-158."""
+    from oracle import pyoracle
+    from tests.test_c_abi import _decode_png
+    scene = S.colored_triangle("draw_backwards_no_cull", 200, 120)       # front face Ccw, no culling: hello_shader's pipeline state
+    ref = pyoracle.render(scene, want_coverage=False)
+    out = str(tmp_path / "frame")
+    exe = os.path.join(ROOT, "examples", "hello_shader")
+    if os.environ.get("WGB_CUSIM") == "1":
+        from tests.cusim import build as cusim_build
+        exe = cusim_build.build_example("hello_shader")
+    p = subprocess.run([exe, os.path.join(ROOT, "wgpu-cpu_b200", "shaders", "index_triangle.wgsl"), "3", "200", "120", out],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    color = np.fromfile(out + ".rgba", dtype=np.uint8).reshape(120, 200, 4)
+    depth = np.fromfile(out + ".depth", dtype=np.float32).reshape(120, 200)
+    assert np.array_equal(color, ref.color)
+    assert np.array_equal(depth.view(np.uint32), ref.depth.view(np.uint32))
+    assert np.array_equal(_decode_png(out + ".png"), color)
+    grey = np.clip(np.trunc(depth * np.float32(255.0)), 0, 255).astype(np.uint8)
+    assert np.array_equal(_decode_png(out + ".depth.png")[:, :, 0], grey)
