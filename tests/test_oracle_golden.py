@@ -1,4 +1,4 @@
-"""The oracle's frames for a fixed set of scenes, pinned by hash (tests/golden/oracle_frames.json, written by
+"""The oracle's frames for a fixed set of scenes, pinned by hash (tests/golden/oracle_frames_sha256.json, written by
 tools/make_golden.py).  These are not reference outputs -- the reference's golden PNGs are LFS pointers and it cannot be
 built here -- they keep the oracle itself from drifting: the recorded frames are the ones the CUDA path was bit-exact
 against (the 32 scenes that already existed at the last commit verified on a B200, 880e5ed, hash the same with that
@@ -14,7 +14,7 @@ def test_oracle_frames_match_the_recorded_hashes():
     spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tools", "make_golden.py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
-    recorded = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_frames.json")))
+    recorded = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_frames_sha256.json")))
     now = m.generate()
     assert set(now) == set(recorded)
     changed = [name for name in sorted(now) if now[name] != recorded[name]]

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Writes tests/golden/oracle_frames.json: SHA-256 of the colour bytes and depth bits the CPU oracle renders for a fixed
+"""Writes tests/golden/oracle_frames_sha256.json: SHA-256 of the colour bytes and depth bits the CPU oracle renders for a fixed
 set of scenes (every BASELINE shape at test size, the parity shaders, a few fuzz seeds).
 
 The reference's own golden images are git-LFS pointers, and the reference cannot be built here, so these
@@ -43,7 +43,7 @@ def generate() -> dict:
 
 
 if __name__ == "__main__":
-    path = os.path.join(ROOT, "tests", "golden", "oracle_frames.json")
+    path = os.path.join(ROOT, "tests", "golden", "oracle_frames_sha256.json")
     with open(path, "w") as f:
         json.dump(generate(), f, indent=1, sort_keys=True)
         f.write("\n")
