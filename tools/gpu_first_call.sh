@@ -16,6 +16,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 (cd wgpu-cpu_b200/csrc && ncu --set full --import-source on --clock-control none -k regex:wgb_ -s 12 -c 4 -f -o ../../gpurun_out/prof_final \
     python ../../bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1)
+# A/B of the tuning experiments that are compiled in on request (each bit-exact on the model, none measured yet)
+WGB_VARY_CACHE=1 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_exp_varycache.json 2>> gpurun_out/${tag}_bench.err
+WGB_VARY_CACHE=1 python bench.py --config c2 --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_exp_varycache_c2.json 2>> gpurun_out/${tag}_bench.err
 for c in c1 c2 c4 c5; do
     python bench.py --config $c --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_${c}.json 2>> gpurun_out/${tag}_bench.err
 done

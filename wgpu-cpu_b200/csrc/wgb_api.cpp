@@ -321,7 +321,7 @@ struct Device : Object {
     std::map<std::pair<uint32_t, uint32_t>, uint32_t> bin_cap_hint;   // (primitives, band tiles) of a draw -> slots per tile it needed
     bool no_direct_bins = false;
     bool small_work_buffers = false;       // testing knob: start the clip-record and big lists at 2 entries so that both overflow-and-replay paths run
-    DevBuf counters, prim_box, setup_cache, vcache_raster, vcache_ndc, vcache_flags, slow_list, clip_records, big_list, tile_count, tile_offset, tile_cursor, bins, coverage, strip_map, strip_count;
+    DevBuf counters, prim_box, setup_cache, vcache_raster, vcache_ndc, vcache_flags, vcache_vary, slow_list, clip_records, big_list, tile_count, tile_offset, tile_cursor, bins, coverage, strip_map, strip_count;
     WgbCounters* host_counters = nullptr;   // pinned
     uint32_t clip_capacity = 0, big_capacity = 0;
     bool coverage_capture = false;
@@ -339,7 +339,7 @@ struct Device : Object {
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         for (auto& f : inflight) cudaEventDestroy(f.done);
         for (auto& kv : kernel_cache) if (kv.second->module && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->module);
-        DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &vcache_raster, &vcache_ndc, &vcache_flags, &slow_list, &clip_records, &big_list, &tile_count, &tile_offset, &tile_cursor, &bins, &coverage, &strip_map, &strip_count};
+        DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &vcache_raster, &vcache_ndc, &vcache_flags, &vcache_vary, &slow_list, &clip_records, &big_list, &tile_count, &tile_offset, &tile_cursor, &bins, &coverage, &strip_map, &strip_count};
         for (DevBuf* b : bufs) b->release();
         if (host_counters) cudaFreeHost(host_counters);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -450,6 +450,7 @@ struct RenderPipeline : Object {
     Ref<Device> device;
     std::string vs_text, fs_text;
     bool has_fragment = false;
+    uint32_t vary_cache_slots = 0;       // WGB_VARY_CACHE=1 at creation (tuning experiment): WGB_VS_VARYING_SLOTS of the vertex stage, else 0
     struct VB { uint64_t stride; uint32_t step_mode; std::vector<wgb_vertex_attribute> attrs; };
     std::vector<VB> vbs;
     uint32_t topology = 0, strip_index_format = 0, front_face = 0, cull_mode = 0;
@@ -522,6 +523,7 @@ struct RenderPipeline : Object {
         if (const char* mb = getenv("WGB_TILE_MIN_BLOCKS")) def("WGB_TILE_MIN_BLOCKS", atoi(mb));   // tuning knobs
         if (const char* mb = getenv("WGB_FILL_ROUNDS")) def("WGB_FILL_ROUNDS", atoi(mb));
         if (const char* mb = getenv("WGB_FILL_TARGET")) def("WGB_FILL_TARGET", atoi(mb));
+        if (vary_cache_slots) def("WGB_VARY_CACHE", 1);                                            // experiment: varyings kept in the vertex cache
         for (size_t b = 0; b < vbs.size(); b++)
             for (const auto& a : vbs[b].attrs) {
                 snprintf(line, sizeof(line), "#define WGB_ATTR%u_SLOT %zu\n#define WGB_ATTR%u_STRIDE %lluu\n#define WGB_ATTR%u_OFFSET %lluu\n#define WGB_ATTR%u_INSTANCE %s\n",
@@ -861,6 +863,10 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 dev->vcache_raster.ensure(nv * 16); dev->vcache_ndc.ensure(nv * 8); dev->vcache_flags.ensure(nv * 4);
                 d.vcache_raster = dev->vcache_raster.addr(); d.vcache_ndc = dev->vcache_ndc.addr(); d.vcache_flags = dev->vcache_flags.addr();
                 d.vcache_count = (uint32_t)vcache_n;
+                if (pipe->vary_cache_slots) {          // pipelines created with WGB_VARY_CACHE=1 (an experiment, off by default)
+                    dev->vcache_vary.ensure(nv * pipe->vary_cache_slots * 4);
+                    d.vcache_vary = dev->vcache_vary.addr();
+                }
             }
             dev->slow_list.ensure((size_t)np * 4);
             dev->clip_records.ensure((size_t)clip_cap * sizeof(WgbClipRecord));
@@ -1729,6 +1735,11 @@ wgb_status wgb_device_create_render_pipeline(wgb_device device, const wgb_render
         p->device = Ref<Device>(dev);
         ShaderModule* vm = from_handle<ShaderModule>(desc->vertex_module, "vertex shader module");
         p->vs_text = vm->cuda_for(WGB_SHADER_STAGE_VERTEX, desc->vertex_entry_point ? desc->vertex_entry_point : "vs_main");
+        if (const char* vc = getenv("WGB_VARY_CACHE")) {
+            const std::string key = "#define WGB_VS_VARYING_SLOTS ";
+            const size_t at = p->vs_text.find(key);
+            if (atoi(vc) != 0 && at != std::string::npos) p->vary_cache_slots = (uint32_t)atoi(p->vs_text.c_str() + at + key.size());
+        }
         if (desc->fragment_module) {
             ShaderModule* fm = from_handle<ShaderModule>(desc->fragment_module, "fragment shader module");
             p->fs_text = fm->cuda_for(WGB_SHADER_STAGE_FRAGMENT, desc->fragment_entry_point ? desc->fragment_entry_point : "fs_main");
