@@ -19,6 +19,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file
 # A/B of the tuning experiments that are compiled in on request (each bit-exact on the model, none measured yet)
 WGB_VARY_CACHE=1 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_exp_varycache.json 2>> gpurun_out/${tag}_bench.err
 WGB_VARY_CACHE=1 python bench.py --config c2 --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_exp_varycache_c2.json 2>> gpurun_out/${tag}_bench.err
+for hp in 2 4 8; do
+    WGB_HIZ_PAIRS=$hp python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_exp_hizpairs${hp}.json 2>> gpurun_out/${tag}_bench.err
+done
+WGB_HIZ_PAIRS=4 WGB_VARY_CACHE=1 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_exp_hizpairs4_varycache.json 2>> gpurun_out/${tag}_bench.err
 for c in c1 c2 c4 c5; do
     python bench.py --config $c --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_${c}.json 2>> gpurun_out/${tag}_bench.err
 done

@@ -523,6 +523,7 @@ struct RenderPipeline : Object {
         if (const char* mb = getenv("WGB_TILE_MIN_BLOCKS")) def("WGB_TILE_MIN_BLOCKS", atoi(mb));   // tuning knobs
         if (const char* mb = getenv("WGB_FILL_ROUNDS")) def("WGB_FILL_ROUNDS", atoi(mb));
         if (const char* mb = getenv("WGB_FILL_TARGET")) def("WGB_FILL_TARGET", atoi(mb));
+        if (const char* mb = getenv("WGB_HIZ_PAIRS")) def("WGB_HIZ_PAIRS", std::max(1, std::min(8, atoi(mb))));
         if (vary_cache_slots) def("WGB_VARY_CACHE", 1);                                            // experiment: varyings kept in the vertex cache
         for (size_t b = 0; b < vbs.size(); b++)
             for (const auto& a : vbs[b].attrs) {
