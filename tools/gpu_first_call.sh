@@ -1,6 +1,6 @@
 #!/bin/bash
-# The first GPU call of a round, in one gpurun invocation (about 12 minutes of box time):
-#   tools/gpu.sh --timeout 1500 -- 'bash tools/gpu_first_call.sh r02'
+# The first GPU call of a round, in one gpurun invocation (about 16 minutes of box time):
+#   tools/gpu.sh --timeout 1800 -- 'bash tools/gpu_first_call.sh r02'
 # 1. the whole GPU suite, not stopping at the first failure (tests/test_zz_model_verified_gpu.py has only run on the
 #    software model so far);  2. the headline bench and the reference arm;  3. the ncu launch list and one full-set
 #    capture of each kernel of a pass;  4. the other configs;  5. compute-sanitizer over a slice of the parity suite.
