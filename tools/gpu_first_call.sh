@@ -26,4 +26,4 @@ WGB_HIZ_PAIRS=4 WGB_VARY_CACHE=1 python bench.py --steps 50 --warmup 5 --no-cpu-
 for c in c1 c2 c4 c5; do
     python bench.py --config $c --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_${c}.json 2>> gpurun_out/${tag}_bench.err
 done
-bash tools/sanitize.sh > gpurun_out/${tag}_sanitize_summary.log 2>&1; cat gpurun_out/${tag}_sanitize_summary.log
+if [ "${SANITIZE:-0}" = 1 ]; then bash tools/sanitize.sh > gpurun_out/${tag}_sanitize_summary.log 2>&1; cat gpurun_out/${tag}_sanitize_summary.log; fi

@@ -23,6 +23,7 @@ from collections import defaultdict
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
+RND = os.environ.get("WGB_ROUND", "r02")      # file-name prefix of the round the run belongs to
 
 METRICS = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -66,26 +67,26 @@ def main():
     tag = sys.argv[1]
     os.makedirs(PROF, exist_ok=True)
     bench = read_line(os.path.join(OUT, "bench_final.json"))
-    json.dump(bench, open(os.path.join(PROF, f"r01_bench_c3_{tag}.json"), "w"), indent=1)
+    json.dump(bench, open(os.path.join(PROF, f"{RND}_bench_c3_{tag}.json"), "w"), indent=1)
     ref = None
     if os.path.exists(os.path.join(OUT, "bench_reference.json")):
         ref = read_line(os.path.join(OUT, "bench_reference.json"))
-        json.dump(ref, open(os.path.join(PROF, "r01_bench_reference_c3.json"), "w"), indent=1)
-    elif os.path.exists(os.path.join(PROF, "r01_bench_reference_c3.json")):
-        ref = json.load(open(os.path.join(PROF, "r01_bench_reference_c3.json")))
-    shutil.copy(os.path.join(OUT, "launches_final.csv"), os.path.join(PROF, f"r01_launches_c3_{tag}.csv"))
+        json.dump(ref, open(os.path.join(PROF, f"{RND}_bench_reference_c3.json"), "w"), indent=1)
+    elif os.path.exists(os.path.join(PROF, f"{RND}_bench_reference_c3.json")):
+        ref = json.load(open(os.path.join(PROF, f"{RND}_bench_reference_c3.json")))
+    shutil.copy(os.path.join(OUT, "launches_final.csv"), os.path.join(PROF, f"{RND}_launches_c3_{tag}.csv"))
     if os.path.exists(os.path.join(ROOT, "build", "ptxas.log")):
-        shutil.copy(os.path.join(ROOT, "build", "ptxas.log"), os.path.join(PROF, f"r01_ptxas_{tag}.log"))
+        shutil.copy(os.path.join(ROOT, "build", "ptxas.log"), os.path.join(PROF, f"{RND}_ptxas_{tag}.log"))
     full = ncu_raw(os.path.join(OUT, "prof_final.ncu-rep"))
-    json.dump(full, open(os.path.join(PROF, f"r01_ncu_full_c3_{tag}.json"), "w"), indent=1)
-    json.dump(full, open(os.path.join(PROF, "r01_ncu_full_c3.json"), "w"), indent=1)
+    json.dump(full, open(os.path.join(PROF, f"{RND}_ncu_full_c3_{tag}.json"), "w"), indent=1)
+    json.dump(full, open(os.path.join(PROF, f"{RND}_ncu_full_c3.json"), "w"), indent=1)
     scaling = {}
     for n in (2, 4, 8):
         p = os.path.join(OUT, f"scale_{n}.json")
         if os.path.exists(p):
             scaling[n] = read_line(p)
     if scaling:
-        json.dump(scaling, open(os.path.join(PROF, f"r01_scaling_{tag}.json"), "w"), indent=1)
+        json.dump(scaling, open(os.path.join(PROF, f"{RND}_scaling_{tag}.json"), "w"), indent=1)
 
     # launch list: average per kernel over the launches of the timed + warm-up passes
     rows = [r for r in csv.reader(open(os.path.join(OUT, "launches_final.csv"))) if len(r) > 10]
@@ -102,10 +103,10 @@ def main():
     w = L.append
     ps = bench["pass_stats"]
     w(f"# Round 1 profile summary (B200, C3: {bench['config']['triangles']} triangles, {bench['config']['width']}x{bench['config']['height']})\n")
-    w(f"Sources: `r01_bench_c3_{tag}.json` (bench.py, not under a profiler), `r01_bench_reference_c3.json` (`--impl reference`), "
-      f"`r01_launches_c3_{tag}.csv` (`ncu --metrics gpu__time_duration.sum --clock-control none`, cold-cache serialised launches: "
-      f"compare shares), `r01_ncu_full_c3_{tag}.json` (`ncu --set full --clock-control none --import-source on`, one launch of each "
-      f"kernel of a pass), `r01_ptxas_{tag}.log` (`ptxas -v` of the kernels as cross-compiled by `build()`). Earlier files in this "
+    w(f"Sources: `{RND}_bench_c3_{tag}.json` (bench.py, not under a profiler), `{RND}_bench_reference_c3.json` (`--impl reference`), "
+      f"`{RND}_launches_c3_{tag}.csv` (`ncu --metrics gpu__time_duration.sum --clock-control none`, cold-cache serialised launches: "
+      f"compare shares), `{RND}_ncu_full_c3_{tag}.json` (`ncu --set full --clock-control none --import-source on`, one launch of each "
+      f"kernel of a pass), `{RND}_ptxas_{tag}.log` (`ptxas -v` of the kernels as cross-compiled by `build()`). Earlier files in this "
       f"directory (v1, v5) are kept for the history of the round.\n")
     w("Commands (one `gpurun` call on a fresh B200, `tools/gpu.sh`):\n\n```\n"
       "python bench.py --steps 50 --warmup 5 > gpurun_out/bench_final.json\n"
@@ -150,7 +151,7 @@ def main():
     others = []
     for cfg, label in (("c1", "C1 teapot 512x512"), ("c2", "C2 bunny 1920x1080, textured"), ("c4", "C4 64-iteration fragment shader 7680x4320"),
                        ("c5", "C5 64 frames of the bunny at 3840x2160"), ("c4_8gpu", "C4 on 8 GPUs (sort-first)"), ("c5_8gpu", "C5 on 8 GPUs (sort-first, frame by frame)")):
-        q = os.path.join(PROF, f"r01_bench_{cfg}_{tag}.json")
+        q = os.path.join(PROF, f"{RND}_bench_{cfg}_{tag}.json")
         if os.path.exists(q):
             others.append((label, read_line(q)))
     if others:
@@ -177,7 +178,7 @@ def main():
         v = vert[0]
         w(f"\nThe vertex kernel is at the HBM roofline: {(num(v, 'dram__bytes_read.sum') + num(v, 'dram__bytes_write.sum')):.0f} MB in {num(v, 'gpu__time_duration.sum'):.1f} us, "
           f"{num(v, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.0f}% DRAM throughput.")
-    open(os.path.join(PROF, "r01_summary.md"), "w").write("\n".join(L) + "\n")
+    open(os.path.join(PROF, f"{RND}_summary.md"), "w").write("\n".join(L) + "\n")
     print("\n".join(L)[:3000])
 
 
