@@ -284,11 +284,27 @@ def main():
     from wgpu_cpu_b200 import api
     from wgpu_cpu_b200.render import SceneRenderer
 
-    if not torch.cuda.is_available():
+    # WGB_CUSIM=1: a dry run of this script's logic (frame numbering, presenter exchange, parity digests) on the software
+    # model of tests/cusim, for development on a machine without a GPU -- test infrastructure, its numbers mean nothing
+    # and its line says so ("data": "software model dry run")
+    model = os.environ.get("WGB_CUSIM") == "1"
+    if model:
+        os.environ.setdefault("CUSIM_ALL_PINNED", "1")
+        os.environ.setdefault("CUSIM_IPC", "1")
+        os.environ.setdefault("CUSIM_DEVICES", str(max(world, 1)))
+        from tests.cusim import build as cusim_build
+        api.LIB_PATH = cusim_build.build()
+    elif not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the B200 backend has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
+    tdev = "cpu" if model else "cuda"
+    sync = (lambda: None) if model else torch.cuda.synchronize
+    if not model:
+        torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if model:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     scene = make(S)
     W, H = scene.width, scene.height
@@ -298,23 +314,32 @@ def main():
     dev, queue = api.instance().request_adapter().request_device(local_rank, band_rank=band_rank, band_count=band_count)
     from wgpu_cpu_b200 import multigpu
     use_emitted = os.environ.get("WGB_USE_EMITTED", "0") == "1"
-    target = None
+    # N > 1: two presenter targets, used alternately, so that a rank that is a frame ahead never stores into the frame
+    # rank 0 is still reading (one barrier per frame is then enough)
+    targets = None
+    n_present = 2 if world > 1 else 1
     if world > 1 and args.present == "peer":
-        own = dev.create_texture(W, H, scene.color_format) if rank == 0 else None
-        target = multigpu.share_presenter_target(dev, own, rank, world, W, H, scene.color_format, dst=0)
-    r = SceneRenderer(dev, queue, scene, use_emitted=use_emitted, target=target)
+        targets = []
+        for _ in range(n_present):
+            own = dev.create_texture(W, H, scene.color_format) if rank == 0 else None
+            targets.append(multigpu.share_presenter_target(dev, own, rank, world, W, H, scene.color_format, dst=0))
+    elif world > 1:
+        targets = [dev.create_texture(W, H, scene.color_format) for _ in range(n_present)]
+    r = SceneRenderer(dev, queue, scene, use_emitted=use_emitted, targets=targets)
     warm = max(args.warmup, 3)
 
     # presenter: every rank's colour band -> rank 0
     row0, row1 = dev.band_rows(H)
     assert (row0, row1) == multigpu.band_rows(H, band_rank, band_count)
-    frame_t = None
+    frame_ts = None
     host_barrier = multigpu.HostBarrier(rank, world, os.environ.get("MASTER_PORT", "0")) if world > 1 and args.present == "peer" else None
     if world > 1 and args.present == "nccl":
-        ptr, nbytes = r.target.device_pointer()
-        frame_t = multigpu.tensor_from_device_pointer(ptr, nbytes, local_rank).view(H, W, 4)
+        frame_ts = []
+        for t in r.targets:
+            ptr, nbytes = t.device_pointer()
+            frame_ts.append(multigpu.tensor_from_device_pointer(ptr, nbytes, local_rank).view(H, W, 4))
 
-    def gather():
+    def gather(which=0):
         if world == 1:
             return
         if args.present == "peer":
@@ -324,13 +349,13 @@ def main():
             host_barrier.wait()
             return
         # the render pass has completed on the backend's stream (poll(Wait)); NCCL runs on torch's stream
-        multigpu.gather_bands(frame_t, rank, world, dst=0)
-        torch.cuda.synchronize()
+        multigpu.gather_bands(frame_ts[which % n_present], rank, world, dst=0)
+        sync()
 
     def barrier():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        sync()
 
     # C5: a step is a batch of 64 frames, each with its own camera (a 64-byte uniform update per frame)
     cameras = None
@@ -342,24 +367,29 @@ def main():
     # The timed span mirrors the reference's own (render_pass/mod.rs:346-392: State::new -> load -> draws -> store, i.e.
     # execution, not recording -- SURVEY 8d): command buffers are recorded before the timed region, one per step, and a
     # step is submit + poll(Wait) (+ the presenter exchange)
-    recorded = []
+    recorded = {}
+    frame_no = [0]          # frames rendered so far: frame k goes to presenter target k % n_present
 
     def step():
+        k = frame_no[0]
         if cameras is None:
-            st = r.render(recorded.pop() if recorded else None)
-            gather()
+            frame_no[0] += 1
+            st = r.render(recorded.pop(k, None) or r.encode(k))
+            gather(k)
             return st
         acc = None
         for cam in cameras:
+            k = frame_no[0]
+            frame_no[0] += 1
             queue.write_buffer(r.resources[(0, 0)], 0, cam)
-            st = r.render()
-            gather()
+            st = r.render(r.encode(k))
+            gather(k)
             if acc is None:
                 acc = dict(st)
             else:
-                for k in ("primitives", "fragments", "shaded", "bin_pairs", "hiz_culled", "big_primitives", "clipped_primitives", "clip_records",
-                          "kernel_launches", "replays", "geometry_ms", "tile_ms", "total_ms"):
-                    acc[k] += st[k]
+                for key in ("primitives", "fragments", "shaded", "bin_pairs", "hiz_culled", "big_primitives", "clipped_primitives", "clip_records",
+                            "kernel_launches", "replays", "geometry_ms", "tile_ms", "total_ms"):
+                    acc[key] += st[key]
         return acc
 
     sampler = ClockSampler(local_rank)
@@ -367,7 +397,8 @@ def main():
     for _ in range(warm):
         step()
     if cameras is None:
-        recorded.extend(r.encode() for _ in range(args.steps))
+        for k in range(frame_no[0], frame_no[0] + args.steps):
+            recorded[k] = r.encode(k)
 
     # ---- timed: K passes, inputs resident in HBM ----
     barrier()
@@ -392,7 +423,7 @@ def main():
     # region, bracketed by barrier + synchronize on both sides, is reported next to it and is used only if the events fail
     dt = event_ms * 1e-3 if event_ms and event_ms > 0 else wall_dt
     if world > 1:
-        tmax = torch.tensor([dt], device="cuda")
+        tmax = torch.tensor([dt], device=tdev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dt = float(tmax.item())
 
@@ -405,70 +436,132 @@ def main():
 
     # ---- e2e: host buffers in, colour target out, every step ----
     e2e = None
-    if not args.no_e2e and cameras is None and (world == 1 or args.present == "peer"):
-        pinned = []
-        for vb in scene.vertex_buffers:
-            t = torch.empty(vb.nbytes, dtype=torch.uint8, pin_memory=True)
-            t.numpy()[:] = vb
-            pinned.append(("vb", t))
+    if not args.no_e2e and cameras is None:
+        # every step uploads one full input set from pinned host memory, renders it and reads the frame back.  At N > 1
+        # each rank uploads 1/N of the vertex and index bytes over its own PCIe link and the ranks all-gather the
+        # slices over NVLink (NCCL, in place in the backend's buffers), so the host feeds the scene once, not N times.
+        sets = [r, SceneRenderer(dev, queue, scene, use_emitted=use_emitted, targets=targets)]
+
+        def pin(a):
+            t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=not model)
+            t.numpy()[:] = a.view(np.uint8).reshape(-1)
+            return t
+
+        big = [("vb", i, pin(vb)) for i, vb in enumerate(scene.vertex_buffers)]
         if scene.index_data is not None:
-            raw = scene.index_data.view(np.uint8).reshape(-1)
-            t = torch.empty(raw.nbytes, dtype=torch.uint8, pin_memory=True)
-            t.numpy()[:] = raw
-            pinned.append(("ib", t))
-        uni = []
-        for key, res in scene.bindings.items():
-            if res[0] == "buffer":
-                t = torch.empty(res[1].nbytes, dtype=torch.uint8, pin_memory=True)
-                t.numpy()[:] = res[1]
-                uni.append((key, t))
-        h2d = sum(t.numel() for _, t in pinned) + sum(t.numel() for _, t in uni)
+            big.append(("ib", 0, pin(scene.index_data)))
+        uni = [(key, pin(res[1])) for key, res in scene.bindings.items() if res[0] == "buffer"]
+
+        def buf_of(rr, kind, i):
+            return rr.vertex_buffers[i] if kind == "vb" else rr.index_buffer
+
+        def chunk(n):           # bytes per rank in the all-gathered part (16-byte granules); the tail is uploaded by every rank
+            return (n // world) & ~15 if world > 1 else n
+
+        alias = {}
+        if world > 1:
+            for si, rr in enumerate(sets):
+                for kind, i, t in big:
+                    ptr, nbytes = buf_of(rr, kind, i).device_pointer()
+                    alias[(si, kind, i)] = multigpu.tensor_from_device_pointer(ptr, nbytes, local_rank)
+        h2d_rank = sum(chunk(t.numel()) + (t.numel() - chunk(t.numel()) * world if world > 1 else 0) for _, _, t in big) + sum(t.numel() for _, t in uni)
         d2h = W * H * 4
+        frame_host = torch.empty(d2h, dtype=torch.uint8, pin_memory=not model)
 
-        # double-buffered: step k+1's inputs upload on the backend's copy stream (wgb_queue_write_buffer from
-        # pinned memory) while step k renders and its colour target is read back; every step still uploads one
-        # full input set, renders it and reads the frame
-        # (N > 1: every rank uploads the whole scene over its own PCIe link -- geometry is replicated in a sort-first
-        # partition -- renders its band into the presenter's target, and rank 0 reads the frame back)
-        sets = [r, SceneRenderer(dev, queue, scene, use_emitted=use_emitted, target=target)]
-        frame_host = torch.empty(d2h, dtype=torch.uint8, pin_memory=True)
-
-        def upload(rr):
-            vi = 0
-            for kind, t in pinned:
-                if kind == "vb":
-                    queue.write_buffer(rr.vertex_buffers[vi], 0, t.numpy())
-                    vi += 1
-                else:
-                    queue.write_buffer(rr.index_buffer, 0, t.numpy())
+        def upload(si):
+            rr = sets[si]
+            for kind, i, t in big:
+                n, c = t.numel(), chunk(t.numel())
+                a = t.numpy()
+                if c:
+                    queue.write_buffer_pinned_async(buf_of(rr, kind, i), rank * c if world > 1 else 0, a[rank * c:(rank + 1) * c] if world > 1 else a)
+                if world > 1 and n > c * world:
+                    queue.write_buffer_pinned_async(buf_of(rr, kind, i), c * world, a[c * world:])
             for key, t in uni:
-                queue.write_buffer(rr.resources[key], 0, t.numpy())
+                queue.write_buffer_pinned_async(rr.resources[key], 0, t.numpy())
+
+        def exchange(si):
+            if world == 1:
+                return
+            queue.wait_uploads()
+            for kind, i, t in big:
+                c = chunk(t.numel())
+                if c:
+                    full = alias[(si, kind, i)]
+                    dist.all_gather_into_tensor(full[:c * world], full[rank * c:(rank + 1) * c])
+            sync()
 
         def e2e_step(k):
-            cur, nxt = sets[k % 2], sets[(k + 1) % 2]
-            upload(nxt)
-            cur.render()
-            gather()
-            return cur.target.read(out=frame_host.numpy()) if rank == 0 else None
+            cur, nxt = k % 2, (k + 1) % 2
+            upload(nxt)                                   # copy stream: overlaps this step's rendering
+            f = frame_no[0]
+            frame_no[0] += 1
+            sets[cur].render(sets[cur].encode(f))
+            gather(f)
+            img = sets[cur].targets[f % n_present].read(out=frame_host.numpy()) if rank == 0 else None
+            exchange(nxt)
+            return img
 
-        upload(sets[0])
+        upload(0)
+        exchange(0)
         for k in range(2):
             e2e_step(k)
         n_e2e = max(4, min(args.steps, 10)) & ~1
         barrier()
         t1 = time.perf_counter()
         for k in range(n_e2e):
-            img = e2e_step(k)
+            e2e_step(k)
+        queue.wait_uploads()
         dev.poll(True)
         barrier()
         de = time.perf_counter() - t1
         if world > 1:
-            tmax = torch.tensor([de], device="cuda")
+            tmax = torch.tensor([de], device=tdev)
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             de = float(tmax.item())
-        e2e = {"value": prims * n_e2e / de / 1e6, "unit": "Mtri/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h),
+            tsum = torch.tensor([float(h2d_rank)], device=tdev, dtype=torch.float64)
+            dist.all_reduce(tsum)
+            h2d_total = int(tsum.item())
+        else:
+            h2d_total = int(h2d_rank)
+        e2e = {"value": prims * n_e2e / de / 1e6, "unit": "Mtri/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": int(d2h),
                "ms_per_step": de / n_e2e * 1e3, "steps": n_e2e,
-               "pipelining": "inputs of step k+1 upload on the copy stream while step k renders (two resident input sets)"}
+               "pipelining": "inputs of step k+1 upload on the copy stream while step k renders (two resident input sets)" +
+                             ("; every rank uploads 1/N of the vertex and index bytes, NCCL all-gather over NVLink" if world > 1 else "")}
+
+    # ---- parity: the frame this run assembles on rank 0 against the oracle's digest (tests/golden, tools/make_bench_golden.py) ----
+    parity = None
+    if not (world == 1 and os.environ.get("WGB_BENCH_BAND")):
+        import hashlib
+        golden = {}
+        try:
+            golden = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_frames_sha256.json"))).get(args.config, {})
+        except Exception:      # noqa: BLE001
+            pass
+        if cameras is None:
+            k = frame_no[0]
+            step()
+            barrier()
+            digest = hashlib.sha256(np.ascontiguousarray(r.targets[k % n_present].read()).tobytes()).hexdigest() if rank == 0 else None
+            want = golden.get("color")
+        else:       # C5: every frame of one more batch
+            frames = []
+            for cam in cameras:
+                k = frame_no[0]
+                frame_no[0] += 1
+                queue.write_buffer(r.resources[(0, 0)], 0, cam)
+                r.render(r.encode(k))
+                gather(k)
+                if rank == 0:
+                    frames.append(hashlib.sha256(np.ascontiguousarray(r.targets[k % n_present].read()).tobytes()).hexdigest())
+                barrier()
+            digest = hashlib.sha256("".join(frames).encode()).hexdigest() if rank == 0 else None
+            want = golden.get("batch")
+        if rank == 0:
+            parity = {"frame_sha256": digest, "oracle_sha256": want, "matches_oracle": (digest == want) if want else None,
+                      "what": ("SHA-256 of the colour bytes of the frame assembled on rank 0" if cameras is None else
+                               f"SHA-256 over the {len(cameras)} frame digests of one more batch") +
+                              ", rendered after the timed region; oracle digest from tests/golden/bench_frames_sha256.json"}
 
     if rank != 0:
         if world > 1:
@@ -491,7 +584,9 @@ def main():
     traffic, note = None, "the kernel is instruction-issue bound; HBM is the roofline the path is held to"
     try:   # one `ncu --set full` capture of this kernel on this workload (tools/make_profiles.py)
         if args.config == "c3" and world == 1:
-            for k in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_c3.json"))):
+            import glob
+            latest = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_ncu_full_c3.json")))[-1]     # the latest round's capture
+            for k in json.load(open(latest)):
                 if k["Kernel Name"] == "wgb_tile_kernel":
                     num = lambda key: float(k[key].split()[0].replace(",", ""))
                     traffic = int((num("dram__bytes_read.sum") + num("dram__bytes_write.sum")) * 1e6)
@@ -523,7 +618,7 @@ def main():
     line = {
         "metric": "Mtri/s", "value": prims * args.steps / dt / 1e6, "unit": "Mtri/s", "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "f32", "data": "software model dry run" if model else "synthetic",
         "config": {"workload": workload, "width": W, "height": H, "triangles": prims,
                    "l2": "inputs (280 MB vertex+index) and attachments (66 MB) exceed the 126 MB L2 at C3; no explicit flush",
                    "timed_span": "submit + poll(Wait) per step (execution, as the reference's own pass timer); command buffers recorded before the timed region",
@@ -540,12 +635,15 @@ def main():
         "device_ms_per_step": dev_ms, "geometry_ms": geom_ms, "tile_ms": tile_ms,
         "pass_stats": {k: last[k] for k in ("primitives", "fragments", "shaded", "bin_pairs", "hiz_culled", "big_primitives",
                                             "clipped_primitives", "clip_records", "kernel_launches", "replays")},
-        "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "parity": parity, "clocks": clocks,
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and parity["matches_oracle"] is False:
+        print(f"bench.py: the rendered frame differs from the oracle's ({parity['frame_sha256']} != {parity['oracle_sha256']})", file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -158,8 +158,19 @@ WGB_API wgb_status wgb_buffer_map_async(wgb_buffer buffer, uint32_t mode, uint64
 WGB_API wgb_status wgb_buffer_get_mapped_range(wgb_buffer buffer, uint64_t offset, uint64_t size, void** out_ptr);
 /* BufferInterface::unmap (buffer.rs:162-172): uploads a write mapping to the device */
 WGB_API wgb_status wgb_buffer_unmap(wgb_buffer buffer);
-/* QueueInterface::write_buffer (device.rs:332-344): immediate, ordered after earlier submissions */
+/* QueueInterface::write_buffer (device.rs:332-344): immediate, ordered after earlier submissions; `data` may be reused or
+ * freed as soon as the call returns, whatever kind of host memory it is */
 WGB_API wgb_status wgb_queue_write_buffer(wgb_queue queue, wgb_buffer buffer, uint64_t offset, const void* data, uint64_t size);
+/* The zero-copy variant (no counterpart in the reference, whose buffers are host memory): `data` must be page-locked
+ * (cudaHostAlloc / cudaHostRegister) and must stay valid and unchanged until wgb_queue_wait_uploads returns, or until
+ * wgb_device_poll has waited for a later submission that uses the buffer.  The copy runs on the device's copy stream,
+ * ordered after the last use of this buffer only, so it overlaps rendering that reads other buffers. */
+WGB_API wgb_status wgb_queue_write_buffer_pinned_async(wgb_queue queue, wgb_buffer buffer, uint64_t offset, const void* data, uint64_t size);
+/* waits for every upload started with wgb_queue_write_buffer_pinned_async */
+WGB_API wgb_status wgb_queue_wait_uploads(wgb_queue queue);
+/* device address and size of the buffer's storage (zero-copy interop with CUDA libraries, e.g. an NCCL all-gather of a
+ * scene that the ranks of a multi-GPU run upload in slices); work on it must be ordered by the caller */
+WGB_API wgb_status wgb_buffer_device_pointer(wgb_buffer buffer, uint64_t* out_ptr, uint64_t* out_size);
 
 /* ---- textures / samplers ---- */
 /* DeviceInterface::create_texture (device.rs:162-175), Texture::new (texture.rs:28-50) */

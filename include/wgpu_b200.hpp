@@ -199,6 +199,9 @@ struct CommandEncoder : Handle<wgb_command_encoder> {
 struct Queue : Handle<wgb_queue> {
     using Handle::Handle;
     void write_buffer(const Buffer& b, uint64_t offset, const void* data, uint64_t size) const { check(wgb_queue_write_buffer(get(), b.get(), offset, data, size)); }   // device.rs:332-344
+    // zero-copy from page-locked memory; `data` stays valid until wait_uploads()
+    void write_buffer_pinned_async(const Buffer& b, uint64_t offset, const void* data, uint64_t size) const { check(wgb_queue_write_buffer_pinned_async(get(), b.get(), offset, data, size)); }
+    void wait_uploads() const { check(wgb_queue_wait_uploads(get())); }
     void write_texture(const Texture& t, const void* data, uint64_t size, uint32_t bytes_per_row = 0) const {                                                           // device.rs:371-434
         check(wgb_queue_write_texture(get(), t.get(), 0, 0, data, size, bytes_per_row, t.desc.width, t.desc.height));
     }

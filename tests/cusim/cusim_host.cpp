@@ -141,7 +141,9 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
 }
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
     memset(a, 0, sizeof *a);
-    a->type = cudaMemoryTypeUnregistered; a->hostPointer = const_cast<void*>(p);
+    // CUSIM_ALL_PINNED=1: every host pointer counts as page-locked (the dry run of bench.py's pinned-upload path)
+    static const bool all_pinned = getenv("CUSIM_ALL_PINNED") != nullptr;
+    a->type = all_pinned ? cudaMemoryTypeHost : cudaMemoryTypeUnregistered; a->hostPointer = const_cast<void*>(p);
     return cudaSuccess;
 }
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* out, void* p) {

@@ -242,6 +242,11 @@ class Adapter(_Handle):
 class Buffer(_Handle):
     size = 0
 
+    def device_pointer(self):
+        p, n = C.c_uint64(), C.c_uint64()
+        _check(_lib.wgb_buffer_device_pointer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
     def get_mapped_range(self, offset=0, size=WHOLE_SIZE) -> np.ndarray:
         """Mapped bytes as a writable numpy view (valid until unmap)."""
         p = C.c_void_p()
@@ -468,6 +473,16 @@ class Queue(_Handle):
     def write_buffer(self, buffer: Buffer, offset: int, data):
         a = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
         _check(_lib.wgb_queue_write_buffer(self._h, buffer._h, C.c_uint64(offset), a.ctypes.data_as(C.c_void_p), C.c_uint64(a.nbytes)))
+
+    def write_buffer_pinned_async(self, buffer: Buffer, offset: int, data):
+        """Zero-copy upload from page-locked memory on the copy stream; `data` must stay valid and unchanged until
+        wait_uploads() (or a poll(wait) of a later submission that uses the buffer)."""
+        a = data if isinstance(data, np.ndarray) and data.flags["C_CONTIGUOUS"] else np.ascontiguousarray(data)
+        a = a.view(np.uint8).reshape(-1)
+        _check(_lib.wgb_queue_write_buffer_pinned_async(self._h, buffer._h, C.c_uint64(offset), a.ctypes.data_as(C.c_void_p), C.c_uint64(a.nbytes)))
+
+    def wait_uploads(self):
+        _check(_lib.wgb_queue_wait_uploads(self._h))
 
     def write_texture(self, texture: Texture, data, bytes_per_row: int = 0, origin=(0, 0), size=None):
         a = np.ascontiguousarray(data)

@@ -221,6 +221,9 @@ std::vector<char> nvrtc_compile(const std::string& source) {
 // ------------------------------------------------------------------------------------------
 // formats
 // ------------------------------------------------------------------------------------------
+// overflow-safe "offset + size <= limit"
+bool range_ok(uint64_t offset, uint64_t size, uint64_t limit) { return offset <= limit && size <= limit - offset; }
+
 uint32_t bytes_per_texel(uint32_t format) {          // texture.rs:457-509
     switch (format) {
         case WGB_TEXTURE_FORMAT_R8_UNORM: return 1;
@@ -321,7 +324,7 @@ struct Device : Object {
     std::map<std::pair<uint32_t, uint32_t>, uint32_t> bin_cap_hint;   // (primitives, band tiles) of a draw -> slots per tile it needed
     bool no_direct_bins = false;
     bool small_work_buffers = false;       // testing knob: start the clip-record and big lists at 2 entries so that both overflow-and-replay paths run
-    DevBuf counters, prim_box, setup_cache, vcache_raster, vcache_ndc, vcache_flags, vcache_vary, slow_list, clip_records, big_list, tile_count, tile_offset, tile_cursor, bins, coverage, strip_map, strip_count;
+    DevBuf counters, prim_box, setup_cache, vcache_raster, vcache_ndc, vcache_flags, slow_list, clip_records, big_list, tile_count, tile_offset, tile_cursor, bins, coverage, strip_map, strip_count;
     WgbCounters* host_counters = nullptr;   // pinned
     uint32_t clip_capacity = 0, big_capacity = 0;
     bool coverage_capture = false;
@@ -339,7 +342,7 @@ struct Device : Object {
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         for (auto& f : inflight) cudaEventDestroy(f.done);
         for (auto& kv : kernel_cache) if (kv.second->module && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->module);
-        DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &vcache_raster, &vcache_ndc, &vcache_flags, &vcache_vary, &slow_list, &clip_records, &big_list, &tile_count, &tile_offset, &tile_cursor, &bins, &coverage, &strip_map, &strip_count};
+        DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &vcache_raster, &vcache_ndc, &vcache_flags, &slow_list, &clip_records, &big_list, &tile_count, &tile_offset, &tile_cursor, &bins, &coverage, &strip_map, &strip_count};
         for (DevBuf* b : bufs) b->release();
         if (host_counters) cudaFreeHost(host_counters);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -450,7 +453,6 @@ struct RenderPipeline : Object {
     Ref<Device> device;
     std::string vs_text, fs_text;
     bool has_fragment = false;
-    uint32_t vary_cache_slots = 0;       // WGB_VARY_CACHE=1 at creation (tuning experiment): WGB_VS_VARYING_SLOTS of the vertex stage, else 0
     struct VB { uint64_t stride; uint32_t step_mode; std::vector<wgb_vertex_attribute> attrs; };
     std::vector<VB> vbs;
     uint32_t topology = 0, strip_index_format = 0, front_face = 0, cull_mode = 0;
@@ -520,11 +522,18 @@ struct RenderPipeline : Object {
         def("WGB_DEPTH_WRITE", (test && depth_write) ? 1 : 0);
         def("WGB_HAS_DEPTH", has_depth_attachment ? 1 : 0);
         def("WGB_NUM_COLOR", (long long)targets.size());
-        if (const char* mb = getenv("WGB_TILE_MIN_BLOCKS")) def("WGB_TILE_MIN_BLOCKS", atoi(mb));   // tuning knobs
-        if (const char* mb = getenv("WGB_FILL_ROUNDS")) def("WGB_FILL_ROUNDS", atoi(mb));
-        if (const char* mb = getenv("WGB_FILL_TARGET")) def("WGB_FILL_TARGET", atoi(mb));
-        if (const char* mb = getenv("WGB_HIZ_PAIRS")) def("WGB_HIZ_PAIRS", std::max(1, std::min(8, atoi(mb))));
-        if (vary_cache_slots) def("WGB_VARY_CACHE", 1);                                            // experiment: varyings kept in the vertex cache
+        // tuning knobs for A/B runs: WGB_TUNE="NAME=value,NAME=value" becomes #define lines ahead of the kernels
+        if (const char* tune = getenv("WGB_TUNE")) {
+            std::string t(tune);
+            for (size_t at = 0; at < t.size();) {
+                size_t end = t.find(',', at);
+                if (end == std::string::npos) end = t.size();
+                const std::string kv = t.substr(at, end - at);
+                const size_t eq = kv.find('=');
+                if (eq != std::string::npos && eq > 0) def(kv.substr(0, eq).c_str(), atoll(kv.c_str() + eq + 1));
+                at = end + 1;
+            }
+        }
         for (size_t b = 0; b < vbs.size(); b++)
             for (const auto& a : vbs[b].attrs) {
                 snprintf(line, sizeof(line), "#define WGB_ATTR%u_SLOT %zu\n#define WGB_ATTR%u_STRIDE %lluu\n#define WGB_ATTR%u_OFFSET %lluu\n#define WGB_ATTR%u_INSTANCE %s\n",
@@ -734,7 +743,10 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
     d.first_instance = sc.first_instance; d.instance_count = sc.instance_count;
     if (indexed) {
         Buffer* ib = st.index_buffer.buffer.get();
+        REQUIRE(ib->device.get() == dev, "index buffer belongs to another device");
         REQUIRE(st.index_buffer.offset <= ib->size, "index buffer offset out of range");
+        // bytemuck::cast_slice panics on a misaligned slice (index.rs:45-51); a misaligned device load would be a sticky fault
+        REQUIRE(st.index_buffer.offset % (st.index_format == WGB_INDEX_FORMAT_UINT16 ? 2 : 4) == 0, "index buffer offset is not a multiple of the index size");
         d.index_ptr = (uint64_t)(uintptr_t)ib->dptr + st.index_buffer.offset;
         d.index_size = std::min<uint64_t>(st.index_buffer.size, ib->size - st.index_buffer.offset);
         // every index of the range is fetched (state.rs:521-535), so a range that leaves the buffer is a certain
@@ -747,6 +759,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
     for (size_t b = 0; b < pipe->vbs.size(); b++) {                                     // vertex.rs:262-272
         Buffer* vb = st.vertex_buffers[b].buffer.get();
         if (!vb) fail(WGB_ERROR_VALIDATION, "Buffer %zu not bound", b);
+        REQUIRE(vb->device.get() == dev, "vertex buffer %zu belongs to another device", b);
         REQUIRE(st.vertex_buffers[b].offset <= vb->size, "vertex buffer offset out of range");
         d.vb[b].ptr = (uint64_t)(uintptr_t)vb->dptr + st.vertex_buffers[b].offset;
         d.vb[b].size = std::min<uint64_t>(st.vertex_buffers[b].size, vb->size - st.vertex_buffers[b].offset);
@@ -769,6 +782,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             WgbResource& r = d.res[g][e.binding];
             r.kind = e.kind;
             if (e.kind == WGB_BINDING_BUFFER) {
+                REQUIRE(e.buffer->device.get() == dev, "bind group buffer belongs to another device");
                 const uint64_t off = e.offset + (dyn.count(e.binding) ? dyn[e.binding] : 0);
                 REQUIRE(off <= e.buffer->size, "bind group buffer offset out of range");
                 r.ptr = (uint64_t)(uintptr_t)e.buffer->dptr + off;
@@ -777,6 +791,8 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 Texture* t = e.view->texture.get();
                 if (t->desc.format != WGB_TEXTURE_FORMAT_RGBA8_UNORM && t->desc.format != WGB_TEXTURE_FORMAT_RGBA8_UNORM_SRGB)
                     fail(WGB_ERROR_UNSUPPORTED, "sampled texture format %u (the reference reads Rgba8Unorm[Srgb] only, texture.rs:176-186)", t->desc.format);
+                REQUIRE(t->device.get() == dev, "sampled texture belongs to another device");
+                if (e.view->base_layer != 0) fail(WGB_ERROR_UNSUPPORTED, "sampled texture views must start at array layer 0 (the reference samples layer 0 only, texture.rs:176-186)");
                 r.ptr = (uint64_t)(uintptr_t)t->dptr;
                 r.tex = (uint64_t)t->texture_object();
                 r.a = t->desc.width; r.b = t->desc.height; r.c = t->desc.format;
@@ -864,10 +880,6 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 dev->vcache_raster.ensure(nv * 16); dev->vcache_ndc.ensure(nv * 8); dev->vcache_flags.ensure(nv * 4);
                 d.vcache_raster = dev->vcache_raster.addr(); d.vcache_ndc = dev->vcache_ndc.addr(); d.vcache_flags = dev->vcache_flags.addr();
                 d.vcache_count = (uint32_t)vcache_n;
-                if (pipe->vary_cache_slots) {          // pipelines created with WGB_VARY_CACHE=1 (an experiment, off by default)
-                    dev->vcache_vary.ensure(nv * pipe->vary_cache_slots * 4);
-                    d.vcache_vary = dev->vcache_vary.addr();
-                }
             }
             dev->slow_list.ensure((size_t)np * 4);
             dev->clip_records.ensure((size_t)clip_cap * sizeof(WgbClipRecord));
@@ -884,10 +896,11 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 uint64_t cap = it != dev->bin_cap_hint.end() ? it->second
                                                              : 2 * ((uint64_t)np * 5 / 4) / std::max<uint32_t>(band_tiles, 1) + 64;
                 cap = (std::max<uint64_t>(cap, 256) + 255) & ~255ull;
-                if (!dev->no_direct_bins && band_tiles > 0 && (uint64_t)band_tiles * cap * 4 <= (1ull << 30)) bin_cap = (uint32_t)cap;
+                if (!dev->no_direct_bins && band_tiles > 0 && (uint64_t)band_tiles * cap * 8 <= (2ull << 30)) bin_cap = (uint32_t)cap;
             }
             d.bin_cap = bin_cap;
-            dev->bins.ensure(bin_cap ? (size_t)band_tiles * bin_cap * 4 : ((size_t)np + clip_cap) * WGB_SMALL_MAX_TILES * 4);
+            // 8 bytes per entry: pipelines with the hierarchical depth test store a bound next to every entry (WGB_BIN_WORDS)
+            dev->bins.ensure(bin_cap ? (size_t)band_tiles * bin_cap * 8 : ((size_t)np + clip_cap) * WGB_SMALL_MAX_TILES * 8);
             d.counters = dev->counters.addr(); d.prim_box = dev->prim_box.addr(); d.slow_list = dev->slow_list.addr();
             d.setup_cache = dev->setup_cache.addr();
             d.clip_records = dev->clip_records.addr(); d.clip_capacity = clip_cap;
@@ -1017,9 +1030,10 @@ void execute_pass_body(Device* dev, const PassCommand& pass) {
         Texture* t = pass.depth_view->texture.get();
         if (pass.has_stencil_ops) fail(WGB_ERROR_UNSUPPORTED, "stencil_ops (fragment.rs:618-620 todo!)");
         if (t->desc.format != WGB_TEXTURE_FORMAT_DEPTH32_FLOAT) fail(WGB_ERROR_UNSUPPORTED, "depth attachments must be Depth32Float (texture.rs:220-239 reads raw f32)");
+        REQUIRE(t->device.get() == dev, "depth attachment belongs to another device");
         check_size(t);
         tg.has_depth = true;
-        tg.depth.ptr = (uint64_t)(uintptr_t)t->dptr;
+        tg.depth.ptr = (uint64_t)(uintptr_t)t->dptr + (uint64_t)pass.depth_view->base_layer * t->desc.width * t->desc.height * 4ull;
         tg.depth.format = t->desc.format;
         tg.depth.bytes_per_texel = 4;
         tg.depth.load_clear = (pass.has_depth_ops && pass.depth_load_op == WGB_LOAD_OP_CLEAR) ? 1u : 0u;
@@ -1171,7 +1185,7 @@ void check_texture_rect(const Texture* t, uint32_t x, uint32_t y, uint32_t layer
 void check_buffer_rect(const Buffer* b, uint64_t offset, uint32_t bytes_per_row, uint32_t bpp, uint32_t w, uint32_t h, const char* what) {
     const uint64_t row = (uint64_t)w * bpp, pitch = bytes_per_row ? bytes_per_row : row;
     REQUIRE(pitch >= row, "%s: bytes_per_row smaller than a row", what);
-    REQUIRE(h == 0 || offset + (uint64_t)(h - 1) * pitch + row <= b->size, "%s: buffer range out of bounds", what);
+    REQUIRE(h == 0 || range_ok(offset, (uint64_t)(h - 1) * pitch + row, b->size), "%s: buffer range out of bounds", what);
 }
 
 
@@ -1413,7 +1427,7 @@ wgb_status wgb_buffer_map_async(wgb_buffer buffer, uint32_t mode, uint64_t offse
         REQUIRE(!b->mapped, "buffer is already mapped");
         REQUIRE(mode == WGB_MAP_MODE_READ || mode == WGB_MAP_MODE_WRITE, "invalid map mode");
         if (size == WGB_WHOLE_SIZE) size = b->size - std::min(offset, b->size);
-        REQUIRE(offset + size <= b->size, "map range out of bounds");
+        REQUIRE(range_ok(offset, size, b->size), "map range out of bounds");
         b->staging.assign(b->size, 0);
         Device* dev = b->device.get();
         if (!dev->compile_only) {
@@ -1435,8 +1449,8 @@ wgb_status wgb_buffer_get_mapped_range(wgb_buffer buffer, uint64_t offset, uint6
         REQUIRE(out_ptr, "out is null");
         std::lock_guard<std::mutex> lk(b->mu);
         REQUIRE(b->mapped, "buffer is not mapped");
-        if (size == WGB_WHOLE_SIZE) size = b->size - std::min(offset, b->size);
-        REQUIRE(offset + size <= b->size, "mapped range out of bounds");
+        if (size == WGB_WHOLE_SIZE) size = (b->map_offset + b->map_size) - std::min(offset, b->map_offset + b->map_size);
+        REQUIRE(offset >= b->map_offset && range_ok(offset, size, b->map_offset + b->map_size), "range lies outside the mapped range");
         *out_ptr = b->staging.data() + offset;
     });
 }
@@ -1458,35 +1472,60 @@ wgb_status wgb_buffer_unmap(wgb_buffer buffer) {
         std::vector<uint8_t>().swap(b->staging);
     });
 }
+static void write_buffer_impl(wgb_queue queue, wgb_buffer buffer, uint64_t offset, const void* data, uint64_t size, bool async) {
+    Queue* q = from_handle<Queue>(queue, "queue");
+    Buffer* b = from_handle<Buffer>(buffer, "buffer");
+    REQUIRE(data || size == 0, "data is null");
+    REQUIRE(range_ok(offset, size, b->size), "write_buffer range out of bounds");
+    Device* dev = q->device.get();
+    REQUIRE(b->device.get() == dev, "buffer belongs to another device");
+    if (dev->compile_only || size == 0) return;
+    std::lock_guard<std::recursive_mutex> dl(dev->mu);
+    dev->make_current();
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, data) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (async) REQUIRE(pinned, "wgb_queue_write_buffer_pinned_async needs page-locked host memory");
+    if (pinned && (async || size >= (1u << 20))) {
+        // an upload from pinned memory: DMA on the copy stream, ordered after the last use of this buffer only, so it
+        // overlaps rendering that reads other buffers; the next submission that uses the buffer waits for it
+        if (b->use_pending) { CUDA_CHECK(cudaStreamWaitEvent(dev->copy_stream, b->ev_use, 0)); b->use_pending = false; }
+        if (b->write_pending) CUDA_CHECK(cudaStreamWaitEvent(dev->copy_stream, b->ev_write, 0));
+        CUDA_CHECK(cudaMemcpyAsync((char*)b->dptr + offset, data, size, cudaMemcpyHostToDevice, dev->copy_stream));
+        if (!b->ev_write) CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_write, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventRecord(b->ev_write, dev->copy_stream));
+        b->write_pending = true;
+        // wgpu's contract (device.rs:332-344): `data` may be reused as soon as write_buffer returns
+        if (!async) CUDA_CHECK(cudaEventSynchronize(b->ev_write));
+    } else {
+        // pageable source: the runtime stages the bytes before cudaMemcpyAsync returns, so `data` may be reused
+        b->acquire_on(dev->stream);
+        CUDA_CHECK(cudaMemcpyAsync((char*)b->dptr + offset, data, size, cudaMemcpyHostToDevice, dev->stream));
+        b->mark_used(dev->stream);
+    }
+}
 wgb_status wgb_queue_write_buffer(wgb_queue queue, wgb_buffer buffer, uint64_t offset, const void* data, uint64_t size) {
+    return guarded([&] { write_buffer_impl(queue, buffer, offset, data, size, false); });
+}
+wgb_status wgb_queue_write_buffer_pinned_async(wgb_queue queue, wgb_buffer buffer, uint64_t offset, const void* data, uint64_t size) {
+    return guarded([&] { write_buffer_impl(queue, buffer, offset, data, size, true); });
+}
+wgb_status wgb_queue_wait_uploads(wgb_queue queue) {
     return guarded([&] {
         Queue* q = from_handle<Queue>(queue, "queue");
-        Buffer* b = from_handle<Buffer>(buffer, "buffer");
-        REQUIRE(data || size == 0, "data is null");
-        REQUIRE(offset + size <= b->size, "write_buffer range out of bounds");
         Device* dev = q->device.get();
-        if (dev->compile_only || size == 0) return;
+        if (dev->compile_only) return;
         std::lock_guard<std::recursive_mutex> dl(dev->mu);
         dev->make_current();
-        cudaPointerAttributes attr;
-        const bool pinned = size >= (1u << 20) && cudaPointerGetAttributes(&attr, data) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-        cudaGetLastError();
-        if (pinned) {
-            // a large upload from pinned memory: DMA on the copy stream, ordered after the last use of this buffer
-            // only, so it overlaps rendering that reads other buffers; the next submission that uses the buffer
-            // waits for it.  (`data` must stay valid until then, as with any pinned asynchronous copy.)
-            if (b->use_pending) { CUDA_CHECK(cudaStreamWaitEvent(dev->copy_stream, b->ev_use, 0)); b->use_pending = false; }
-            if (b->write_pending) CUDA_CHECK(cudaStreamWaitEvent(dev->copy_stream, b->ev_write, 0));
-            CUDA_CHECK(cudaMemcpyAsync((char*)b->dptr + offset, data, size, cudaMemcpyHostToDevice, dev->copy_stream));
-            if (!b->ev_write) CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_write, cudaEventDisableTiming));
-            CUDA_CHECK(cudaEventRecord(b->ev_write, dev->copy_stream));
-            b->write_pending = true;
-        } else {
-            // pageable source: the copy is staged before the call returns, so `data` may be reused
-            b->acquire_on(dev->stream);
-            CUDA_CHECK(cudaMemcpyAsync((char*)b->dptr + offset, data, size, cudaMemcpyHostToDevice, dev->stream));
-            b->mark_used(dev->stream);
-        }
+        CUDA_CHECK(cudaStreamSynchronize(dev->copy_stream));
+    });
+}
+wgb_status wgb_buffer_device_pointer(wgb_buffer buffer, uint64_t* out_ptr, uint64_t* out_size) {
+    return guarded([&] {
+        Buffer* b = from_handle<Buffer>(buffer, "buffer");
+        REQUIRE(out_ptr, "out is null");
+        *out_ptr = (uint64_t)(uintptr_t)b->dptr;
+        if (out_size) *out_size = b->size;
     });
 }
 
@@ -1736,11 +1775,6 @@ wgb_status wgb_device_create_render_pipeline(wgb_device device, const wgb_render
         p->device = Ref<Device>(dev);
         ShaderModule* vm = from_handle<ShaderModule>(desc->vertex_module, "vertex shader module");
         p->vs_text = vm->cuda_for(WGB_SHADER_STAGE_VERTEX, desc->vertex_entry_point ? desc->vertex_entry_point : "vs_main");
-        if (const char* vc = getenv("WGB_VARY_CACHE")) {
-            const std::string key = "#define WGB_VS_VARYING_SLOTS ";
-            const size_t at = p->vs_text.find(key);
-            if (atoi(vc) != 0 && at != std::string::npos) p->vary_cache_slots = (uint32_t)atoi(p->vs_text.c_str() + at + key.size());
-        }
         if (desc->fragment_module) {
             ShaderModule* fm = from_handle<ShaderModule>(desc->fragment_module, "fragment shader module");
             p->fs_text = fm->cuda_for(WGB_SHADER_STAGE_FRAGMENT, desc->fragment_entry_point ? desc->fragment_entry_point : "fs_main");
@@ -1911,7 +1945,7 @@ wgb_status wgb_command_encoder_copy_buffer_to_buffer(wgb_command_encoder encoder
         c->src_buffer = Ref<Buffer>(from_handle<Buffer>(source, "buffer"));
         c->dst_buffer = Ref<Buffer>(from_handle<Buffer>(destination, "buffer"));
         if (size == WGB_WHOLE_SIZE) size = c->src_buffer->size - std::min(c->src_buffer->size, source_offset);
-        REQUIRE(source_offset + size <= c->src_buffer->size && destination_offset + size <= c->dst_buffer->size, "copy_buffer_to_buffer range out of bounds");
+        REQUIRE(range_ok(source_offset, size, c->src_buffer->size) && range_ok(destination_offset, size, c->dst_buffer->size), "copy_buffer_to_buffer range out of bounds");
         c->src_offset = source_offset; c->dst_offset = destination_offset; c->size = size;
         record_copy(encoder, c);
     });
@@ -1968,7 +2002,7 @@ wgb_status wgb_command_encoder_clear_buffer(wgb_command_encoder encoder, wgb_buf
         c->kind = CopyCommand::ClearBuffer;
         c->dst_buffer = Ref<Buffer>(from_handle<Buffer>(buffer, "buffer"));
         if (size == WGB_WHOLE_SIZE) size = c->dst_buffer->size - std::min(c->dst_buffer->size, offset);
-        REQUIRE(offset + size <= c->dst_buffer->size, "clear_buffer range out of bounds");
+        REQUIRE(range_ok(offset, size, c->dst_buffer->size), "clear_buffer range out of bounds");
         c->dst_offset = offset; c->size = size;
         record_copy(encoder, c);
     });

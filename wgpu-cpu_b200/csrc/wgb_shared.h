@@ -165,5 +165,4 @@ struct WgbDraw {
     wgb_u64 tile_cursor;                 // u32 per tile
     wgb_u64 bins;                        // u32 entries
     wgb_u64 coverage;                    // optional u32 per pixel (stats)
-    wgb_u64 vcache_vary;                 // WGB_VARY_CACHE pipelines (a tuning experiment, off by default): u32 x WGB_VS_VARYING_SLOTS per cached vertex, else 0
 };

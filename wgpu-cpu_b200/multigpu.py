@@ -86,6 +86,11 @@ class HostBarrier:
 def tensor_from_device_pointer(ptr: int, nbytes: int, device_index: int):
     """Zero-copy torch uint8 view of device memory owned by the backend (a texture's texel storage)."""
     import torch
+    import os
+    if os.environ.get("WGB_CUSIM") == "1":      # the software model of tests/cusim: "device" memory is host memory
+        import ctypes
+        import numpy as np
+        return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(ptr)))
 
     class _Holder:
         pass

@@ -26,9 +26,11 @@ class SceneRenderer:
     """Holds the device-resident resources of one scene so that frames can be re-submitted."""
 
     def __init__(self, device: api.Device, queue: api.Queue, scene: Scene, use_emitted: bool = False,
-                 target: Optional[api.Texture] = None):
+                 target: Optional[api.Texture] = None, targets: Optional[list] = None):
         """`target`: render into this texture instead of creating one (e.g. the presenter's colour target
-        imported over CUDA IPC, so that the tile kernel stores its band straight into peer memory)."""
+        imported over CUDA IPC, so that the tile kernel stores its band straight into peer memory).
+        `targets`: several colour targets to alternate between (`encode(which)`): consecutive frames of a multi-GPU run
+        go to different presenter targets, so that a rank that is ahead never stores into the frame being read."""
         self.device, self.queue, self.scene = device, queue, scene
         s = scene
         if use_emitted:
@@ -82,8 +84,12 @@ class SceneRenderer:
                     [fmt for fmt, _ in (s.extra_targets or [])])
         self.extra_targets = [device.create_texture(s.width, s.height, fmt) for fmt, _ in (s.extra_targets or [])]
         self.extra_views = [t.create_view() for t in self.extra_targets]
-        self.target = target if target is not None else device.create_texture(s.width, s.height, s.color_format)
-        self.target_view = self.target.create_view()
+        if targets:
+            self.targets = list(targets)
+        else:
+            self.targets = [target if target is not None else device.create_texture(s.width, s.height, s.color_format)]
+        self.target_views = [t.create_view() for t in self.targets]
+        self.target, self.target_view = self.targets[0], self.target_views[0]
         self.depth_texture = self.depth_view = None
         if s.has_depth:
             self.depth_texture = device.create_texture(s.width, s.height, "depth32float")
@@ -93,10 +99,10 @@ class SceneRenderer:
         if s.initial_depth is not None and self.depth_texture is not None:
             queue.write_texture(self.depth_texture, np.ascontiguousarray(s.initial_depth, dtype=np.float32))
 
-    def encode(self) -> api.CommandBuffer:
+    def encode(self, which: int = 0) -> api.CommandBuffer:
         s = self.scene
         enc = self.device.create_command_encoder()
-        color = {"view": self.target_view, "load": ("clear", s.clear_color) if s.clear_color is not None else "load"}
+        color = {"view": self.target_views[which % len(self.target_views)], "load": ("clear", s.clear_color) if s.clear_color is not None else "load"}
         depth = None
         if s.has_depth:
             depth = {"view": self.depth_view, "depth_load": ("clear", s.clear_depth) if s.clear_depth is not None else "load",
