@@ -334,6 +334,40 @@ struct Device : Object {
     wgb_pass_stats last_stats{};
     std::map<std::string, std::shared_ptr<KernelSet>> kernel_cache;   // by translation-unit text
 
+    // Asynchronous submissions (device.rs:436-462: submit returns an index at once, poll waits).  A render pass whose
+    // attachments are all cleared on load is enqueued without waiting for its counters; what it left behind -- counters
+    // of every draw batch in pinned memory, events for the timings -- is looked at when somebody waits (`settle`).  If a
+    // batch overflowed its work buffers or raised an error, its tile kernel has set the `poison` word and every later
+    // tile / clear kernel has left the attachments alone: settle re-runs the failed pass and everything queued behind
+    // it, synchronously.  (Passes that load their attachments, strips with primitive restart and the coverage capture
+    // of the parity tests are executed synchronously as before; so is everything with WGB_SYNC_SUBMIT=1.)
+    bool async_submit = true;
+    struct PendingBatch { WgbCounters* host; cudaEvent_t ev[3]; uint32_t np, band_tiles; };
+    struct Unsettled {
+        uint64_t submission = 0;
+        std::shared_ptr<struct PassCommand> pass;              // a render pass that was enqueued without waiting, or ...
+        struct Buffer* write_buffer = nullptr;                 // ... a small queue.write_buffer issued behind one (kept alive by write_ref)
+        std::shared_ptr<void> write_ref;
+        uint64_t write_offset = 0;
+        std::vector<uint8_t> write_data;
+        std::vector<PendingBatch> batches;
+        wgb_pass_stats stats{};
+    };
+    std::deque<Unsettled> unsettled;
+    Unsettled* recording = nullptr;        // the pass being enqueued asynchronously (execute_draw appends its batches)
+    bool settling = false;
+    uint64_t current_submission = 0;
+    DevBuf poison;
+    static constexpr uint32_t COUNTER_RING = 2048;
+    WgbCounters* counter_ring = nullptr;   // pinned
+    uint32_t counter_ring_used = 0;
+    std::vector<cudaEvent_t> event_pool;
+    size_t event_pool_used = 0;
+    cudaEvent_t pool_event() {
+        if (event_pool_used == event_pool.size()) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); event_pool.push_back(e); }
+        return event_pool[event_pool_used++];
+    }
+
     void make_current() const { if (!compile_only) CUDA_CHECK(cudaSetDevice(ordinal)); }
     ~Device() override {
         if (compile_only) return;
@@ -345,6 +379,9 @@ struct Device : Object {
         DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &vcache_raster, &vcache_ndc, &vcache_flags, &slow_list, &clip_records, &big_list, &tile_count, &tile_offset, &tile_cursor, &bins, &coverage, &strip_map, &strip_count};
         for (DevBuf* b : bufs) b->release();
         if (host_counters) cudaFreeHost(host_counters);
+        if (counter_ring) cudaFreeHost(counter_ring);
+        for (auto& e : event_pool) cudaEventDestroy(e);
+        poison.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : timer_ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -367,6 +404,7 @@ struct Buffer : Object {
     // guarded by the device mutex
     cudaEvent_t ev_write = nullptr, ev_use = nullptr;
     bool write_pending = false, use_pending = false;
+    uint64_t last_use_submission = 0;       // the latest submission that reads or writes the buffer (guarded by the device mutex)
     ~Buffer() override {
         if (!dptr) return;
         cudaSetDevice(device->ordinal);
@@ -701,6 +739,40 @@ struct PassTargets {
     WgbAttachment depth;
 };
 
+// What a draw batch left behind, once its kernels have completed: timings, the capacity the fullest tile needed, counters.
+// Returns true if a work buffer overflowed (the capacities have been raised: the batch has to run again); raises the
+// error a geometry-stage status bit stands for.
+bool batch_result(Device* dev, const Device::PendingBatch& pb, uint32_t np, uint32_t band_tiles, wgb_pass_stats& stats) {
+    const WgbCounters c = *pb.host;
+    float g_ms = 0, t_ms = 0;
+    cudaEventElapsedTime(&g_ms, pb.ev[0], pb.ev[1]);
+    cudaEventElapsedTime(&t_ms, pb.ev[1], pb.ev[2]);
+    stats.geometry_ms += g_ms;
+    stats.tile_ms += t_ms;
+    stats.total_ms += g_ms + t_ms;
+    if (dev->bin_cap_hint.size() > 4096) dev->bin_cap_hint.clear();
+    if (c.max_tile_pairs) {     // never shrinks: draws of one shape whose fullest tile varies (a moving camera) must not alternate between overflow and replay
+        uint32_t& hint = dev->bin_cap_hint[std::make_pair(np, band_tiles)];
+        hint = std::max<uint32_t>(hint, (uint32_t)std::min<uint64_t>((uint64_t)c.max_tile_pairs * 5 / 4 + 64, 0xFFFFFF00ull));
+    }
+    if (c.status & (WGB_STATUS_CLIP_OVERFLOW | WGB_STATUS_BIG_OVERFLOW | WGB_STATUS_BIN_OVERFLOW)) {
+        if (c.status & WGB_STATUS_CLIP_OVERFLOW) dev->clip_capacity = std::max<uint32_t>(dev->clip_capacity * 2, c.num_clip_records + 1024);
+        if (c.status & WGB_STATUS_BIG_OVERFLOW) dev->big_capacity = std::max<uint32_t>(dev->big_capacity * 2, c.num_big + 1024);
+        return true;
+    }
+    if (c.status & WGB_STATUS_INDEX_OOB) fail(WGB_ERROR_OUT_OF_BOUNDS, "an index lies outside the bound index buffer or overflows with base_vertex (index.rs:45-62)");
+    if (c.status & WGB_STATUS_VERTEX_OOB) fail(WGB_ERROR_OUT_OF_BOUNDS, "a vertex attribute fetch lies outside its vertex buffer (vertex.rs:143-154)");
+    if (c.status & WGB_STATUS_W_ZERO) fail(WGB_ERROR_VALIDATION, "a clip position has w = 0 (the reference panics: raster.rs:146, primitive.rs:175-177)");
+    stats.fragments += c.fragments;
+    stats.shaded += c.shaded;
+    stats.bin_pairs += c.num_small_pairs;
+    stats.big_primitives += c.num_big;
+    stats.clipped_primitives += c.num_slow;
+    stats.clip_records += c.num_clip_records;
+    stats.hiz_culled += c.hiz_culled;
+    return false;
+}
+
 void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand& sc) {
     RenderPipeline* pipe = st.pipeline.get();
     if (!pipe) fail(WGB_ERROR_VALIDATION, "No pipeline bound");                       // state.rs:240-243
@@ -896,11 +968,10 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 uint64_t cap = it != dev->bin_cap_hint.end() ? it->second
                                                              : 2 * ((uint64_t)np * 5 / 4) / std::max<uint32_t>(band_tiles, 1) + 64;
                 cap = (std::max<uint64_t>(cap, 256) + 255) & ~255ull;
-                if (!dev->no_direct_bins && band_tiles > 0 && (uint64_t)band_tiles * cap * 8 <= (2ull << 30)) bin_cap = (uint32_t)cap;
+                if (!dev->no_direct_bins && band_tiles > 0 && (uint64_t)band_tiles * cap * 4 <= (1ull << 30)) bin_cap = (uint32_t)cap;
             }
             d.bin_cap = bin_cap;
-            // 8 bytes per entry: pipelines with the hierarchical depth test store a bound next to every entry (WGB_BIN_WORDS)
-            dev->bins.ensure(bin_cap ? (size_t)band_tiles * bin_cap * 8 : ((size_t)np + clip_cap) * WGB_SMALL_MAX_TILES * 8);
+            dev->bins.ensure(bin_cap ? (size_t)band_tiles * bin_cap * 4 : ((size_t)np + clip_cap) * WGB_SMALL_MAX_TILES * 4);
             d.counters = dev->counters.addr(); d.prim_box = dev->prim_box.addr(); d.slow_list = dev->slow_list.addr();
             d.setup_cache = dev->setup_cache.addr();
             d.clip_records = dev->clip_records.addr(); d.clip_capacity = clip_cap;
@@ -908,7 +979,18 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             d.tile_count = dev->counters.addr() + sizeof(WgbCounters); d.tile_offset = dev->tile_offset.addr(); d.tile_cursor = dev->tile_cursor.addr();
             d.bins = dev->bins.addr();
 
-            CUDA_CHECK(cudaEventRecord(dev->ev[0], dev->stream));
+            const bool async = dev->recording != nullptr;
+            d.poison = async ? dev->poison.addr() : 0;
+            Device::PendingBatch pb{};
+            if (async) {
+                pb.host = dev->counter_ring + dev->counter_ring_used++;
+                for (auto& e : pb.ev) e = dev->pool_event();
+                pb.np = np; pb.band_tiles = band_tiles;
+            } else {
+                pb.host = dev->host_counters;
+                for (int k = 0; k < 3; k++) pb.ev[k] = dev->ev[k];
+            }
+            CUDA_CHECK(cudaEventRecord(pb.ev[0], dev->stream));
             CUDA_CHECK(cudaMemsetAsync(dev->counters.p, 0, sizeof(WgbCounters) + (size_t)(band_tiles + 1) * 4, dev->stream));
             const uint32_t gblocks = (np + 255) / 256;
             if (vcache_n) {
@@ -922,42 +1004,24 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 launch(dev, ks->fill, dim3(gblocks), dim3(256), &d);
             }
             if (ks->ordered) launch(dev, ks->big_sort, dim3(1), dim3(1024), &d);
-            CUDA_CHECK(cudaEventRecord(dev->ev[1], dev->stream));
+            CUDA_CHECK(cudaEventRecord(pb.ev[1], dev->stream));
             launch(dev, ks->tile, dim3(d.tiles_x, d.band_ty1 - d.band_ty0), dim3(256), &d);
-            CUDA_CHECK(cudaEventRecord(dev->ev[2], dev->stream));
-            CUDA_CHECK(cudaMemcpyAsync(dev->host_counters, dev->counters.p, sizeof(WgbCounters), cudaMemcpyDeviceToHost, dev->stream));
-            CUDA_CHECK(cudaStreamSynchronize(dev->stream));
-            const WgbCounters c = *dev->host_counters;
-            float g_ms = 0, t_ms = 0;
-            cudaEventElapsedTime(&g_ms, dev->ev[0], dev->ev[1]);
-            cudaEventElapsedTime(&t_ms, dev->ev[1], dev->ev[2]);
-            dev->last_stats.geometry_ms += g_ms;
-            dev->last_stats.tile_ms += t_ms;
-            dev->last_stats.total_ms += g_ms + t_ms;
-            if (dev->bin_cap_hint.size() > 4096) dev->bin_cap_hint.clear();
-            if (c.max_tile_pairs) {     // never shrinks: draws of one shape whose fullest tile varies (a moving camera) must not alternate between overflow and replay
-                uint32_t& hint = dev->bin_cap_hint[std::make_pair(np, band_tiles)];
-                hint = std::max<uint32_t>(hint, (uint32_t)std::min<uint64_t>((uint64_t)c.max_tile_pairs * 5 / 4 + 64, 0xFFFFFF00ull));
+            CUDA_CHECK(cudaEventRecord(pb.ev[2], dev->stream));
+            CUDA_CHECK(cudaMemcpyAsync(pb.host, dev->counters.p, sizeof(WgbCounters), cudaMemcpyDeviceToHost, dev->stream));
+            if (async) {
+                // not waited for: settle() looks at the counters when somebody waits, and re-runs the pass if this batch failed
+                dev->recording->batches.push_back(pb);
+                dev->last_stats.primitives += np;
+                break;
             }
-            if (c.status & (WGB_STATUS_CLIP_OVERFLOW | WGB_STATUS_BIG_OVERFLOW | WGB_STATUS_BIN_OVERFLOW)) {
-                // the tile kernel saw the flag and left the attachments untouched: grow and replay
+            CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+            if (batch_result(dev, pb, np, band_tiles, dev->last_stats)) {
+                // the tile kernel saw the overflow flag and left the attachments untouched: the buffers have grown, replay
                 if (attempt >= 8) fail(WGB_ERROR_OUT_OF_MEMORY, "work buffers still too small after %d replays", attempt);
-                if (c.status & WGB_STATUS_CLIP_OVERFLOW) dev->clip_capacity = std::max<uint32_t>(dev->clip_capacity * 2, c.num_clip_records + 1024);
-                if (c.status & WGB_STATUS_BIG_OVERFLOW) dev->big_capacity = std::max<uint32_t>(dev->big_capacity * 2, c.num_big + 1024);
                 dev->last_stats.replays++;
                 continue;
             }
-            if (c.status & WGB_STATUS_INDEX_OOB) fail(WGB_ERROR_OUT_OF_BOUNDS, "an index lies outside the bound index buffer or overflows with base_vertex (index.rs:45-62)");
-            if (c.status & WGB_STATUS_VERTEX_OOB) fail(WGB_ERROR_OUT_OF_BOUNDS, "a vertex attribute fetch lies outside its vertex buffer (vertex.rs:143-154)");
-            if (c.status & WGB_STATUS_W_ZERO) fail(WGB_ERROR_VALIDATION, "a clip position has w = 0 (the reference panics: raster.rs:146, primitive.rs:175-177)");
             dev->last_stats.primitives += np;
-            dev->last_stats.fragments += c.fragments;
-            dev->last_stats.shaded += c.shaded;
-            dev->last_stats.bin_pairs += c.num_small_pairs;
-            dev->last_stats.big_primitives += c.num_big;
-            dev->last_stats.clipped_primitives += c.num_slow;
-            dev->last_stats.clip_records += c.num_clip_records;
-            dev->last_stats.hiz_culled += c.hiz_culled;
             break;
         }
         // the clear has been applied by the first executed batch
@@ -988,13 +1052,103 @@ struct TraceRange {
 };
 
 void execute_pass_body(Device* dev, const PassCommand& pass);
-void execute_pass(Device* dev, const PassCommand& pass) {
+
+// may this pass be enqueued without waiting for its draws?  It has to be safe to run again from its start: every
+// attachment is cleared on load, so a second run starts from the same texels whatever the first one wrote.
+bool pass_can_run_async(const Device* dev, const PassCommand& pass) {
+    if (!dev->async_submit || dev->compile_only || dev->coverage_capture) return false;
+    if (pass.colors.empty() && !pass.has_depth) return false;
+    for (const auto& c : pass.colors) if (c.load_op != WGB_LOAD_OP_CLEAR) return false;
+    if (pass.has_depth && !(pass.has_depth_ops && pass.depth_load_op == WGB_LOAD_OP_CLEAR)) return false;
+    size_t draws = 0;
+    for (const SubCommand& sc : pass.sub) {
+        if (sc.kind == SubCommand::SetPipeline && sc.pipeline && sc.pipeline->strip_index_format != WGB_INDEX_FORMAT_NONE) return false;   // needs the strip map's count on the host
+        if (sc.kind == SubCommand::Draw || sc.kind == SubCommand::DrawIndexed) {
+            // (a draw of more than 2^26 primitives is split into batches; keep those synchronous)
+            if ((uint64_t)sc.count * std::max<uint32_t>(sc.instance_count, 1u) > (1ull << 26)) return false;
+            draws++;
+        }
+    }
+    return draws + 8 < Device::COUNTER_RING;
+}
+
+void execute_pass(Device* dev, const std::shared_ptr<PassCommand>& pass, bool allow_async);
+
+// Wait for the asynchronous passes and look at what they left behind (see Device::unsettled).
+void settle(Device* dev) {
+    if (dev->unsettled.empty() || dev->settling) return;
+    dev->settling = true;
+    struct Done { Device* d; ~Done() { d->settling = false; d->counter_ring_used = 0; d->event_pool_used = 0; } } done{dev};
+    CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+    std::deque<Device::Unsettled> work;
+    work.swap(dev->unsettled);
+    auto defer = [&](const Error& e) {
+        if (dev->deferred_status == WGB_OK) { dev->deferred_status = e.status; dev->deferred_error = e.what(); }
+    };
+    size_t i = 0;
+    bool overflow = false, error = false;
+    for (; i < work.size(); i++) {
+        Device::Unsettled& u = work[i];
+        if (!u.pass) continue;
+        try {
+            for (const auto& b : u.batches)
+                if (batch_result(dev, b, b.np, b.band_tiles, u.stats)) { overflow = true; break; }
+        } catch (const Error& e) { defer(e); error = true; }
+        if (overflow || error) break;
+        dev->last_stats = u.stats;
+    }
+    if (i == work.size()) return;
+    // Pass i failed; its tile kernel raised the poison word, so no later pass has touched an attachment.  Bring the
+    // small writes that were queued since the last settle back into their order, then run pass i (unless it failed
+    // with an error: then the rest of its submission is dropped, as when the error is raised synchronously) and
+    // everything behind it again, waiting for every draw.
+    CUDA_CHECK(cudaMemsetAsync(dev->poison.p, 0, 4, dev->stream));
+    auto rewrite = [&](const Device::Unsettled& u) {
+        CUDA_CHECK(cudaMemcpyAsync((char*)u.write_buffer->dptr + u.write_offset, u.write_data.data(), u.write_data.size(), cudaMemcpyHostToDevice, dev->stream));
+    };
+    for (size_t k = 0; k < i; k++) if (work[k].write_buffer) rewrite(work[k]);
+    size_t j = i;
+    uint64_t dropped = 0;
+    if (error) { dropped = work[i].submission; j = i + 1; }
+    for (; j < work.size(); j++) {
+        Device::Unsettled& u = work[j];
+        if (u.write_buffer) { rewrite(u); continue; }
+        if (u.submission == dropped) continue;
+        try {
+            execute_pass(dev, u.pass, false);
+            if (j == i) dev->last_stats.replays++;          // the attempt that overflowed
+        } catch (const Error& e) { defer(e); dropped = u.submission; }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+}
+
+void execute_pass(Device* dev, const std::shared_ptr<PassCommand>& pass_ptr, bool allow_async) {
+    const PassCommand& pass = *pass_ptr;
     TraceRange range("wgb::render_pass");
     const auto t0 = std::chrono::steady_clock::now();
+    const bool async = allow_async && !dev->settling && pass_can_run_async(dev, pass);
+    if (async) {
+        size_t draws = 0;
+        for (const SubCommand& sc : pass.sub) draws += (sc.kind == SubCommand::Draw || sc.kind == SubCommand::DrawIndexed) ? 1 : 0;
+        if (dev->counter_ring_used + draws + 8 > Device::COUNTER_RING) settle(dev);
+        if (!dev->counter_ring) CUDA_CHECK(cudaMallocHost((void**)&dev->counter_ring, sizeof(WgbCounters) * Device::COUNTER_RING));
+        if (!dev->poison.p) { dev->poison.ensure(4); CUDA_CHECK(cudaMemsetAsync(dev->poison.p, 0, 4, dev->stream)); }
+        dev->unsettled.emplace_back();
+        dev->unsettled.back().submission = dev->current_submission;
+        dev->unsettled.back().pass = pass_ptr;
+        dev->recording = &dev->unsettled.back();
+    } else if (!dev->settling) {
+        settle(dev);            // a pass that waits for its draws runs after everything queued before it has been looked at
+    }
+    struct Stop { Device* d; ~Stop() { if (d->recording) { d->recording->stats = d->last_stats; d->recording = nullptr; } } } stop{dev};
     execute_pass_body(dev, pass);
     if (log_level() >= 1) {
         const wgb_pass_stats& s = dev->last_stats;
         const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (async)
+            fprintf(stderr, "wgpu-b200 DEBUG render pass enqueued: %.3f ms on the host; draws=%u primitives_drawn=%llu launches=%u (counters at the next wait)\n",
+                    host_ms, s.draws, (unsigned long long)s.primitives, s.kernel_launches);
+        else
         fprintf(stderr, "wgpu-b200 DEBUG render pass time: %.3f ms on the device (geometry %.3f, tile %.3f), %.3f ms on the host; draws=%u "
                         "primitives_drawn=%llu fragments=%llu shaded=%llu bin_pairs=%llu big=%llu clipped=%llu hiz_culled=%llu launches=%u replays=%u\n",
                 s.total_ms, s.geometry_ms, s.tile_ms, host_ms, s.draws, (unsigned long long)s.primitives, (unsigned long long)s.fragments,
@@ -1121,13 +1275,18 @@ void execute_pass_body(Device* dev, const PassCommand& pass) {
         d.num_color = tg.num_color; d.has_depth = tg.has_depth;
         for (uint32_t c = 0; c < tg.num_color; c++) d.color[c] = tg.color[c];
         if (tg.has_depth) d.depth = tg.depth;
-        CUDA_CHECK(cudaEventRecord(dev->ev[0], dev->stream));
-        launch(dev, ks->clear, dim3(148 * 4), dim3(256), &d);
-        CUDA_CHECK(cudaEventRecord(dev->ev[2], dev->stream));
-        CUDA_CHECK(cudaStreamSynchronize(dev->stream));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, dev->ev[0], dev->ev[2]);
-        dev->last_stats.total_ms += ms;
+        if (dev->recording) {       // asynchronous pass: not waited for (and not timed)
+            d.poison = dev->poison.addr();
+            launch(dev, ks->clear, dim3(148 * 4), dim3(256), &d);
+        } else {
+            CUDA_CHECK(cudaEventRecord(dev->ev[0], dev->stream));
+            launch(dev, ks->clear, dim3(148 * 4), dim3(256), &d);
+            CUDA_CHECK(cudaEventRecord(dev->ev[2], dev->stream));
+            CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, dev->ev[0], dev->ev[2]);
+            dev->last_stats.total_ms += ms;
+        }
     }
 }
 
@@ -1326,6 +1485,7 @@ wgb_status wgb_adapter_request_device(wgb_adapter adapter, const wgb_device_desc
             CUDA_CHECK(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
             dev->no_direct_bins = getenv("WGB_NO_DIRECT_BINS") != nullptr;      // testing knob: always count / scan / fill
             dev->small_work_buffers = getenv("WGB_TEST_SMALL_WORK_BUFFERS") != nullptr;
+            dev->async_submit = getenv("WGB_SYNC_SUBMIT") == nullptr;                // WGB_SYNC_SUBMIT=1: every draw is waited for where it is issued
             for (auto& e2 : dev->ev) CUDA_CHECK(cudaEventCreate(&e2));
             for (auto& e2 : dev->timer_ev) CUDA_CHECK(cudaEventCreate(&e2));
             CUDA_CHECK(cudaMallocHost((void**)&dev->host_counters, sizeof(WgbCounters)));
@@ -1385,6 +1545,10 @@ wgb_status wgb_device_poll(wgb_device device, int32_t wait, uint64_t submission_
                     }
                 }
             }
+            // what the asynchronous passes left behind: looked at once nothing of them is in flight any more (a failed
+            // pass is re-run here, an error it raised is reported below -- where the reference's engine-thread panic
+            // would surface, device.rs:498-503)
+            if (dev->inflight.empty()) settle(dev);
         } else if (wait) result = WGB_POLL_QUEUE_EMPTY;
         if (out_poll) *out_poll = result;
         if (dev->deferred_status != WGB_OK) {
@@ -1433,6 +1597,7 @@ wgb_status wgb_buffer_map_async(wgb_buffer buffer, uint32_t mode, uint64_t offse
         if (!dev->compile_only) {
             std::lock_guard<std::recursive_mutex> dl(dev->mu);
             dev->make_current();
+        settle(dev);
             b->acquire_on(dev->stream);
             CUDA_CHECK(cudaStreamSynchronize(dev->stream));
             // both modes start from the buffer's contents (a write guard derefs to the live Vec<u8>)
@@ -1463,6 +1628,7 @@ wgb_status wgb_buffer_unmap(wgb_buffer buffer) {
         if (b->map_mode == WGB_MAP_MODE_WRITE && b->size && !dev->compile_only) {
             std::lock_guard<std::recursive_mutex> dl(dev->mu);
             dev->make_current();
+        settle(dev);
             b->acquire_on(dev->stream);
             CUDA_CHECK(cudaMemcpyAsync(b->dptr, b->staging.data(), b->size, cudaMemcpyHostToDevice, dev->stream));
             CUDA_CHECK(cudaStreamSynchronize(dev->stream));
@@ -1482,6 +1648,18 @@ static void write_buffer_impl(wgb_queue queue, wgb_buffer buffer, uint64_t offse
     if (dev->compile_only || size == 0) return;
     std::lock_guard<std::recursive_mutex> dl(dev->mu);
     dev->make_current();
+    if (!dev->unsettled.empty()) {
+        // passes are in flight that may have to run again (Device::unsettled): a small write is remembered so that the
+        // re-run sees the buffer as it was at that point of the queue; a large one waits for them if they use the buffer
+        if (size <= (64u << 10)) {
+            dev->unsettled.emplace_back();
+            Device::Unsettled& u = dev->unsettled.back();
+            u.write_buffer = b;
+            u.write_ref = std::make_shared<Ref<Buffer>>(b);
+            u.write_offset = offset;
+            u.write_data.assign((const uint8_t*)data, (const uint8_t*)data + size);
+        } else if (b->last_use_submission != 0) settle(dev);
+    }
     cudaPointerAttributes attr;
     const bool pinned = cudaPointerGetAttributes(&attr, data) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
@@ -1580,6 +1758,7 @@ wgb_status wgb_queue_write_texture(wgb_queue queue, wgb_texture texture, uint32_
         if (dev->compile_only || width == 0 || height == 0) return;
         std::lock_guard<std::recursive_mutex> dl(dev->mu);
         dev->make_current();
+        settle(dev);
         char* dst = (char*)t->dptr + ((uint64_t)y * t->desc.width + x) * t->bpp;
         CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)t->desc.width * t->bpp, data, pitch, row, height, cudaMemcpyHostToDevice, dev->stream));
         CUDA_CHECK(cudaStreamSynchronize(dev->stream));
@@ -1593,6 +1772,7 @@ wgb_status wgb_texture_read(wgb_texture texture, void* dst, uint64_t dst_size) {
         if (dev->compile_only) fail(WGB_ERROR_DEVICE, "a compile-only device has no texture storage");
         std::lock_guard<std::recursive_mutex> dl(dev->mu);
         dev->make_current();
+        settle(dev);
         CUDA_CHECK(cudaMemcpyAsync(dst, t->dptr, t->size, cudaMemcpyDeviceToHost, dev->stream));
         CUDA_CHECK(cudaStreamSynchronize(dev->stream));
     });
@@ -1611,6 +1791,7 @@ wgb_status wgb_texture_dump_png(wgb_texture texture, const char* path) {
         {
             std::lock_guard<std::recursive_mutex> dl(dev->mu);
             dev->make_current();
+            settle(dev);
             CUDA_CHECK(cudaMemcpyAsync(texels.data(), t->dptr, texels.size(), cudaMemcpyDeviceToHost, dev->stream));
             CUDA_CHECK(cudaStreamSynchronize(dev->stream));
         }
@@ -2038,6 +2219,7 @@ wgb_status wgb_queue_submit(wgb_queue queue, const wgb_command_buffer* command_b
         dev->make_current();
         const uint64_t index = dev->next_submission++;                                  // device.rs:443-444
         if (out_submission_index) *out_submission_index = index;
+        dev->current_submission = index;
         wgb_status st = WGB_OK;
         std::string msg;
         for (uint32_t i = 0; i < count && st == WGB_OK; i++) {
@@ -2064,7 +2246,7 @@ wgb_status wgb_queue_submit(wgb_queue queue, const wgb_command_buffer* command_b
             // once the pass is recorded) and are cleared below, before this scope ends: keep the buffers alive until the
             // end-of-scope bookkeeping has run
             std::vector<Ref<Buffer>> keep_alive(used.begin(), used.end());
-            for (Buffer* b : used) b->acquire_on(dev->stream);
+            for (Buffer* b : used) { b->acquire_on(dev->stream); b->last_use_submission = index; }
             struct MarkUsed {
                 std::vector<Buffer*>& v; cudaStream_t s;
                 ~MarkUsed() { for (Buffer* b : v) b->mark_used(s); }
@@ -2072,7 +2254,10 @@ wgb_status wgb_queue_submit(wgb_queue queue, const wgb_command_buffer* command_b
             for (const auto& cmd : cb->passes) {
                 // errors raised while a submission executes surface at poll, where the reference's
                 // engine-thread panic would be observed (device.rs:498-503)
-                try { if (cmd.pass) execute_pass(dev, *cmd.pass); else execute_copy(dev, *cmd.copy); }
+                try {
+                    if (cmd.pass) execute_pass(dev, cmd.pass, true);
+                    else { settle(dev); execute_copy(dev, *cmd.copy); }
+                }
                 catch (const Error& e) { st = e.status; msg = e.what(); break; }
             }
             cb->passes.clear();
@@ -2091,6 +2276,7 @@ wgb_status wgb_device_get_last_pass_stats(wgb_device device, wgb_pass_stats* out
         Device* dev = from_handle<Device>(device, "device");
         REQUIRE(out, "out is null");
         std::lock_guard<std::recursive_mutex> lk(dev->mu);
+        if (!dev->compile_only) { dev->make_current(); settle(dev); }
         *out = dev->last_stats;
     });
 }
@@ -2098,6 +2284,7 @@ wgb_status wgb_device_set_coverage_capture(wgb_device device, int32_t enabled) {
     return guarded([&] {
         Device* dev = from_handle<Device>(device, "device");
         std::lock_guard<std::recursive_mutex> lk(dev->mu);
+        if (!dev->compile_only) { dev->make_current(); settle(dev); }
         dev->coverage_capture = enabled != 0;
         dev->coverage_w = dev->coverage_h = 0;
     });
@@ -2110,6 +2297,7 @@ wgb_status wgb_device_read_coverage(wgb_device device, uint32_t* dst, uint64_t p
         REQUIRE(dev->coverage_capture && dev->coverage.p, "coverage capture is not enabled or no pass has run");
         REQUIRE(pixel_count == (uint64_t)dev->coverage_w * dev->coverage_h, "pixel_count does not match the last pass (%ux%u)", dev->coverage_w, dev->coverage_h);
         dev->make_current();
+        settle(dev);
         CUDA_CHECK(cudaMemcpyAsync(dst, dev->coverage.p, pixel_count * 4, cudaMemcpyDeviceToHost, dev->stream));
         CUDA_CHECK(cudaStreamSynchronize(dev->stream));
     });
@@ -2120,6 +2308,7 @@ wgb_status wgb_device_set_band(wgb_device device, uint32_t band_rank, uint32_t b
         std::lock_guard<std::recursive_mutex> lk(dev->mu);
         if (band_count == 0) band_count = 1;
         REQUIRE(band_rank < band_count, "band_rank %u >= band_count %u", band_rank, band_count);
+        if (!dev->compile_only) { dev->make_current(); settle(dev); }
         dev->band_rank = band_rank; dev->band_count = band_count;
     });
 }

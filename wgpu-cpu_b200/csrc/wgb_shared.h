@@ -165,4 +165,5 @@ struct WgbDraw {
     wgb_u64 tile_cursor;                 // u32 per tile
     wgb_u64 bins;                        // u32 entries
     wgb_u64 coverage;                    // optional u32 per pixel (stats)
+    wgb_u64 poison;                      // asynchronous submissions: u32 the tile kernels raise / obey (0 = synchronous execution)
 };
