@@ -26,7 +26,7 @@ class SceneRenderer:
     """Holds the device-resident resources of one scene so that frames can be re-submitted."""
 
     def __init__(self, device: api.Device, queue: api.Queue, scene: Scene, use_emitted: bool = False,
-                 target: Optional[api.Texture] = None, targets: Optional[list] = None):
+                 target: Optional[api.Texture] = None, targets: Optional[list] = None, wgsl: Optional[str] = None):
         """`target`: render into this texture instead of creating one (e.g. the presenter's colour target
         imported over CUDA IPC, so that the tile kernel stores its band straight into peer memory).
         `targets`: several colour targets to alternate between (`encode(which)`): consecutive frames of a multi-GPU run
@@ -37,6 +37,8 @@ class SceneRenderer:
             module = device.create_shader_module(None, [
                 (api.STAGE_VERTEX, "vs_main", shaders.emitted(s.shader, "vs")),
                 (api.STAGE_FRAGMENT, "fs_main", shaders.emitted(s.shader, "fs"))])
+        elif wgsl is not None:          # the application's own WGSL text instead of this repository's text for the scene's program
+            module = device.create_shader_module(wgsl)
         else:
             module = device.create_shader_module(shaders.wgsl(s.shader))
         self.module = module
@@ -155,9 +157,9 @@ class SceneRenderer:
 
 
 def render_scene(device: api.Device, queue: api.Queue, scene: Scene, want_coverage: bool = True,
-                 use_emitted: bool = False) -> Frame:
+                 use_emitted: bool = False, wgsl: Optional[str] = None) -> Frame:
     device.set_coverage_capture(want_coverage)
-    r = SceneRenderer(device, queue, scene, use_emitted=use_emitted)
+    r = SceneRenderer(device, queue, scene, use_emitted=use_emitted, wgsl=wgsl)
     r.render()
     f = r.read(want_coverage)
     device.set_coverage_capture(False)
