@@ -435,6 +435,24 @@ static inline void wgb_mbar_wait(unsigned long long* mbar, unsigned parity) {
     me->state = CUSIM_RUN;
 }
 static inline void wgb_fence_proxy_async() {}
+// tensor-map copies (see cusim_cuTensorMapEncodeTiled for the words): a store skips the texels of the box that lie
+// outside the tensor, a load fills them with zeros and completes the full box's bytes on the mbarrier
+struct WgbTensorMap;
+static inline void wgb_tensor_store_tile(const WgbTensorMap* map, unsigned x, unsigned y, const void* smem_src) {
+    const unsigned long long* w = (const unsigned long long*)map;
+    const unsigned bw = (unsigned)w[4], bh = (unsigned)w[5];
+    for (unsigned r = 0; r < bh; r++)
+        for (unsigned c = 0; c < bw; c++)
+            if (x + c < w[1] && y + r < w[2]) *(unsigned*)(uintptr_t)(w[0] + (unsigned long long)(y + r) * w[3] + (x + c) * 4ull) = ((const unsigned*)smem_src)[r * bw + c];
+}
+static inline void wgb_tensor_load_tile(void* smem_dst, const WgbTensorMap* map, unsigned x, unsigned y, unsigned long long* mbar) {
+    const unsigned long long* w = (const unsigned long long*)map;
+    const unsigned bw = (unsigned)w[4], bh = (unsigned)w[5];
+    for (unsigned r = 0; r < bh; r++)
+        for (unsigned c = 0; c < bw; c++)
+            ((unsigned*)smem_dst)[r * bw + c] = (x + c < w[1] && y + r < w[2]) ? *(const unsigned*)(uintptr_t)(w[0] + (unsigned long long)(y + r) * w[3] + (x + c) * 4ull) : 0u;
+    CusimMbar* m = (CusimMbar*)mbar; m->tx -= (int)(bw * bh * 4u); cusim_mbar_check(m);
+}
 
 // MUFU.RCP (rcp.approx.ftz.f32, at most 1 ulp off) is modelled by the correctly rounded reciprocal
 #define WGB_RCP_APPROX_PROVIDED 1

@@ -207,6 +207,17 @@ CUresult cusim_cuGetErrorString(CUresult r, const char** s) {
     *s = r == CUDA_SUCCESS ? "no error" : r == CUDA_ERROR_NOT_FOUND ? "named symbol not found" : r == CUDA_ERROR_INVALID_VALUE ? "invalid value" : "unknown driver error";
     return CUDA_SUCCESS;
 }
+// the alignment and extent rules of the real call (a map the hardware would reject must not pass here either)
+CUresult cusim_cuTensorMapEncodeTiled(CUtensorMap* out, CUtensorMapDataType type, cuuint32_t rank, void* base, const cuuint64_t* dims, const cuuint64_t* strides,
+                                      const cuuint32_t* box, const cuuint32_t* elem, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+    if (!out || type != CU_TENSOR_MAP_DATA_TYPE_UINT32 || rank != 2 || !base || ((uintptr_t)base & 15u) || (strides[0] & 15u) || !dims[0] || !dims[1] ||
+        box[0] == 0 || box[0] > 256 || box[1] == 0 || box[1] > 256 || (box[0] * 4u) % 16u || elem[0] != 1 || elem[1] != 1 || strides[0] < dims[0] * 4)
+        return CUDA_ERROR_INVALID_VALUE;
+    memset(out, 0, sizeof *out);
+    out->opaque[0] = (cuuint64_t)(uintptr_t)base; out->opaque[1] = dims[0]; out->opaque[2] = dims[1]; out->opaque[3] = strides[0];
+    out->opaque[4] = box[0]; out->opaque[5] = box[1];
+    return CUDA_SUCCESS;
+}
 cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q) {
     *fn = nullptr;
     if (!strcmp(name, "cuModuleLoadData")) *fn = (void*)&cusim_cuModuleLoadData;
@@ -214,6 +225,7 @@ cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long l
     else if (!strcmp(name, "cuModuleGetFunction")) *fn = (void*)&cusim_cuModuleGetFunction;
     else if (!strcmp(name, "cuLaunchKernel")) *fn = (void*)&cusim_cuLaunchKernel;
     else if (!strcmp(name, "cuGetErrorString")) *fn = (void*)&cusim_cuGetErrorString;
+    else if (!strcmp(name, "cuTensorMapEncodeTiled")) *fn = (void*)&cusim_cuTensorMapEncodeTiled;
     if (q) *q = *fn ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
     return cudaSuccess;
 }

@@ -147,6 +147,23 @@ def test_load_op_load(gpu):
     _compare(s, gpu)
 
 
+@pytest.mark.parametrize("size", [(200, 100), (36, 36), (4, 4), (64, 33), (132, 64)])
+@pytest.mark.parametrize("load", [False, True])
+def test_tensor_map_tiles_on_the_edges(gpu, size, load):
+    """Widths that are a multiple of four texels take the tensor-map path of the write-back (one cp.async.bulk.tensor.2d
+    per tile and attachment): tiles cut by the right and bottom edges store only the texels inside the attachment, and
+    with LoadOp::Load the texels of the box outside it arrive as zeros without disturbing the byte count the mbarrier
+    waits for."""
+    rng = np.random.default_rng(size[0] * 1000 + size[1])
+    kw = dict(clear_color=None, clear_depth=None) if load else {}
+    s = S.random_triangles(size[0], size[1], count=60, seed=5 + size[0], **kw)
+    if load:
+        s.initial_color = rng.integers(0, 255, (s.height, s.width, 4), dtype=np.uint8)
+        s.initial_depth = rng.random((s.height, s.width), dtype=np.float32)
+    s.name += f"_tmap_{int(load)}"
+    _compare(s, gpu)
+
+
 @pytest.mark.parametrize("scene_name", ["hello_mesh", "synthetic_clipped", "random_clipped"])
 @pytest.mark.parametrize("bands", [2, 3, 8])
 def test_sort_first_bands_reassemble_the_single_gpu_frame(gpu, bands, scene_name):

@@ -15,7 +15,11 @@ if [ -n "$tests" ]; then
 fi
 n=0
 for v in "" "$@"; do
-    WGB_TUNE="$v" python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ab_${n}.json 2>> gpurun_out/${tag}_ab.err
+    if [ "${v#ENV }" != "$v" ]; then      # "ENV NAME=value": an environment variable instead of a kernel #define
+        env "${v#ENV }" python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ab_${n}.json 2>> gpurun_out/${tag}_ab.err
+    else
+        WGB_TUNE="$v" python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/${tag}_ab_${n}.json 2>> gpurun_out/${tag}_ab.err
+    fi
     python - "$v" gpurun_out/${tag}_ab_${n}.json <<'PY'
 import json, sys
 try:

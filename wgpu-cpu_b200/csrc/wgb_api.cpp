@@ -129,6 +129,9 @@ struct DriverApi {
     CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    // optional (CUDA 12): tensor maps for the tile kernel's one-copy tile loads / stores
+    CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
     bool loaded = false;
 };
 DriverApi g_drv;
@@ -148,6 +151,14 @@ void load_driver_api() {
     get("cuModuleGetFunction", (void**)&g_drv.ModuleGetFunction);
     get("cuLaunchKernel", (void**)&g_drv.LaunchKernel);
     get("cuGetErrorString", (void**)&g_drv.GetErrorString);
+    {
+        cudaDriverEntryPointQueryResult q;
+        void* fn = nullptr;
+        if (!getenv("WGB_NO_TENSOR_MAP") && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess && fn)
+            g_drv.TensorMapEncodeTiled = (decltype(g_drv.TensorMapEncodeTiled))fn;
+        cudaGetLastError();
+    }
     g_drv.loaded = true;
 }
 const char* cu_error(CUresult r) {
@@ -737,7 +748,24 @@ struct PassTargets {
     WgbAttachment color[WGB_MAX_COLOR];
     bool has_depth = false;
     WgbAttachment depth;
+    // tensor maps over colour attachment 0 and the depth attachment (encoded once per pass)
+    bool tmap_color = false, tmap_depth = false;
+    WgbTensorMap map_color, map_depth;
 };
+
+// The attachment (linear, W x H texels of 4 bytes, texture.rs:250-302) as a 2-D tensor map with a tile-sized box.  TMA
+// wants a 16-byte aligned base and row pitch; attachments that do not qualify keep the row-by-row bulk copies.
+bool encode_attachment_map(const WgbAttachment& a, uint32_t width, uint32_t height, WgbTensorMap& out) {
+    static_assert(sizeof(WgbTensorMap) == sizeof(CUtensorMap), "WgbTensorMap mirrors CUtensorMap");
+    if (!g_drv.TensorMapEncodeTiled || a.bytes_per_texel != 4 || (a.ptr & 15ull) || (((uint64_t)width * 4) & 15ull) || !width || !height) return false;
+    const cuuint64_t dims[2] = {width, height};
+    const cuuint64_t strides[1] = {(cuuint64_t)width * 4};
+    const cuuint32_t box[2] = {WGB_TILE_W, WGB_TILE_H};
+    const cuuint32_t elem[2] = {1, 1};
+    return g_drv.TensorMapEncodeTiled(reinterpret_cast<CUtensorMap*>(&out), CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)(uintptr_t)a.ptr, dims, strides, box, elem,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // What a draw batch left behind, once its kernels have completed: timings, the capacity the fullest tile needed, counters.
 // Returns true if a work buffer overflowed (the capacities have been raised: the batch has to run again); raises the
@@ -897,6 +925,8 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
         if (dev->features & WGB_FEATURE_COLOR_WRITE_MASK) d.color[c].write_mask = texel_write_mask(pipe->targets[c].write_mask, tg.color[c].format);
     }
     if (tg.has_depth) d.depth = tg.depth;
+    if (tg.tmap_color) { d.tmap_color = 1u; d.map_color = tg.map_color; }
+    if (tg.tmap_depth) { d.tmap_depth = 1u; d.map_depth = tg.map_depth; }
     memcpy(d.blend_constant, st.blend_constant, sizeof(d.blend_constant));
     if (dev->features & WGB_FEATURE_VIEWPORT_DEPTH_RANGE) {
         d.depth_range = 1u; d.depth_min = st.vp[4]; d.depth_scale = st.vp[5] - st.vp[4];
@@ -1193,6 +1223,10 @@ void execute_pass_body(Device* dev, const PassCommand& pass) {
         tg.depth.load_clear = (pass.has_depth_ops && pass.depth_load_op == WGB_LOAD_OP_CLEAR) ? 1u : 0u;
         memcpy(&tg.depth.clear_texel, &pass.depth_clear, 4);
     }
+    // (a target mapped from another process keeps the row copies: peer memory is written with plain bulk stores)
+    if (!dev->compile_only && tg.num_color >= 1 && !pass.colors[0].view->texture->imported)
+        tg.tmap_color = encode_attachment_map(tg.color[0], tg.width, tg.height, tg.map_color);
+    if (!dev->compile_only && tg.has_depth) tg.tmap_depth = encode_attachment_map(tg.depth, tg.width, tg.height, tg.map_depth);
     PassState st;
     // default viewport / scissor: the whole framebuffer (state.rs:604-628)
     st.vp[0] = 0; st.vp[1] = 0; st.vp[2] = (float)tg.width; st.vp[3] = (float)tg.height; st.vp[4] = 0; st.vp[5] = 1;

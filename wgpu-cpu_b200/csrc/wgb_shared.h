@@ -110,6 +110,10 @@ struct WgbBigEntry {            // 16 bytes
 // bin entry encoding: bit 31 = 1 -> clip record index in the low bits, 0 -> primitive sequence number
 #define WGB_ENTRY_CLIP 0x80000000u
 
+// a CUtensorMap (128 bytes, 64-byte aligned), encoded by the host with cuTensorMapEncodeTiled: the attachment as a
+// 2-D tensor of 4-byte texels with a 32 x 32 box, for one-instruction tile loads / stores (cp.async.bulk.tensor.2d)
+struct alignas(64) WgbTensorMap { wgb_u64 opaque[16]; };
+
 // parameters of one draw batch; passed by value as a __grid_constant__ kernel argument
 struct WgbDraw {
     // framebuffer
@@ -166,4 +170,6 @@ struct WgbDraw {
     wgb_u64 bins;                        // u32 entries
     wgb_u64 coverage;                    // optional u32 per pixel (stats)
     wgb_u64 poison;                      // asynchronous submissions: u32 the tile kernels raise / obey (0 = synchronous execution)
+    wgb_u32 tmap_color, tmap_depth;      // 1: map_color / map_depth describe colour attachment 0 / the depth attachment
+    WgbTensorMap map_color, map_depth;
 };
