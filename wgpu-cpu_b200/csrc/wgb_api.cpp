@@ -979,7 +979,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             if (!vcache_n) dev->setup_cache.ensure((size_t)np * 48);
             if (vcache_n) {
                 const size_t nv = (size_t)vcache_n * sc.instance_count;
-                dev->vcache_raster.ensure(nv * 16); dev->vcache_ndc.ensure(nv * 8); dev->vcache_flags.ensure(nv * 4);
+                dev->vcache_raster.ensure(nv * 16); dev->vcache_ndc.ensure(nv * 8); dev->vcache_flags.ensure(nv);
                 d.vcache_raster = dev->vcache_raster.addr(); d.vcache_ndc = dev->vcache_ndc.addr(); d.vcache_flags = dev->vcache_flags.addr();
                 d.vcache_count = (uint32_t)vcache_n;
             }

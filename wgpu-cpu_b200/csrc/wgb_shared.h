@@ -87,10 +87,16 @@ struct WgbCounters {             // 64 bytes
 #define WGB_STATUS_BIG_OVERFLOW 16u
 #define WGB_STATUS_BIN_OVERFLOW 32u    // direct binning: a tile received more than bin_cap entries
 
+// post-transform vertex flags: ONE BYTE per vertex (the geometry stage gathers three of them per primitive -- of every
+// primitive, on every rank of a sort-first partition -- so the table is kept small enough to stay in L1 / L2: 5 MB at C3)
 #define WGB_VFLAG_INSIDE 1u              // inside all six clip planes
 #define WGB_VFLAG_W_ZERO 2u              // clip.w == 0 (the reference panics when such a vertex is used)
-#define WGB_VFLAG_ROW_SHIFT 2            // bits 2..17: the vertex's framebuffer row, min(trunc(vp.y), 65535)
-#define WGB_VFLAG_W_POS (1u << 18)       // clip.w > 0: clipping keeps the primitive inside the row range of its vertices
+#define WGB_VFLAG_W_POS 4u               // clip.w > 0: clipping keeps the primitive inside the row range of its vertices
+#define WGB_VFLAG_ROW_OK 8u              // the framebuffer row trunc(vp.y) is below 65535; the four bits below are valid
+#define WGB_VFLAG_ABOVE 16u              // row < first row of the draw's window (scissor, framebuffer, this rank's band)
+#define WGB_VFLAG_BELOW 32u              // row >= one past the window's last row
+#define WGB_VFLAG_ABOVE1 64u             // row + 1 < first row   (one row of slack: clipped primitives)
+#define WGB_VFLAG_BELOW1 128u            // row >= one past the last row + 1
 
 // one record per primitive emitted by the clipper (slow path only)
 struct WgbClipRecord {          // 100 bytes
@@ -154,7 +160,7 @@ struct WgbDraw {
     // post-transform vertex cache (indexed draws): the vertex stage runs once per (instance, vertex) instead of once per index
     wgb_u64 vcache_raster;               // float4 per vertex: (vp.x, vp.y, ndc.z, 1/w)
     wgb_u64 vcache_ndc;                  // float2 per vertex: ndc.xy (winding)
-    wgb_u64 vcache_flags;                // u32 per vertex: WGB_VFLAG_*
+    wgb_u64 vcache_flags;                // u8 per vertex: WGB_VFLAG_*
     wgb_u32 vcache_count;                // vertices per instance in the cache (0 = cache not in use)
     wgb_u32 pad2;
     wgb_u64 slow_list;                   // u32 per slow primitive
