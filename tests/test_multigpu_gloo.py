@@ -80,3 +80,39 @@ def test_host_barrier_world_size_2(tmp_path):
     mp.spawn(_barrier_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     log = np.load(out)
     assert (log >= np.arange(50)).all()
+
+
+def _bench_dry_run(tmp_path, world, extra):
+    """bench.py itself on the software model of tests/cusim (WGB_CUSIM=1: gloo instead of NCCL, "device" memory is host
+    memory, the presenter's targets shared through a memfd): frame numbering, the presenter exchange with alternating
+    targets, the sharded upload + all-gather of the e2e leg and the oracle digest of the assembled frame."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, WGB_CUSIM="1", CUSIM_THREADS="2", CUSIM_CACHE=str(tmp_path / "cache"))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), "bench.py", "--gpus", str(world), "--config", "c1", "--steps", "2", "--warmup", "1",
+           "--no-cpu-baseline"] + extra
+    p = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, "rank 0 prints one JSON line"
+    return json.loads(lines[0])
+
+
+def test_bench_dry_run_two_ranks_peer_presenter(tmp_path):
+    d = _bench_dry_run(tmp_path, 2, [])
+    assert d["n_gpus"] == 2 and d["data"] == "software model dry run"
+    assert d["parity"]["matches_oracle"] is True
+    # every rank uploads half of the vertex and index bytes (+ the 16-byte tail and the uniforms): the scene once, not twice
+    from wgpu_cpu_b200 import scenes as S
+    sc = S.hello_mesh(512, 512)
+    scene_bytes = sum(v.nbytes for v in sc.vertex_buffers) + sc.index_data.nbytes
+    assert scene_bytes <= d["e2e"]["h2d_bytes_per_step"] <= scene_bytes + 2 * 64 + 64
+    assert d["e2e"]["d2h_bytes_per_step"] == 512 * 512 * 4
+
+
+def test_bench_dry_run_two_ranks_nccl_presenter(tmp_path):
+    d = _bench_dry_run(tmp_path, 2, ["--present", "nccl", "--no-e2e"])
+    assert d["parity"]["matches_oracle"] is True and "send/recv" in d["config"]["parallelism"]
