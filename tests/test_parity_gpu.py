@@ -147,6 +147,22 @@ def test_load_op_load(gpu):
     _compare(s, gpu)
 
 
+def test_every_texel_value_decodes_as_the_division_does(gpu):
+    """u8 as f32 / 255.0 (texture.rs:170-188) is computed without a division on the device (wgb_unorm8); a texture of
+    random bytes -- every value in every channel -- sampled all over the bunny must give the oracle's bytes: the target's
+    truncating encode turns a last-bit difference of the quotient into a different byte."""
+    rng = np.random.default_rng(255)
+    s = S.hello_texture(320, 180)
+    s.bindings = dict(s.bindings)
+    for key, res in list(s.bindings.items()):
+        if res[0] == "texture":
+            img = rng.integers(0, 256, res[1].shape, dtype=np.uint8)
+            img.reshape(-1)[:1024] = np.repeat(np.arange(256, dtype=np.uint8), 4)
+            s.bindings[key] = ("texture", img) + tuple(res[2:])
+    s.name += "_random_texels"
+    _compare(s, gpu)
+
+
 @pytest.mark.parametrize("size", [(200, 100), (36, 36), (4, 4), (64, 33), (132, 64)])
 @pytest.mark.parametrize("load", [False, True])
 def test_tensor_map_tiles_on_the_edges(gpu, size, load):

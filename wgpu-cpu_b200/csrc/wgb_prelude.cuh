@@ -470,7 +470,13 @@ template <> WGB_DEV mat4x4f wgb_load<mat4x4f>(const WgbDraw& d, int g, int b, u3
 
 // f32::rem_euclid (Rust std): r = fmod(x, rhs); r < 0 ? r + |rhs| : r
 WGB_DEV f32 wgb_rem_euclid(f32 x, f32 rhs) {
-    const f32 r = fmodf(x, rhs);
+    f32 r;
+    if (rhs == 1.0f) {
+        // fmod(x, 1) = x - trunc(x): both sides are exact (the difference of x and its integer part is representable),
+        // a zero result takes the sign of x as fmod's does, infinities give NaN either way
+        r = __fsub_rn(x, truncf(x));
+        if (r == 0.0f) r = copysignf(0.0f, x);
+    } else r = fmodf(x, rhs);
     return r < 0.0f ? __fadd_rn(r, fabsf(rhs)) : r;
 }
 // Rust `as u32` on f32: saturating, NaN -> 0 (== cvt.rzi.u32.f32)
@@ -491,6 +497,14 @@ WGB_DEV u32 wgb_texel_coordinate(f32 x, u32 address_mode, u32 size) {
     return wgb_f32_as_u32(roundf(__fmul_rn(x, __uint2float_rn(size - 1u))));
 }
 
+// u8 as f32 / 255.0 (texture.rs:170-188), correctly rounded: the quotient from the rounded reciprocal of 255 and one
+// residual correction -- the fast path a compiler emits for div.rn.f32, without its range check, which 0..255 over 255
+// cannot fail (tests/test_parity_gpu.py::test_every_texel_value_decodes_as_the_division_does)
+WGB_DEV f32 wgb_unorm8(u32 v) {
+    const f32 a = __uint2float_rn(v), r = 0.003921568859368563f;      // RN(1 / 255) = 0x3B808081
+    const f32 q = __fmaf_rn(a, r, 0.0f);
+    return __fmaf_rn(__fmaf_rn(-255.0f, q, a), r, q);
+}
 // textureSample: nearest, mip 0, 2-D (binding.rs:93-149), texel decode u8 as f32 / 255.0
 // without sRGB decode (texture.rs:170-188).  The texel is fetched through the bindless
 // texture object by integer element index, so the hardware never rounds or filters.
@@ -500,8 +514,7 @@ WGB_DEV vec4f wgb_texture_sample(const WgbDraw& d, int tg, int tb, int sg, int s
     const u32 tx = wgb_texel_coordinate(uv.x, s.a, t.a);
     const u32 ty = wgb_texel_coordinate(uv.y, s.b, t.b);
     const uchar4 p = tex1Dfetch<uchar4>((cudaTextureObject_t)t.tex, (int)(ty * t.a + tx));
-    return vec4f(__fdiv_rn((f32)p.x, 255.0f), __fdiv_rn((f32)p.y, 255.0f), __fdiv_rn((f32)p.z, 255.0f),
-                 __fdiv_rn((f32)p.w, 255.0f));
+    return vec4f(wgb_unorm8(p.x), wgb_unorm8(p.y), wgb_unorm8(p.z), wgb_unorm8(p.w));
 }
 
 WGB_DEV vec2u wgb_texture_dimensions(const WgbDraw& d, int tg, int tb) { return vec2u(d.res[tg][tb].a, d.res[tg][tb].b); }
