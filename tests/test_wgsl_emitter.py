@@ -97,6 +97,19 @@ def test_unsupported_wgsl_is_rejected_with_a_message(src, fragment):
     assert fragment in str(e.value)
 
 
+def test_f16_is_reported_as_unsupported_not_as_a_broken_shader():
+    """f16 exists in the reference's type table (naga-cranelift/src/types.rs:103-136) but none of its tests or examples
+    uses it; this backend says so with WGB_ERROR_UNSUPPORTED (2) -- for the type, for a literal and for the enable
+    directive's consequences -- while a genuinely malformed shader is WGB_ERROR_SHADER (5)."""
+    for body in ("return vec4f(f16(1.0));", "let h = 1.0h; return vec4f(1.0);", "var v: vec2<f16>; return vec4f(1.0);"):
+        with pytest.raises(api.WgpuError) as e:
+            api.translate_wgsl(_fs(body), api.STAGE_FRAGMENT, "fs_main")
+        assert e.value.status == 2 and "f16" in str(e.value), str(e.value)
+    with pytest.raises(api.WgpuError) as e:
+        api.translate_wgsl(_fs("return vec4f(q);"), api.STAGE_FRAGMENT, "fs_main")
+    assert e.value.status == 5
+
+
 def test_array_length_translates():
     """Expression::ArrayLength (SURVEY 2.3; tests.rs:997-1103): (bound size - array offset) / element stride."""
     from wgpu_cpu_b200 import api

@@ -68,6 +68,22 @@ struct Error : std::runtime_error {
                                     "%s failed: %s", #expr, cudaGetErrorString(e_));                  \
     } while (0)
 
+// The emitter reports problems as std::runtime_error("WGSL:<line>: ...").  What WGSL allows and this backend (like the
+// reference's JIT for most of it) does not run -- f16, overrides, workgroup variables, texture offsets, ... -- is
+// WGB_ERROR_UNSUPPORTED; anything else is a shader error.
+std::string emit_wgsl(const std::string& wgsl, uint32_t stage, const std::string& entry_point) {
+    try {
+        return wgb_emit_wgsl(wgsl, stage, entry_point);
+    } catch (const Error&) {
+        throw;
+    } catch (const std::runtime_error& e) {
+        const std::string m = e.what();
+        const bool unsupported = m.find("not supported") != std::string::npos || m.find("unsupported") != std::string::npos ||
+                                 m.find("only ") != std::string::npos;
+        throw Error(unsupported ? WGB_ERROR_UNSUPPORTED : WGB_ERROR_SHADER, m);
+    }
+}
+
 template <class F>
 wgb_status guarded(F f) {
     try {
@@ -482,7 +498,7 @@ struct ShaderModule : Object {
         for (const auto& e : emitted)
             if (e.stage == stage && e.entry == entry) return e.cuda;
         if (wgsl.empty()) fail(WGB_ERROR_SHADER, "shader module has neither WGSL nor emitted CUDA for entry point '%s'", entry.c_str());
-        return wgb_emit_wgsl(wgsl, stage, entry);
+        return emit_wgsl(wgsl, stage, entry);
     }
 };
 struct BindGroupLayout : Object { std::vector<wgb_bind_group_layout_entry> entries; };
@@ -1927,7 +1943,7 @@ wgb_status wgb_device_create_shader_module(wgb_device device, const wgb_shader_m
 wgb_status wgb_translate_wgsl(const char* wgsl, uint32_t stage, const char* entry_point, char** out_cuda) {
     return guarded([&] {
         REQUIRE(wgsl && entry_point && out_cuda, "null argument");
-        const std::string s = wgb_emit_wgsl(wgsl, stage, entry_point);
+        const std::string s = emit_wgsl(wgsl, stage, entry_point);
         *out_cuda = (char*)malloc(s.size() + 1);
         if (!*out_cuda) throw std::bad_alloc();
         memcpy(*out_cuda, s.c_str(), s.size() + 1);
