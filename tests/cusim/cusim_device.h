@@ -454,6 +454,11 @@ static inline void wgb_tensor_load_tile(void* smem_dst, const WgbTensorMap* map,
     CusimMbar* m = (CusimMbar*)mbar; m->tx -= (int)(bw * bh * 4u); cusim_mbar_check(m);
 }
 
+// binary16 <-> binary32 (cvt.rn.f16.f32 / cvt.f32.f16) through the host compiler's _Float16 (round to nearest even)
+#define WGB_F16_CONVERSIONS_PROVIDED 1
+static inline unsigned short wgb_f32_to_f16_bits(float v) { _Float16 h = (_Float16)v; unsigned short b; memcpy(&b, &h, 2); return b; }
+static inline float wgb_f16_bits_to_f32(unsigned short b) { _Float16 h; memcpy(&h, &b, 2); return (float)h; }
+
 // MUFU.RCP (rcp.approx.ftz.f32, at most 1 ulp off) is modelled by the correctly rounded reciprocal
 #define WGB_RCP_APPROX_PROVIDED 1
 static inline float wgb_rcp_approx(float b) { return 1.0f / b; }

@@ -81,7 +81,6 @@ struct U { m: mat4x4f, lights: array<Light, 2>, k: vec2f, }
 
 @pytest.mark.parametrize("src,fragment", [
     (_fs("return vec4f(1.0);", "override k: f32 = 1.0;"), "override"),
-    (_fs("return vec4f(f16(1.0));"), "f16"),
     ("@compute @workgroup_size(1) fn fs_main() {}", "not a fragment entry point"),
     (_fs("return textureSample(t, s, p.xy, vec2i(1, 1));", "@group(0) @binding(0) var t: texture_2d<f32>;\n@group(0) @binding(1) var s: sampler;"), "offset"),
     (_fs("b = 1.0; return vec4f(1.0);", "@group(0) @binding(0) var<storage, read_write> b: f32;"), "read-only"),
@@ -97,14 +96,23 @@ def test_unsupported_wgsl_is_rejected_with_a_message(src, fragment):
     assert fragment in str(e.value)
 
 
-def test_f16_is_reported_as_unsupported_not_as_a_broken_shader():
-    """f16 exists in the reference's type table (naga-cranelift/src/types.rs:103-136) but none of its tests or examples
-    uses it; this backend says so with WGB_ERROR_UNSUPPORTED (2) -- for the type, for a literal and for the enable
-    directive's consequences -- while a genuinely malformed shader is WGB_ERROR_SHADER (5)."""
-    for body in ("return vec4f(f16(1.0));", "let h = 1.0h; return vec4f(1.0);", "var v: vec2<f16>; return vec4f(1.0);"):
+def test_f16_values_translate_and_f16_at_the_boundaries_is_unsupported():
+    """f16 (naga-cranelift/src/types.rs:103-136 has the scalar; none of the reference's tests or examples uses it): values,
+    vectors, literals, conversions, arithmetic, comparisons, select, abs / min / max / clamp translate -- every operator
+    one correctly rounded binary16 operation (wgb_prelude.cuh).  f16 in buffers, in entry-point interfaces, in matrices
+    and in the other math builtins is WGB_ERROR_UNSUPPORTED (2); a malformed shader stays WGB_ERROR_SHADER (5)."""
+    fs = api.translate_wgsl("enable f16;\n" + _fs("var a: f16 = 1.5h; let v = vec2h(a, 2.0h) * 3.0h; let c = clamp(-v.x, 0.0h, v.y); return vec4f(f32(c), f32(v.y % a), f32(a < c), 1.0);"),
+                            api.STAGE_FRAGMENT, "fs_main")
+    assert "f16 a = wgb_f16(1.5f);" in fs and "vec2h" in fs and "wgb_clamp(" in fs and "wgb_rem(" in fs
+    for decl, body in (("@group(0) @binding(0) var<uniform> u: f16;", "return vec4f(f32(u));"),
+                       ("", "return vec4f(f32(sqrt(2.0h)));"),
+                       ("", "let m = mat2x2<f16>(); return vec4f(1.0);")):
         with pytest.raises(api.WgpuError) as e:
-            api.translate_wgsl(_fs(body), api.STAGE_FRAGMENT, "fs_main")
+            api.translate_wgsl("enable f16;\n" + _fs(body, decl), api.STAGE_FRAGMENT, "fs_main")
         assert e.value.status == 2 and "f16" in str(e.value), str(e.value)
+    with pytest.raises(api.WgpuError) as e:
+        api.translate_wgsl("enable f16;\n" + _fs("return vec4h(1.0h);", "", "@location(0) vec4<f16>"), api.STAGE_FRAGMENT, "fs_main")
+    assert e.value.status == 2
     with pytest.raises(api.WgpuError) as e:
         api.translate_wgsl(_fs("return vec4f(q);"), api.STAGE_FRAGMENT, "fs_main")
     assert e.value.status == 5

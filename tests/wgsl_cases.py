@@ -4,6 +4,17 @@ plus cases for what the reference leaves todo!() (swizzles, splats, math builtin
 
 Each case: (name, module-scope declarations, body statements, result expression of type f32, expected)."""
 
+import functools as _ft
+
+import numpy as _np
+
+_h = _np.float16
+
+
+def _h16(x):
+    return float(_h(x))
+
+
 CASES = [
     # tests.rs:200-210 init_variable / store_variable
     ("init_variable", "", "var a: u32 = 123;", "f32(a)", 123.0),
@@ -135,6 +146,26 @@ CASES = [
     ("vector_dynamic_index", "", "var v = vec4f(1.0, 2.0, 3.0, 4.0); var i = 2; var j = 9;", "v[i] + v[j]", 7.0),
     ("call_result_after_discard_check", "fn pick(x: f32) -> f32 { if (x > 100.0) { discard; } return x * 2.0; }\nfn twice(x: f32) -> f32 { return pick(x) + pick(x + 1.0); }", "let y = twice(3.0);", "y", 14.0),
     ("compound_assign", "", "var a: f32 = 8.0; a /= 2.0; a -= 1.0; a *= 3.0; var i: i32 = 5; i %= 3; i <<= 2u;", "a + f32(i)", 17.0),
+    # f16 (`enable f16;`): every operator is one correctly rounded binary16 operation -- expectations from numpy.float16
+    ("f16_literal_rounds", "", "let a = 0.1h;", "f32(a)", _h16(0.1)),
+    ("f16_add_rounds", "", "var a: f16 = 2048.0h; var b: f16 = 1.0h;", "f32(a + b)", float(_h(2048.0) + _h(1.0))),
+    ("f16_mul", "", "var a: f16 = 1.1h; var b: f16 = 3.3h;", "f32(a * b)", float(_h(1.1) * _h(3.3))),
+    ("f16_div", "", "var a: f16 = 1.0h; var b: f16 = 3.0h;", "f32(a / b)", float(_h(1.0) / _h(3.0))),
+    ("f16_sub_chain", "", "var a: f16 = 1000.5h; var b: f16 = 0.3h; var c: f16 = 999.9h;", "f32(a + b - c)", float(_h(_h(1000.5) + _h(0.3)) - _h(999.9))),
+    ("f16_rem", "", "var a: f16 = 5.5h; var b: f16 = 2.0h;", "f32(a % b)", 1.5),
+    ("f16_neg_cmp", "", "var a: f16 = 1.5h;", "f32(-a < a) + f32(a == 1.5h) + f32(a >= 2.0h)", 2.0),
+    ("f16_overflow_to_inf", "", "var a: f16 = 60000.0h; var b: f16 = 2.0h;", "f32(a * b > 65504.0h)", 1.0),
+    ("f16_from_f32_rounds", "", "var x: f32 = 1.00048828125; var h: f16 = f16(x);", "f32(h)", _h16(1.00048828125)),
+    ("f16_from_int", "", "var i: i32 = 2049; var h: f16 = f16(i);", "f32(h)", _h16(2049)),
+    ("f16_to_int_trunc", "", "var h: f16 = -3.75h;", "f32(i32(h))", -3.0),
+    ("f16_vec_ops", "", "var v = vec3h(1.1h, 2.2h, 3.3h); let w = v * 2.5h + vec3h(0.05h);", "f32(w.x) + f32(w.y) * 100.0 + f32(w.z) * 10000.0",
+     float(_np.float32(_np.float32(_np.float32(_h(_h(1.1) * _h(2.5)) + _h(0.05)) + _np.float32(_np.float32(_h(_h(2.2) * _h(2.5)) + _h(0.05)) * _np.float32(100.0))) +
+                       _np.float32(_np.float32(_h(_h(3.3) * _h(2.5)) + _h(0.05)) * _np.float32(10000.0))))),
+    ("f16_vec_convert", "", "let v = vec2f(vec2h(0.1h, 0.2h)); let b = vec2h(v) == vec2h(0.1h, 0.2h);", "v.x + v.y + f32(all(b))",
+     float(_np.float32(_np.float32(_np.float32(_h(0.1)) + _np.float32(_h(0.2))) + _np.float32(1.0)))),
+    ("f16_builtins", "", "var a: f16 = -2.5h; let c = clamp(abs(a), 0.0h, 2.0h); let m = max(a, min(c, 1.5h));", "f32(c) + f32(m) * 10.0", 2.0 + 1.5 * 10.0),
+    ("f16_select_private", "var<private> acc: f16;", "acc = 0.0h; for (var i = 0; i < 10; i++) { acc = acc + 0.1h; } let s = select(acc, 2.0h, acc > 1.5h);", "f32(s)",
+     float(_ft.reduce(lambda t, _: _h(t + _h(0.1)), range(10), _h(0.0)))),
 ]
 
 

@@ -23,6 +23,41 @@ WGB_DEV f32 wgb_div(f32 a, f32 b) { return __fdiv_rn(a, b); }
 WGB_DEV f32 wgb_rem(f32 a, f32 b) { return __fsub_rn(a, __fmul_rn(b, truncf(__fdiv_rn(a, b)))); }
 
 // ---------------------------------------------------------------------------------------
+// f16 (`enable f16;` -- the scalar exists in the reference's type table, naga-cranelift/src/types.rs:103-136).
+// A value is its IEEE binary16 bits; every operator converts to binary32 (exact), applies ONE binary32 operation and
+// rounds back to binary16.  binary32 carries 24 >= 2 * 11 + 2 significand bits, so for + - * / the second rounding
+// cannot disagree with rounding the exact result once: these are the correctly rounded binary16 operations.
+// ---------------------------------------------------------------------------------------
+#ifndef WGB_F16_CONVERSIONS_PROVIDED     // (tests/cusim converts through the host compiler's _Float16)
+WGB_DEV unsigned short wgb_f32_to_f16_bits(f32 v) { unsigned short h; asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(v)); return h; }
+WGB_DEV f32 wgb_f16_bits_to_f32(unsigned short h) { f32 v; asm("cvt.f32.f16 %0, %1;" : "=f"(v) : "h"(h)); return v; }
+#endif
+struct f16 {
+    unsigned short bits;
+    WGB_DEV f16() : bits(0) {}
+    WGB_DEV explicit f16(int) : bits(0) {}            // f16(0): the zero value the emitter writes for an uninitialised var
+};
+WGB_DEV f16 wgb_f16(f32 v) { f16 h; h.bits = wgb_f32_to_f16_bits(v); return h; }
+WGB_DEV f32 wgb_f32(f16 h) { return wgb_f16_bits_to_f32(h.bits); }
+WGB_DEV f16 wgb_add(f16 a, f16 b) { return wgb_f16(__fadd_rn(wgb_f32(a), wgb_f32(b))); }
+WGB_DEV f16 wgb_sub(f16 a, f16 b) { return wgb_f16(__fsub_rn(wgb_f32(a), wgb_f32(b))); }
+WGB_DEV f16 wgb_mul(f16 a, f16 b) { return wgb_f16(__fmul_rn(wgb_f32(a), wgb_f32(b))); }
+WGB_DEV f16 wgb_div(f16 a, f16 b) { return wgb_f16(__fdiv_rn(wgb_f32(a), wgb_f32(b))); }
+// a - b*trunc(a/b), every step a binary16 operation (as wgb_rem for f32)
+WGB_DEV f16 wgb_rem(f16 a, f16 b) { return wgb_sub(a, wgb_mul(b, wgb_f16(truncf(wgb_f32(wgb_div(a, b)))))); }
+WGB_DEV f16 operator-(f16 a) { f16 r; r.bits = (unsigned short)(a.bits ^ 0x8000u); return r; }
+WGB_DEV f16 operator+(f16 a, f16 b) { return wgb_add(a, b); }
+WGB_DEV f16 operator-(f16 a, f16 b) { return wgb_sub(a, b); }
+WGB_DEV f16 operator*(f16 a, f16 b) { return wgb_mul(a, b); }
+WGB_DEV f16 operator/(f16 a, f16 b) { return wgb_div(a, b); }
+WGB_DEV bool operator==(f16 a, f16 b) { return wgb_f32(a) == wgb_f32(b); }
+WGB_DEV bool operator!=(f16 a, f16 b) { return wgb_f32(a) != wgb_f32(b); }
+WGB_DEV bool operator<(f16 a, f16 b) { return wgb_f32(a) < wgb_f32(b); }
+WGB_DEV bool operator>(f16 a, f16 b) { return wgb_f32(a) > wgb_f32(b); }
+WGB_DEV bool operator<=(f16 a, f16 b) { return wgb_f32(a) <= wgb_f32(b); }
+WGB_DEV bool operator>=(f16 a, f16 b) { return wgb_f32(a) >= wgb_f32(b); }
+
+// ---------------------------------------------------------------------------------------
 // vectors
 // ---------------------------------------------------------------------------------------
 #define WGB_VEC_TYPES(T, S)                                                                         \
@@ -63,22 +98,30 @@ WGB_VEC_TYPES(f32, f)
 WGB_VEC_TYPES(i32, i)
 WGB_VEC_TYPES(u32, u)
 WGB_VEC_TYPES(bool, b)
+WGB_VEC_TYPES(f16, h)
 
 // element-wise float operators; scalar (x) vector in both orders (binary.rs:210-268, 343-418)
-#define WGB_VEC_FLOAT_OP(OP, FN)                                                                                  \
-    WGB_DEV vec2f operator OP(vec2f a, vec2f b) { return vec2f(FN(a.x, b.x), FN(a.y, b.y)); }                      \
-    WGB_DEV vec3f operator OP(vec3f a, vec3f b) { return vec3f(FN(a.x, b.x), FN(a.y, b.y), FN(a.z, b.z)); }        \
-    WGB_DEV vec4f operator OP(vec4f a, vec4f b) { return vec4f(FN(a.x, b.x), FN(a.y, b.y), FN(a.z, b.z), FN(a.w, b.w)); } \
-    WGB_DEV vec2f operator OP(vec2f a, f32 s) { return vec2f(FN(a.x, s), FN(a.y, s)); }                            \
-    WGB_DEV vec3f operator OP(vec3f a, f32 s) { return vec3f(FN(a.x, s), FN(a.y, s), FN(a.z, s)); }                \
-    WGB_DEV vec4f operator OP(vec4f a, f32 s) { return vec4f(FN(a.x, s), FN(a.y, s), FN(a.z, s), FN(a.w, s)); }    \
-    WGB_DEV vec2f operator OP(f32 s, vec2f a) { return vec2f(FN(s, a.x), FN(s, a.y)); }                            \
-    WGB_DEV vec3f operator OP(f32 s, vec3f a) { return vec3f(FN(s, a.x), FN(s, a.y), FN(s, a.z)); }                \
-    WGB_DEV vec4f operator OP(f32 s, vec4f a) { return vec4f(FN(s, a.x), FN(s, a.y), FN(s, a.z), FN(s, a.w)); }
-WGB_VEC_FLOAT_OP(+, wgb_add)
-WGB_VEC_FLOAT_OP(-, wgb_sub)
-WGB_VEC_FLOAT_OP(*, wgb_mul)
-WGB_VEC_FLOAT_OP(/, wgb_div)
+#define WGB_VEC_FLOAT_OP(S, T, OP, FN)                                                                            \
+    WGB_DEV vec2##S operator OP(vec2##S a, vec2##S b) { return vec2##S(FN(a.x, b.x), FN(a.y, b.y)); }              \
+    WGB_DEV vec3##S operator OP(vec3##S a, vec3##S b) { return vec3##S(FN(a.x, b.x), FN(a.y, b.y), FN(a.z, b.z)); } \
+    WGB_DEV vec4##S operator OP(vec4##S a, vec4##S b) { return vec4##S(FN(a.x, b.x), FN(a.y, b.y), FN(a.z, b.z), FN(a.w, b.w)); } \
+    WGB_DEV vec2##S operator OP(vec2##S a, T s) { return vec2##S(FN(a.x, s), FN(a.y, s)); }                        \
+    WGB_DEV vec3##S operator OP(vec3##S a, T s) { return vec3##S(FN(a.x, s), FN(a.y, s), FN(a.z, s)); }            \
+    WGB_DEV vec4##S operator OP(vec4##S a, T s) { return vec4##S(FN(a.x, s), FN(a.y, s), FN(a.z, s), FN(a.w, s)); } \
+    WGB_DEV vec2##S operator OP(T s, vec2##S a) { return vec2##S(FN(s, a.x), FN(s, a.y)); }                        \
+    WGB_DEV vec3##S operator OP(T s, vec3##S a) { return vec3##S(FN(s, a.x), FN(s, a.y), FN(s, a.z)); }            \
+    WGB_DEV vec4##S operator OP(T s, vec4##S a) { return vec4##S(FN(s, a.x), FN(s, a.y), FN(s, a.z), FN(s, a.w)); }
+WGB_VEC_FLOAT_OP(f, f32, +, wgb_add)
+WGB_VEC_FLOAT_OP(f, f32, -, wgb_sub)
+WGB_VEC_FLOAT_OP(f, f32, *, wgb_mul)
+WGB_VEC_FLOAT_OP(f, f32, /, wgb_div)
+WGB_VEC_FLOAT_OP(h, f16, +, wgb_add)
+WGB_VEC_FLOAT_OP(h, f16, -, wgb_sub)
+WGB_VEC_FLOAT_OP(h, f16, *, wgb_mul)
+WGB_VEC_FLOAT_OP(h, f16, /, wgb_div)
+WGB_DEV vec2h operator-(vec2h a) { return vec2h(-a.x, -a.y); }
+WGB_DEV vec3h operator-(vec3h a) { return vec3h(-a.x, -a.y, -a.z); }
+WGB_DEV vec4h operator-(vec4h a) { return vec4h(-a.x, -a.y, -a.z, -a.w); }
 WGB_DEV vec2f operator-(vec2f a) { return vec2f(-a.x, -a.y); }
 WGB_DEV vec3f operator-(vec3f a) { return vec3f(-a.x, -a.y, -a.z); }
 WGB_DEV vec4f operator-(vec4f a) { return vec4f(-a.x, -a.y, -a.z, -a.w); }
@@ -171,6 +214,17 @@ WGB_DEV bool wgb_to_bool(f32 v) { return v != 0.0f; }
 WGB_DEV bool wgb_to_bool(i32 v) { return v != 0; }
 WGB_DEV bool wgb_to_bool(u32 v) { return v != 0u; }
 WGB_DEV bool wgb_to_bool(bool v) { return v; }
+// f16: to it through binary32 (integers up to binary16's largest finite value are exact there, larger ones round to
+// infinity either way), from it exactly
+WGB_DEV f16 wgb_to_f16(f16 v) { return v; }
+WGB_DEV f16 wgb_to_f16(f32 v) { return wgb_f16(v); }
+WGB_DEV f16 wgb_to_f16(i32 v) { return wgb_f16(__int2float_rn(v)); }
+WGB_DEV f16 wgb_to_f16(u32 v) { return wgb_f16(__uint2float_rn(v)); }
+WGB_DEV f16 wgb_to_f16(bool v) { return wgb_f16(v ? 1.0f : 0.0f); }
+WGB_DEV f32 wgb_to_f32(f16 v) { return wgb_f32(v); }
+WGB_DEV i32 wgb_to_i32(f16 v) { return __float2int_rz(wgb_f32(v)); }
+WGB_DEV u32 wgb_to_u32(f16 v) { return __float2uint_rz(wgb_f32(v)); }
+WGB_DEV bool wgb_to_bool(f16 v) { return wgb_f32(v) != 0.0f; }
 
 // integer division / remainder: the reference aborts on division by zero and on
 // i32::MIN / -1 (binary.rs:451-563); WGSL's defined results are used here instead
@@ -199,6 +253,7 @@ WGB_LIFT2(wgb_idiv, u, u32)
 WGB_LIFT2(wgb_irem, i, i32)
 WGB_LIFT2(wgb_irem, u, u32)
 WGB_LIFT2(wgb_rem, f, f32)
+WGB_LIFT2(wgb_rem, h, f16)
 WGB_DEV vec2i operator-(vec2i a) { return vec2i(-a.x, -a.y); }
 WGB_DEV vec3i operator-(vec3i a) { return vec3i(-a.x, -a.y, -a.z); }
 WGB_DEV vec4i operator-(vec4i a) { return vec4i(-a.x, -a.y, -a.z, -a.w); }
@@ -211,6 +266,7 @@ WGB_DEV vec4i operator-(vec4i a) { return vec4i(-a.x, -a.y, -a.z, -a.w); }
 #define WGB_VEC_CMP_ALL(S) WGB_VEC_CMP(wgb_eq, ==, S) WGB_VEC_CMP(wgb_ne, !=, S) WGB_VEC_CMP(wgb_lt, <, S) \
     WGB_VEC_CMP(wgb_gt, >, S) WGB_VEC_CMP(wgb_le, <=, S) WGB_VEC_CMP(wgb_ge, >=, S)
 WGB_VEC_CMP_ALL(f)
+WGB_VEC_CMP_ALL(h)
 WGB_VEC_CMP_ALL(i)
 WGB_VEC_CMP_ALL(u)
 WGB_VEC_CMP(wgb_eq, ==, b)
@@ -247,6 +303,7 @@ template <class T> WGB_DEV T wgb_select(T f, T t, bool cond) { return cond ? t :
     WGB_DEV vec3##S wgb_select(vec3##S f, vec3##S t, vec3b c) { return vec3##S(c.x ? t.x : f.x, c.y ? t.y : f.y, c.z ? t.z : f.z); } \
     WGB_DEV vec4##S wgb_select(vec4##S f, vec4##S t, vec4b c) { return vec4##S(c.x ? t.x : f.x, c.y ? t.y : f.y, c.z ? t.z : f.z, c.w ? t.w : f.w); }
 WGB_VEC_SELECT(f)
+WGB_VEC_SELECT(h)
 WGB_VEC_SELECT(i)
 WGB_VEC_SELECT(u)
 WGB_VEC_SELECT(b)
@@ -327,6 +384,12 @@ WGB_LIFT2(wgb_min, i, i32) WGB_LIFT2(wgb_max, i, i32) WGB_LIFT2(wgb_min, u, u32)
     WGB_DEV vec3##S FN(vec3##S a, T b, T c) { return vec3##S(FN(a.x, b, c), FN(a.y, b, c), FN(a.z, b, c)); } \
     WGB_DEV vec4##S FN(vec4##S a, T b, T c) { return vec4##S(FN(a.x, b, c), FN(a.y, b, c), FN(a.z, b, c), FN(a.w, b, c)); }
 WGB_LIFT3(wgb_clamp, f, f32) WGB_LIFT3(wgb_clamp, i, i32) WGB_LIFT3(wgb_clamp, u, u32) WGB_LIFT3(wgb_fma, f, f32)
+// f16: the selections are exact (the result is one of the operands); the other math builtins are not offered for f16
+WGB_DEV f16 wgb_abs(f16 a) { f16 r; r.bits = (unsigned short)(a.bits & 0x7FFFu); return r; }
+WGB_DEV f16 wgb_min(f16 a, f16 b) { return wgb_f16(fminf(wgb_f32(a), wgb_f32(b))); }
+WGB_DEV f16 wgb_max(f16 a, f16 b) { return wgb_f16(fmaxf(wgb_f32(a), wgb_f32(b))); }
+WGB_DEV f16 wgb_clamp(f16 x, f16 lo, f16 hi) { return wgb_min(wgb_max(x, lo), hi); }
+WGB_LIFT1(wgb_abs, h) WGB_LIFT2(wgb_min, h, f16) WGB_LIFT2(wgb_max, h, f16) WGB_LIFT3(wgb_clamp, h, f16)
 // ---- integer bit builtins (WGSL 17.5.x; all `todo!()` in the reference with the rest of Math) ----
 WGB_DEV u32 wgb_countOneBits(u32 a) { return (u32)__popc(a); }
 WGB_DEV i32 wgb_countOneBits(i32 a) { return __popc((u32)a); }

@@ -126,16 +126,16 @@ std::vector<Tok> lex(const std::string& src) {
 // ------------------------------------------------------------------------------------------
 struct StructDecl;
 struct Type {
-    enum K { Void, Bool, I32, U32, F32, AInt, AFloat, Vec, Mat, Array, Struct, Texture2D, Sampler } k = Void;
+    enum K { Void, Bool, I32, U32, F32, F16, AInt, AFloat, Vec, Mat, Array, Struct, Texture2D, Sampler } k = Void;
     int n = 0;            // vector size / matrix columns
     int rows = 0;         // matrix rows
     std::shared_ptr<Type> elem;   // vector / matrix scalar, array element
     int count = 0;        // array length (0 = runtime sized)
     const StructDecl* st = nullptr;
 
-    bool is_scalar() const { return k == Bool || k == I32 || k == U32 || k == F32 || k == AInt || k == AFloat; }
+    bool is_scalar() const { return k == Bool || k == I32 || k == U32 || k == F32 || k == F16 || k == AInt || k == AFloat; }
     bool is_abstract() const { return k == AInt || k == AFloat || ((k == Vec || k == Mat || k == Array) && elem && elem->is_abstract()); }
-    bool is_float_scalar() const { return k == F32 || k == AFloat; }
+    bool is_float_scalar() const { return k == F32 || k == F16 || k == AFloat; }
     bool is_int_scalar() const { return k == I32 || k == U32 || k == AInt; }
     const Type& scalar() const { return (k == Vec || k == Mat) ? *elem : *this; }
 };
@@ -162,6 +162,7 @@ struct StructDecl { std::string name; std::vector<Member> members; uint32_t size
 std::string scalar_suffix(const Type& s, int line) {
     switch (s.k) {
         case Type::F32: case Type::AFloat: return "f";
+        case Type::F16: return "h";
         case Type::I32: case Type::AInt: return "i";
         case Type::U32: return "u";
         case Type::Bool: return "b";
@@ -175,9 +176,11 @@ std::string cuda_type(const Type& t, int line) {
         case Type::I32: case Type::AInt: return "i32";
         case Type::U32: return "u32";
         case Type::F32: case Type::AFloat: return "f32";
+        case Type::F16: return "f16";
         case Type::Vec: return "vec" + std::to_string(t.n) + scalar_suffix(*t.elem, line);
         case Type::Mat:
             if (t.n != t.rows || !(t.n == 2 || t.n == 3 || t.n == 4)) err(line, "only square matrices are supported");
+            if (t.elem->k == Type::F16) err(line, "f16 matrices are not supported");
             return "mat" + std::to_string(t.n) + "x" + std::to_string(t.rows) + "f";
         case Type::Array:
             if (t.count == 0) err(line, "runtime-sized arrays cannot be used by value");
@@ -189,7 +192,7 @@ std::string cuda_type(const Type& t, int line) {
 std::string wgsl_type_name(const Type& t) {
     switch (t.k) {
         case Type::Void: return "void"; case Type::Bool: return "bool"; case Type::I32: return "i32"; case Type::U32: return "u32";
-        case Type::F32: return "f32"; case Type::AInt: return "abstract-int"; case Type::AFloat: return "abstract-float";
+        case Type::F32: return "f32"; case Type::F16: return "f16"; case Type::AInt: return "abstract-int"; case Type::AFloat: return "abstract-float";
         case Type::Vec: return "vec" + std::to_string(t.n) + "<" + wgsl_type_name(*t.elem) + ">";
         case Type::Mat: return "mat" + std::to_string(t.n) + "x" + std::to_string(t.rows) + "<" + wgsl_type_name(*t.elem) + ">";
         case Type::Array: return "array<" + wgsl_type_name(*t.elem) + ">";
@@ -203,7 +206,10 @@ std::string wgsl_type_name(const Type& t) {
 void layout_of(const Type& t, uint32_t& align, uint32_t& size, int line) {
     switch (t.k) {
         case Type::I32: case Type::U32: case Type::F32: align = 4; size = 4; return;
-        case Type::Vec: align = t.n == 2 ? 8 : 16; size = 4 * t.n; return;
+        case Type::F16: err(line, "f16 in uniform / storage buffers is not supported (f16 values live in function and private variables)");
+        case Type::Vec:
+            if (t.elem->k == Type::F16) err(line, "f16 in uniform / storage buffers is not supported (f16 values live in function and private variables)");
+            align = t.n == 2 ? 8 : 16; size = 4 * t.n; return;
         case Type::Mat: { const uint32_t ca = t.rows == 2 ? 8 : 16; align = ca; size = ca * t.n; return; }
         case Type::Array: {
             uint32_t ea, es;
@@ -306,7 +312,7 @@ struct Parser {
         if (s == "i32") return T(Type::I32);
         if (s == "u32") return T(Type::U32);
         if (s == "bool") return T(Type::Bool);
-        if (s == "f16") err(line, "f16 is not supported");
+        if (s == "f16") return T(Type::F16);
         err(line, "unknown scalar type '" + s + "'");
     }
     // parses a type; returns false in *ok if the identifier is not a type name
@@ -332,7 +338,7 @@ struct Parser {
             if (s.size() == 5) {
                 Type e;
                 switch (s[4]) { case 'f': e = T(Type::F32); break; case 'i': e = T(Type::I32); break; case 'u': e = T(Type::U32); break;
-                                case 'h': err(line, "f16 is not supported"); default: return false; }
+                                case 'h': e = T(Type::F16); break; default: return false; }
                 p++; out = vec_t(n, e); return true;
             }
             return false;
@@ -342,10 +348,11 @@ struct Parser {
             if (s.size() == 6) {
                 p++;
                 Type e;
-                if (templ_scalar(e)) { out = mat_t(c, r, e); return true; }
+                if (templ_scalar(e)) { if (e.k == Type::F16) err(line, "f16 matrices are not supported"); out = mat_t(c, r, e); return true; }
                 if (!allow_infer) err(line, "matrix type needs a component type here");
                 out = mat_t(c, r, T(Type::F32)); if (inferred) *inferred = true; return true;
             }
+            if (s.size() == 7 && s[6] == 'h') err(line, "f16 matrices are not supported");
             if (s.size() == 7 && s[6] == 'f') { p++; out = mat_t(c, r, T(Type::F32)); return true; }
             return false;
         }
@@ -734,8 +741,8 @@ struct Emitter {
     // can a value of type `from` be used where `to` is expected (abstract conversions only)?
     static bool converts(const Type& from, const Type& to) {
         if (same(from, to)) return true;
-        if (from.k == Type::AInt) return to.k == Type::I32 || to.k == Type::U32 || to.k == Type::F32 || to.k == Type::AFloat;
-        if (from.k == Type::AFloat) return to.k == Type::F32;
+        if (from.k == Type::AInt) return to.k == Type::I32 || to.k == Type::U32 || to.k == Type::F32 || to.k == Type::F16 || to.k == Type::AFloat;
+        if (from.k == Type::AFloat) return to.k == Type::F32 || to.k == Type::F16;
         if (from.k == Type::Vec && to.k == Type::Vec && from.n == to.n) return converts(*from.elem, *to.elem);
         if (from.k == Type::Mat && to.k == Type::Mat && from.n == to.n && from.rows == to.rows) return converts(*from.elem, *to.elem);
         if (from.k == Type::Array && to.k == Type::Array && from.count == to.count) return converts(*from.elem, *to.elem);
@@ -748,6 +755,10 @@ struct Emitter {
     std::string lit_text(const Val& v, const Type& want, int line) {
         // a folded abstract constant rendered as `want`
         if (want.k == Type::F32 || want.k == Type::AFloat) return fmt_float(v.num);
+        if (want.k == Type::F16) {          // the literal rounded to binary16 (65504 is the largest finite value; halfway cases round to even)
+            if (std::fabs(v.num) >= 65520.0) err(line, "literal out of range for f16");
+            return "wgb_f16(" + fmt_float((double)(float)v.num) + ")";
+        }
         if (want.k == Type::U32) { if (v.num < 0 || v.num > 4294967295.0) err(line, "literal out of range for u32"); return std::to_string((unsigned long long)v.num) + "u"; }
         if (want.k == Type::I32 || want.k == Type::AInt) {
             if (v.num < -2147483648.0 || v.num > 2147483647.0) err(line, "literal out of range for i32");
@@ -876,7 +887,7 @@ struct Emitter {
                 Val v;
                 if (e->is_bool) { v.s = e->f != 0 ? "true" : "false"; v.t = T(Type::Bool); return v; }
                 v.is_const_num = true; v.num = e->f;
-                if (e->is_float) { v.t = e->suffix == 'f' ? T(Type::F32) : T(Type::AFloat); if (e->suffix == 'h') err(line, "f16 literals are not supported"); }
+                if (e->is_float || e->suffix == 'h') v.t = e->suffix == 'f' ? T(Type::F32) : e->suffix == 'h' ? T(Type::F16) : T(Type::AFloat);
                 else v.t = e->suffix == 'u' ? T(Type::U32) : e->suffix == 'i' ? T(Type::I32) : T(Type::AInt);
                 v.s = lit_text(v, v.t, line);
                 return v;
@@ -902,7 +913,7 @@ struct Emitter {
                 a = concrete(a, line); v.t = a.t;
                 if (e->name == "-") {
                     const Type& sc = a.t.scalar();
-                    if (!(sc.k == Type::F32 || sc.k == Type::I32)) err(line, "unary '-' needs a signed numeric operand");
+                    if (!(sc.k == Type::F32 || sc.k == Type::F16 || sc.k == Type::I32)) err(line, "unary '-' needs a signed numeric operand");
                     v.s = "(-" + a.s + ")";
                 } else if (e->name == "!") {
                     if (a.t.scalar().k != Type::Bool) err(line, "'!' needs a bool operand");
@@ -1031,7 +1042,7 @@ struct Emitter {
         const Type &ta = a.t, &tb = b.t;
         if (ta.scalar().k == Type::Bool || tb.scalar().k == Type::Bool) err(line, "arithmetic on bool");
         if (!same(ta.scalar(), tb.scalar())) err(line, "operands of '" + op + "' have different component types: " + wgsl_type_name(ta) + " and " + wgsl_type_name(tb));
-        const bool fl = ta.scalar().k == Type::F32;
+        const bool fl = ta.scalar().k == Type::F32 || ta.scalar().k == Type::F16;
         if (ta.is_scalar() && tb.is_scalar()) {
             v.t = ta;
             if (fl) {
@@ -1077,12 +1088,12 @@ struct Emitter {
             Val a = args[0];
             if (a.is_const_num && a.t.is_abstract()) {
                 if (to.k == Type::Bool) { v.s = a.num != 0 ? "true" : "false"; v.t = to; return v; }
-                Val c = a; if (to.k != Type::F32 && a.t.k == Type::AFloat) c.num = std::trunc(a.num);
+                Val c = a; if (to.k != Type::F32 && to.k != Type::F16 && a.t.k == Type::AFloat) c.num = std::trunc(a.num);
                 c.t = to; c.s = lit_text(c, to, line); c.is_const_num = true; return c;
             }
             a = concrete(a, line);
             if (!a.t.is_scalar()) err(line, "cannot convert " + wgsl_type_name(a.t) + " to a scalar");
-            static const std::map<int, std::string> fn = {{Type::F32, "wgb_to_f32"}, {Type::I32, "wgb_to_i32"}, {Type::U32, "wgb_to_u32"}, {Type::Bool, "wgb_to_bool"}};
+            static const std::map<int, std::string> fn = {{Type::F32, "wgb_to_f32"}, {Type::F16, "wgb_to_f16"}, {Type::I32, "wgb_to_i32"}, {Type::U32, "wgb_to_u32"}, {Type::Bool, "wgb_to_bool"}};
             v.s = fn.at(to.k) + "(" + a.s + ")"; v.t = to; return v;
         }
         if (to.k == Type::Vec) {
@@ -1095,7 +1106,7 @@ struct Emitter {
                     const Type& s = a.t.scalar();
                     if (!any) { elem = s; any = true; continue; }
                     if (elem.k == Type::AInt && s.k != Type::AInt) elem = s;
-                    else if (elem.k == Type::AFloat && s.k == Type::F32) elem = s;
+                    else if (elem.k == Type::AFloat && (s.k == Type::F32 || s.k == Type::F16)) elem = s;
                 }
                 if (!any) elem = T(Type::F32);
                 elem = concretize(elem);
@@ -1113,7 +1124,7 @@ struct Emitter {
                     if (args.size() == 1 && a.t.n == to.n && !same(concretize(*a.t.elem), elem)) {
                         // vector conversion, e.g. vec3f(vec3i): component-wise cast
                         a = concrete(a, line);
-                        static const std::map<int, std::string> fn = {{Type::F32, "wgb_to_f32"}, {Type::I32, "wgb_to_i32"}, {Type::U32, "wgb_to_u32"}, {Type::Bool, "wgb_to_bool"}};
+                        static const std::map<int, std::string> fn = {{Type::F32, "wgb_to_f32"}, {Type::F16, "wgb_to_f16"}, {Type::I32, "wgb_to_i32"}, {Type::U32, "wgb_to_u32"}, {Type::Bool, "wgb_to_bool"}};
                         static const char* comp = "xyzw";
                         std::string c;
                         for (int k = 0; k < to.n; k++) { if (k) c += ", "; c += fn.at(elem.k) + "(wgb_t." + comp[k] + ")"; }
@@ -1292,7 +1303,9 @@ struct Emitter {
             for (auto& a : args) { if (want.is_abstract() && !a.t.is_abstract()) want = a.t; if (a.t.k == Type::Vec && want.is_scalar()) want = vec_t(a.t.n, want.scalar()); }
             want = concretize(want);
             const bool int_ok = name == "abs" || name == "min" || name == "max" || name == "clamp" || name == "sign" || name == "dot";
-            if (table[i].ret != 2 && want.scalar().k != Type::F32 && !int_ok) {
+            if (want.scalar().k == Type::F16 && !(name == "abs" || name == "min" || name == "max" || name == "clamp"))
+                err(line, name + " is not supported for f16 arguments (abs, min, max, clamp and select are)");
+            if (table[i].ret != 2 && want.scalar().k != Type::F32 && want.scalar().k != Type::F16 && !int_ok) {
                 if (want.scalar().k == Type::I32 && args[0].t.is_abstract()) want = want.k == Type::Vec ? vec_t(want.n, T(Type::F32)) : T(Type::F32);
                 else err(line, name + " needs float arguments");
             }
@@ -1673,6 +1686,7 @@ struct Emitter {
             for (auto& mb : t.st->members) collect_io(prefix + "." + mb.name, mb.type, mb.attrs, mb.line, items);
             return;
         }
+        if (t.scalar().k == Type::F16) err(line, "f16 entry point inputs / outputs are not supported (convert to f32 at the stage boundary)");
         IoItem it; it.access = prefix; it.type = t; it.line = line;
         if (const Attr* b = find_attr(attrs, "builtin")) { if (b->args.empty()) err(line, "@builtin needs a name"); it.builtin = b->args[0]; }
         if (const Attr* l = find_attr(attrs, "location")) { if (l->args.empty()) err(line, "@location needs an index"); it.location = atoi(l->args[0].c_str()); }
