@@ -102,7 +102,7 @@ def main():
     L = []
     w = L.append
     ps = bench["pass_stats"]
-    w(f"# Round 1 profile summary (B200, C3: {bench['config']['triangles']} triangles, {bench['config']['width']}x{bench['config']['height']})\n")
+    w(f"# Round {int(RND[1:])} profile summary (B200, C3: {bench['config']['triangles']} triangles, {bench['config']['width']}x{bench['config']['height']})\n")
     w(f"Sources: `{RND}_bench_c3_{tag}.json` (bench.py, not under a profiler), `{RND}_bench_reference_c3.json` (`--impl reference`), "
       f"`{RND}_launches_c3_{tag}.csv` (`ncu --metrics gpu__time_duration.sum --clock-control none`, cold-cache serialised launches: "
       f"compare shares), `{RND}_ncu_full_c3_{tag}.json` (`ncu --set full --clock-control none --import-source on`, one launch of each "
