@@ -1042,9 +1042,9 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             if (vcache_n) {
                 // the cache holds every instance of the draw, so it is filled once, by the first batch
                 if (base == 0) launch(dev, ks->vertex, dim3((uint32_t)(((uint64_t)vcache_n * sc.instance_count + 255) / 256)), dim3(256), &d);
-                launch(dev, ks->geometry_cached, dim3(((np + 1) / 2 + 255) / 256), dim3(256), &d);      // two primitives per thread
+                launch(dev, ks->geometry_cached, dim3(((np >= WGB_GEOMETRY_PAIRED_MIN ? (np + 1) / 2 : np) + 255) / 256), dim3(256), &d);      // two primitives per thread of a large batch
             } else launch(dev, ks->geometry, dim3(gblocks), dim3(256), &d);
-            launch(dev, ks->clip, dim3(std::min<uint32_t>((np + 127) / 128, 148 * 8)), dim3(128), &d);
+            launch(dev, ks->clip, dim3(std::min<uint32_t>(std::max<uint32_t>((np + 127) / 128, 148), 148 * 8)), dim3(128), &d);      // (the kernel deals its list out over the warps it finds)
             if (!bin_cap) {
                 launch(dev, ks->scan, dim3(1), dim3(1024), &d);
                 launch(dev, ks->fill, dim3(gblocks), dim3(256), &d);
