@@ -472,7 +472,9 @@ def main():
         # every step uploads one full input set from pinned host memory, renders it and reads the frame back.  At N > 1
         # each rank uploads 1/N of the vertex and index bytes over its own PCIe link and the ranks all-gather the
         # slices over NVLink (NCCL, in place in the backend's buffers), so the host feeds the scene once, not N times.
-        sets = [r, SceneRenderer(dev, queue, scene, use_emitted=use_emitted, targets=targets)]
+        # three resident input sets at N > 1 (upload of k+2, all-gather of k+1 and rendering of k run side by side), two at N = 1
+        n_sets = 3 if world > 1 else 2
+        sets = [r] + [SceneRenderer(dev, queue, scene, use_emitted=use_emitted, targets=targets) for _ in range(n_sets - 1)]
 
         def pin(a):
             t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=not model)
@@ -498,7 +500,7 @@ def main():
                     alias[(si, kind, i)] = multigpu.tensor_from_device_pointer(ptr, nbytes, local_rank)
         h2d_rank = sum(chunk(t.numel()) + (t.numel() - chunk(t.numel()) * world if world > 1 else 0) for _, _, t in big) + sum(t.numel() for _, t in uni)
         d2h = W * H * 4
-        frame_host = torch.empty(d2h, dtype=torch.uint8, pin_memory=not model)
+        frame_host = [torch.empty(d2h, dtype=torch.uint8, pin_memory=not model) for _ in range(2)]
 
         def upload(si):
             rr = sets[si]
@@ -512,39 +514,60 @@ def main():
             for key, t in uni:
                 queue.write_buffer_pinned_async(rr.resources[key], 0, t.numpy())
 
-        def exchange(si):
-            if world == 1:
-                return
-            queue.wait_uploads()
+        def exchange_start(si):
+            """All-gather of the ranks' slices of input set `si`, in place in the backend's buffers, on torch's stream; not
+            waited for here.  The caller has waited for this rank's slice (queue.wait_uploads)."""
             for kind, i, t in big:
                 c = chunk(t.numel())
                 if c:
                     full = alias[(si, kind, i)]
                     dist.all_gather_into_tensor(full[:c * world], full[rank * c:(rank + 1) * c])
-            sync()
 
-        def e2e_step(k):
-            cur, nxt = k % 2, (k + 1) % 2
-            upload(nxt)                                   # copy stream: overlaps this step's rendering
+        e2e_k = [0]
+
+        def e2e_step():
+            """Step k renders input set k % n_sets and starts the read-back of its frame.  Beside it: the upload of the
+            set after next on the copy stream, the all-gather of the next set on torch's stream (N > 1), and the
+            read-back of the previous frame on the read-back stream (the presenter targets alternate)."""
+            k = e2e_k[0]
+            e2e_k[0] += 1
+            cur = k % n_sets
+            if world > 1:
+                nxt = (k + 1) % n_sets
+                queue.wait_uploads()                      # this rank's slice of set k+1, started a step ago
+                exchange_start(nxt)
+                upload((k + 2) % n_sets)                  # last used by step k-1, which has been waited for
+            else:
+                upload((k + 1) % n_sets)
             f = frame_no[0]
             frame_no[0] += 1
-            sets[cur].render(sets[cur].encode(f))
+            dev.poll(True, sets[cur].submit(sets[cur].encode(f)))
+            if rank == 0:
+                dev.wait_readbacks()                      # frame f-1 is on the host: after the exchange below the ranks may go on to frame f+1, which overwrites its target
             gather(f)
-            img = sets[cur].targets[f % n_present].read(out=frame_host.numpy()) if rank == 0 else None
-            exchange(nxt)
-            return img
+            if rank == 0:
+                sets[cur].targets[f % n_present].read_pinned_async(frame_host[f % 2].numpy())
+            if world > 1:
+                sync()                                    # the all-gather of set k+1 has completed
 
         upload(0)
-        exchange(0)
-        for k in range(2):
-            e2e_step(k)
+        if world > 1:
+            queue.wait_uploads()
+            exchange_start(0)
+            sync()
+            upload(1)
+        for _ in range(3):
+            e2e_step()
         n_e2e = max(4, min(args.steps, 10)) & ~1
+        queue.wait_uploads()
+        dev.wait_readbacks()
         barrier()
         t1 = time.perf_counter()
-        for k in range(n_e2e):
-            e2e_step(k)
+        for _ in range(n_e2e):
+            e2e_step()
         queue.wait_uploads()
         dev.poll(True)
+        dev.wait_readbacks()
         barrier()
         de = time.perf_counter() - t1
         if world > 1:
@@ -558,8 +581,8 @@ def main():
             h2d_total = int(h2d_rank)
         e2e = {"value": prims * n_e2e / de / 1e6, "unit": "Mtri/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": int(d2h),
                "ms_per_step": de / n_e2e * 1e3, "steps": n_e2e,
-               "pipelining": "inputs of step k+1 upload on the copy stream while step k renders (two resident input sets)" +
-                             ("; every rank uploads 1/N of the vertex and index bytes, NCCL all-gather over NVLink" if world > 1 else "")}
+               "pipelining": "while step k renders, the inputs of a later step upload on the copy stream and frame k-1 is read back on the read-back stream" +
+                             ("; every rank uploads 1/N of the vertex and index bytes of step k+2 while NCCL all-gathers those of step k+1 over NVLink (three resident input sets)" if world > 1 else " (two resident input sets)")}
 
     # ---- parity: the frame this run assembles on rank 0 against the oracle's digest (tests/golden, tools/make_bench_golden.py) ----
     parity = None

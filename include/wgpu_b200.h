@@ -192,6 +192,13 @@ WGB_API wgb_status wgb_queue_write_texture(wgb_queue queue, wgb_texture texture,
 /* Read-back of a texture's texels, row-major and tightly packed: what wgpu_cpu::dump_texture /
  * image::rgba_texture_image observe (lib.rs:111-173).  Waits for earlier submissions. */
 WGB_API wgb_status wgb_texture_read(wgb_texture texture, void* dst, uint64_t dst_size);
+/* The same read-back, not waited for (no counterpart in the reference, whose textures are host memory): the texels as
+ * the submissions made so far leave them, copied to page-locked `dst` on the device's read-back stream.  Later
+ * submissions run while the copy does, and wait for it only where they write this texture; `dst` holds the texels once
+ * wgb_device_wait_readbacks has returned. */
+WGB_API wgb_status wgb_texture_read_pinned_async(wgb_texture texture, void* dst, uint64_t dst_size);
+/* waits for every read-back started with wgb_texture_read_pinned_async */
+WGB_API wgb_status wgb_device_wait_readbacks(wgb_device device);
 /* wgpu_cpu::dump_texture (lib.rs:111-158): layer 0 of the texture as a PNG file.  Rgba8Unorm[Srgb] bytes as they are,
  * Bgra8Unorm[Srgb] swizzled to RGBA, Depth32Float as 8-bit grey `(depth * 255.0) as u8`; other formats are
  * WGB_ERROR_UNSUPPORTED (`todo!()` in the reference).  The file is a plain (stored, uncompressed) PNG. */

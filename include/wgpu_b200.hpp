@@ -92,6 +92,8 @@ struct Texture : Handle<wgb_texture> {
         check(wgb_texture_read(get(), out.data(), out.size()));
         return out;
     }
+    // not waited for: `dst` is page-locked and holds the texels after Device::wait_readbacks()
+    void read_pinned_async(void* dst, uint64_t size) const { check(wgb_texture_read_pinned_async(get(), dst, size)); }
     void dump_png(const std::string& path) const { check(wgb_texture_dump_png(get(), path.c_str())); }
 };
 
@@ -287,6 +289,7 @@ struct Device : Handle<wgb_device> {
         check(wgb_device_poll(get(), 1, submission_index, timeout_ns, &out));
         return out;
     }
+    void wait_readbacks() const { check(wgb_device_wait_readbacks(get())); }
     wgb_pass_stats last_pass_stats() const {
         wgb_pass_stats s{};
         check(wgb_device_get_last_pass_stats(get(), &s));

@@ -77,6 +77,39 @@ def test_an_overflow_in_the_middle_of_the_queue_is_rerun_in_order(gpu, monkeypat
     assert not np.array_equal(refs[0].color, refs[1].color)
 
 
+def _corner_camera(a):
+    """The camera of scene `a` followed by a clip-space shrink towards a corner of the frame (piles the mesh into a few tiles)."""
+    scale = np.diag([0.15, 0.15, 1.0, 1.0]).astype(np.float32)
+    shift = np.eye(4, dtype=np.float32)
+    shift[0, 3], shift[1, 3] = -0.8, 0.8
+    cam_a = np.frombuffer(a.bindings[(0, 0)][1].tobytes(), dtype=np.float32).reshape(4, 4)
+    cam_b = (shift @ scale @ cam_a.T).T.astype(np.float32)
+    return np.frombuffer(np.ascontiguousarray(cam_b).tobytes(), dtype=np.uint8).copy()
+
+
+def test_an_overflow_at_the_head_of_the_queue_sees_the_camera_written_before_it(gpu):
+    """The pass that has to run again is the FIRST one in flight, and the camera it was submitted with was written while
+    nothing was in flight; the write queued behind it has gone over that camera by the time the pass is run again."""
+    from oracle import pyoracle
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    a = S.hello_texture(256, 192)
+    b = S.hello_texture(256, 192)
+    b.bindings = dict(b.bindings)
+    b.bindings[(0, 0)] = ("buffer", _corner_camera(a))
+    targets = [dev.create_texture(a.width, a.height, a.color_format) for _ in range(2)]
+    r = SceneRenderer(dev, queue, a, targets=targets)
+    r.render()
+    dev.poll(True)
+    queue.write_buffer(r.resources[(0, 0)], 0, b.bindings[(0, 0)][1])      # nothing in flight
+    r.submit(r.encode(0))                                                   # overflows the bins frame `a` sized
+    queue.write_buffer(r.resources[(0, 0)], 0, a.bindings[(0, 0)][1])      # behind it
+    last = r.submit(r.encode(1))
+    dev.poll(True, last)
+    assert np.array_equal(targets[0].read(), pyoracle.render(b, want_coverage=False).color), "the re-run pass saw the wrong camera"
+    assert np.array_equal(targets[1].read(), pyoracle.render(a, want_coverage=False).color)
+
+
 def test_an_error_in_the_middle_of_the_queue_surfaces_at_poll_and_later_submissions_still_run(gpu):
     from oracle import pyoracle
     from wgpu_cpu_b200 import api
@@ -110,3 +143,46 @@ def test_synchronous_mode_gives_the_same_frames(monkeypatch):
     r = SceneRenderer(dev, queue, sc)
     r.render()
     assert np.array_equal(r.read().color, pyoracle.render(sc, want_coverage=False).color)
+
+
+def _pinned(nbytes):
+    """Page-locked host bytes: torch's allocator on the device; on the software model every host pointer counts as
+    page-locked when CUSIM_ALL_PINNED is set."""
+    import os
+    if os.environ.get("WGB_CUSIM"):
+        return np.empty(nbytes, dtype=np.uint8) if os.environ.get("CUSIM_ALL_PINNED") else None
+    import torch
+    return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True).numpy()
+
+
+def test_a_read_back_that_is_not_waited_for_sees_its_frame_and_holds_back_the_next_writer(gpu):
+    """wgb_texture_read_pinned_async: frame A is read back from target 0 while frame B renders into target 1 and frame C
+    into target 0 again -- C's pass has to wait for the read-back, the host does not."""
+    from oracle import pyoracle
+    from wgpu_cpu_b200 import api
+    from wgpu_cpu_b200.render import SceneRenderer
+    dev, queue = gpu
+    frames = _bunny_frames(3, size=(192, 128))
+    targets = [dev.create_texture(192, 128, frames[0].color_format) for _ in range(2)]
+    r = SceneRenderer(dev, queue, frames[0], targets=targets)
+    r.render()
+    nbytes = 192 * 128 * 4
+    host = _pinned(nbytes)
+    if host is None:
+        with pytest.raises(api.WgpuError):
+            targets[0].read_pinned_async(np.empty(nbytes, dtype=np.uint8))      # pageable memory is refused, not staged
+        return
+    queue.write_buffer(r.resources[(0, 0)], 0, frames[0].bindings[(0, 0)][1])
+    dev.poll(True, r.submit(r.encode(0)))
+    targets[0].read_pinned_async(host)
+    last = 0
+    for k in (1, 2):
+        queue.write_buffer(r.resources[(0, 0)], 0, frames[k].bindings[(0, 0)][1])
+        last = r.submit(r.encode(k))
+    dev.wait_readbacks()
+    refs = [pyoracle.render(sc, want_coverage=False).color for sc in frames]
+    assert np.array_equal(host.reshape(refs[0].shape), refs[0]), "the read-back is not frame A"
+    dev.poll(True, last)
+    assert np.array_equal(targets[1].read(), refs[1])
+    assert np.array_equal(targets[0].read(), refs[2])
+    assert not np.array_equal(refs[0], refs[2])

@@ -296,6 +296,13 @@ class Texture(_Handle):
             out = out.view(np.float32).reshape(self.layers, self.height, self.width)
         return out if self.layers > 1 else out[0]      # array textures come back with the layer axis first
 
+    def read_pinned_async(self, out: np.ndarray):
+        """The read-back that is not waited for: `out` (uint8, page-locked, the texture's byte size) holds the texels
+        after Device.wait_readbacks(); submissions made in between run while the copy does."""
+        if out.dtype != np.uint8 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous uint8 array")
+        _check(_lib.wgb_texture_read_pinned_async(self._h, out.ctypes.data_as(C.c_void_p), C.c_uint64(out.nbytes)))
+
     def dump_png(self, path: str):
         """wgpu_cpu::dump_texture (lib.rs:111-158)."""
         _check(_lib.wgb_texture_dump_png(self._h, os.fsencode(path)))
@@ -506,6 +513,10 @@ class Device(_Handle):
         idx = WHOLE_SIZE if submission_index is None else submission_index
         _check(_lib.wgb_device_poll(self._h, 1 if wait else 0, C.c_uint64(idx), C.c_uint64(timeout_ns), C.byref(out)))
         return out.value
+
+    def wait_readbacks(self):
+        """Waits for every Texture.read_pinned_async started on this device."""
+        _check(_lib.wgb_device_wait_readbacks(self._h))
 
     def create_buffer(self, size: int, usage: int = 0, mapped_at_creation: bool = False) -> Buffer:
         desc = _BufferDescriptor(size, usage, 1 if mapped_at_creation else 0)

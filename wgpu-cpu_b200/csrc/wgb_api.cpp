@@ -338,6 +338,8 @@ struct Device : Object {
     bool compile_only = false;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;    // large host->device uploads (wgb_queue_write_buffer from pinned memory)
+    cudaStream_t readback_stream = nullptr;    // device->host read-backs that are not waited for (wgb_texture_read_pinned_async)
+    cudaEvent_t ev_readback_order = nullptr;
     std::recursive_mutex mu;
     uint32_t band_rank = 0, band_count = 1;
     uint32_t features = 0;                  // WGB_FEATURE_* (opt-in behaviour beyond the reference)
@@ -381,6 +383,27 @@ struct Device : Object {
         wgb_pass_stats stats{};
     };
     std::deque<Unsettled> unsettled;
+    // What the small writes made before the first entry of `unsettled` left in their regions (the latest one per region):
+    // a pass that is run again from the head of the log has to see those regions as they were then, although writes
+    // queued behind it have gone over them since.  A small write is queued behind passes only if its exact region has an
+    // entry here; otherwise the passes are settled first, and the write becomes the entry.  Anything else that changes
+    // a buffer (large writes, copies, unmap) drops the buffer's entries.
+    struct BaseWrite { struct Buffer* buffer; uint64_t offset; std::vector<uint8_t> data; };
+    std::deque<BaseWrite> base_writes;
+    static constexpr size_t BASE_WRITES_MAX = 64;
+    void forget_base_writes(const struct Buffer* b) {
+        for (auto it = base_writes.begin(); it != base_writes.end();) it = (it->buffer == b) ? base_writes.erase(it) : it + 1;
+    }
+    const BaseWrite* find_base_write(const struct Buffer* b, uint64_t offset, uint64_t size) const {
+        for (const auto& w : base_writes) if (w.buffer == b && w.offset == offset && w.data.size() == size) return &w;
+        return nullptr;
+    }
+    void note_base_write(struct Buffer* b, uint64_t offset, const void* data, uint64_t size) {
+        for (auto it = base_writes.begin(); it != base_writes.end();)      // the regions this write goes over (its own too)
+            it = (it->buffer == b && it->offset < offset + size && offset < it->offset + it->data.size()) ? base_writes.erase(it) : it + 1;
+        base_writes.push_back(BaseWrite{b, offset, std::vector<uint8_t>((const uint8_t*)data, (const uint8_t*)data + size)});
+        if (base_writes.size() > BASE_WRITES_MAX) base_writes.pop_front();
+    }
     Unsettled* recording = nullptr;        // the pass being enqueued asynchronously (execute_draw appends its batches)
     bool settling = false;
     uint64_t current_submission = 0;
@@ -401,6 +424,8 @@ struct Device : Object {
         cudaSetDevice(ordinal);
         if (stream) cudaStreamSynchronize(stream);
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+        if (readback_stream) { cudaStreamSynchronize(readback_stream); cudaStreamDestroy(readback_stream); }
+        if (ev_readback_order) cudaEventDestroy(ev_readback_order);
         for (auto& f : inflight) cudaEventDestroy(f.done);
         for (auto& kv : kernel_cache) if (kv.second->module && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->module);
         DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &vcache_raster, &vcache_ndc, &vcache_flags, &slow_list, &clip_records, &big_list, &tile_count, &tile_offset, &tile_cursor, &bins, &coverage, &strip_map, &strip_count};
@@ -432,7 +457,12 @@ struct Buffer : Object {
     cudaEvent_t ev_write = nullptr, ev_use = nullptr;
     bool write_pending = false, use_pending = false;
     uint64_t last_use_submission = 0;       // the latest submission that reads or writes the buffer (guarded by the device mutex)
+    bool external_writers = false;          // wgb_buffer_device_pointer has handed the storage out: its contents are the caller's business
     ~Buffer() override {
+        {
+            std::lock_guard<std::recursive_mutex> dl(device->mu);
+            device->forget_base_writes(this);
+        }
         if (!dptr) return;
         cudaSetDevice(device->ordinal);
         if (write_pending) cudaEventSynchronize(ev_write);
@@ -461,9 +491,18 @@ struct Texture : Object {
     bool imported = false;          // dptr maps another process's allocation (cudaIpcOpenMemHandle)
     cudaTextureObject_t texobj = 0;
     std::mutex mu;
+    // a read-back in flight on the device's read-back stream (wgb_texture_read_pinned_async): work on the render stream
+    // that writes the texture waits for it; guarded by the device mutex
+    cudaEvent_t ev_read = nullptr;
+    bool read_pending = false;
+    void acquire_for_write(cudaStream_t stream) {
+        if (read_pending) { cudaStreamWaitEvent(stream, ev_read, 0); read_pending = false; }
+    }
     ~Texture() override {
         if (device->compile_only) return;
         cudaSetDevice(device->ordinal);
+        if (read_pending) cudaEventSynchronize(ev_read);
+        if (ev_read) cudaEventDestroy(ev_read);
         if (texobj) cudaDestroyTextureObject(texobj);
         if (dptr) { if (imported) cudaIpcCloseMemHandle(dptr); else cudaFree(dptr); }
     }
@@ -1131,6 +1170,8 @@ void settle(Device* dev) {
     auto defer = [&](const Error& e) {
         if (dev->deferred_status == WGB_OK) { dev->deferred_status = e.status; dev->deferred_error = e.what(); }
     };
+    // whatever happens below, the queued writes are what their regions hold when this returns
+    struct Fold { Device* d; std::deque<Device::Unsettled>& w; ~Fold() { for (auto& u : w) if (u.write_buffer) d->note_base_write(u.write_buffer, u.write_offset, u.write_data.data(), u.write_data.size()); } } fold{dev, work};
     size_t i = 0;
     bool overflow = false, error = false;
     for (; i < work.size(); i++) {
@@ -1152,6 +1193,11 @@ void settle(Device* dev) {
     auto rewrite = [&](const Device::Unsettled& u) {
         CUDA_CHECK(cudaMemcpyAsync((char*)u.write_buffer->dptr + u.write_offset, u.write_data.data(), u.write_data.size(), cudaMemcpyHostToDevice, dev->stream));
     };
+    // (first the regions as they were at the head of the log: writes queued behind pass i have gone over them)
+    for (const auto& u : work)
+        if (u.write_buffer)
+            if (const Device::BaseWrite* w = dev->find_base_write(u.write_buffer, u.write_offset, u.write_data.size()))
+                CUDA_CHECK(cudaMemcpyAsync((char*)w->buffer->dptr + w->offset, w->data.data(), w->data.size(), cudaMemcpyHostToDevice, dev->stream));
     for (size_t k = 0; k < i; k++) if (work[k].write_buffer) rewrite(work[k]);
     size_t j = i;
     uint64_t dropped = 0;
@@ -1218,6 +1264,7 @@ void execute_pass_body(Device* dev, const PassCommand& pass) {
         check_size(t);
         REQUIRE(tg.num_color < WGB_MAX_COLOR, "too many colour attachments");
         WgbAttachment& a = tg.color[tg.num_color++];
+        t->acquire_for_write(dev->stream);
         a.ptr = (uint64_t)(uintptr_t)t->dptr + (uint64_t)c.view->base_layer * t->desc.width * t->desc.height * t->bpp;
         a.format = t->desc.format;
         a.bytes_per_texel = t->bpp;
@@ -1233,6 +1280,7 @@ void execute_pass_body(Device* dev, const PassCommand& pass) {
         REQUIRE(t->device.get() == dev, "depth attachment belongs to another device");
         check_size(t);
         tg.has_depth = true;
+        t->acquire_for_write(dev->stream);
         tg.depth.ptr = (uint64_t)(uintptr_t)t->dptr + (uint64_t)pass.depth_view->base_layer * t->desc.width * t->desc.height * 4ull;
         tg.depth.format = t->desc.format;
         tg.depth.bytes_per_texel = 4;
@@ -1346,16 +1394,20 @@ void execute_copy(Device* dev, const CopyCommand& c) {
     };
     switch (c.kind) {
         case CopyCommand::BufferToBuffer:
+            dev->forget_base_writes(c.dst_buffer.get());
             if (c.size) CUDA_CHECK(cudaMemcpyAsync((char*)c.dst_buffer->dptr + c.dst_offset, (char*)c.src_buffer->dptr + c.src_offset, c.size, cudaMemcpyDeviceToDevice, dev->stream));
             break;
         case CopyCommand::ClearBuffer:
+            dev->forget_base_writes(c.dst_buffer.get());
             if (c.size) CUDA_CHECK(cudaMemsetAsync((char*)c.dst_buffer->dptr + c.dst_offset, 0, c.size, dev->stream));
             break;
         case CopyCommand::ClearTexture:
+            c.dst_texture->acquire_for_write(dev->stream);
             CUDA_CHECK(cudaMemsetAsync(c.dst_texture->dptr, 0, c.dst_texture->size, dev->stream));
             break;
         case CopyCommand::BufferToTexture: {
             Texture* t = c.dst_texture.get();
+            t->acquire_for_write(dev->stream);
             const size_t row = (size_t)c.width * t->bpp, pitch = c.bytes_per_row ? c.bytes_per_row : row;
             if (c.width && c.height)
                 CUDA_CHECK(cudaMemcpy2DAsync(tex_ptr(t, c.dst_x, c.dst_y, c.dst_layer), (size_t)t->desc.width * t->bpp,
@@ -1364,6 +1416,7 @@ void execute_copy(Device* dev, const CopyCommand& c) {
         }
         case CopyCommand::TextureToBuffer: {
             Texture* t = c.src_texture.get();
+            dev->forget_base_writes(c.dst_buffer.get());
             const size_t row = (size_t)c.width * t->bpp, pitch = c.bytes_per_row ? c.bytes_per_row : row;
             if (c.width && c.height)
                 CUDA_CHECK(cudaMemcpy2DAsync((char*)c.dst_buffer->dptr + c.dst_offset, pitch, tex_ptr(t, c.src_x, c.src_y, c.src_layer),
@@ -1372,6 +1425,7 @@ void execute_copy(Device* dev, const CopyCommand& c) {
         }
         case CopyCommand::TextureToTexture: {
             Texture *st = c.src_texture.get(), *dt = c.dst_texture.get();
+            dt->acquire_for_write(dev->stream);
             if (c.width && c.height)
                 CUDA_CHECK(cudaMemcpy2DAsync(tex_ptr(dt, c.dst_x, c.dst_y, c.dst_layer), (size_t)dt->desc.width * dt->bpp,
                                              tex_ptr(st, c.src_x, c.src_y, c.src_layer), (size_t)st->desc.width * st->bpp,
@@ -1678,7 +1732,8 @@ wgb_status wgb_buffer_unmap(wgb_buffer buffer) {
         if (b->map_mode == WGB_MAP_MODE_WRITE && b->size && !dev->compile_only) {
             std::lock_guard<std::recursive_mutex> dl(dev->mu);
             dev->make_current();
-        settle(dev);
+            settle(dev);
+            dev->forget_base_writes(b);
             b->acquire_on(dev->stream);
             CUDA_CHECK(cudaMemcpyAsync(b->dptr, b->staging.data(), b->size, cudaMemcpyHostToDevice, dev->stream));
             CUDA_CHECK(cudaStreamSynchronize(dev->stream));
@@ -1698,10 +1753,22 @@ static void write_buffer_impl(wgb_queue queue, wgb_buffer buffer, uint64_t offse
     if (dev->compile_only || size == 0) return;
     std::lock_guard<std::recursive_mutex> dl(dev->mu);
     dev->make_current();
+    const bool small = size <= (64u << 10) && !b->external_writers;
+    if (small && !dev->unsettled.empty()) {
+        // (a region is queued behind passes only with its contents at the head of the log known, and no other extent of
+        // it in the log -- Device::base_writes)
+        bool known = dev->find_base_write(b, offset, size) != nullptr;
+        for (const auto& u : dev->unsettled)
+            if (u.write_buffer == b && !(u.write_offset == offset && u.write_data.size() == size) &&
+                u.write_offset < offset + size && offset < u.write_offset + u.write_data.size()) known = false;
+        if (!known) settle(dev);
+    }
+    if (small && dev->unsettled.empty()) dev->note_base_write(b, offset, data, size);
+    if (!small) dev->forget_base_writes(b);
     if (!dev->unsettled.empty()) {
         // passes are in flight that may have to run again (Device::unsettled): a small write is remembered so that the
         // re-run sees the buffer as it was at that point of the queue; a large one waits for them if they use the buffer
-        if (size <= (64u << 10)) {
+        if (small) {
             dev->unsettled.emplace_back();
             Device::Unsettled& u = dev->unsettled.back();
             u.write_buffer = b;
@@ -1752,6 +1819,11 @@ wgb_status wgb_buffer_device_pointer(wgb_buffer buffer, uint64_t* out_ptr, uint6
     return guarded([&] {
         Buffer* b = from_handle<Buffer>(buffer, "buffer");
         REQUIRE(out_ptr, "out is null");
+        {
+            std::lock_guard<std::recursive_mutex> dl(b->device->mu);
+            b->external_writers = true;
+            b->device->forget_base_writes(b);
+        }
         *out_ptr = (uint64_t)(uintptr_t)b->dptr;
         if (out_size) *out_size = b->size;
     });
@@ -1809,6 +1881,7 @@ wgb_status wgb_queue_write_texture(wgb_queue queue, wgb_texture texture, uint32_
         std::lock_guard<std::recursive_mutex> dl(dev->mu);
         dev->make_current();
         settle(dev);
+        t->acquire_for_write(dev->stream);
         char* dst = (char*)t->dptr + ((uint64_t)y * t->desc.width + x) * t->bpp;
         CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)t->desc.width * t->bpp, data, pitch, row, height, cudaMemcpyHostToDevice, dev->stream));
         CUDA_CHECK(cudaStreamSynchronize(dev->stream));
@@ -1825,6 +1898,43 @@ wgb_status wgb_texture_read(wgb_texture texture, void* dst, uint64_t dst_size) {
         settle(dev);
         CUDA_CHECK(cudaMemcpyAsync(dst, t->dptr, t->size, cudaMemcpyDeviceToHost, dev->stream));
         CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+    });
+}
+// The read-back that is not waited for: the texels as every submission made so far leaves them, copied to page-locked
+// host memory on the device's read-back stream, so that the copy overlaps the submissions that follow (they wait for it
+// only where they write this texture).  `dst` is valid after wgb_device_wait_readbacks.
+wgb_status wgb_texture_read_pinned_async(wgb_texture texture, void* dst, uint64_t dst_size) {
+    return guarded([&] {
+        Texture* t = from_handle<Texture>(texture, "texture");
+        REQUIRE(dst && dst_size >= t->size, "destination too small: need %llu bytes", (unsigned long long)t->size);
+        Device* dev = t->device.get();
+        if (dev->compile_only) fail(WGB_ERROR_DEVICE, "a compile-only device has no texture storage");
+        std::lock_guard<std::recursive_mutex> dl(dev->mu);
+        dev->make_current();
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        REQUIRE(pinned, "wgb_texture_read_pinned_async needs page-locked host memory");
+        settle(dev);            // passes that have to run again have done so before their target is read
+        if (!dev->readback_stream) {
+            CUDA_CHECK(cudaStreamCreateWithFlags(&dev->readback_stream, cudaStreamNonBlocking));
+            CUDA_CHECK(cudaEventCreateWithFlags(&dev->ev_readback_order, cudaEventDisableTiming));
+        }
+        CUDA_CHECK(cudaEventRecord(dev->ev_readback_order, dev->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(dev->readback_stream, dev->ev_readback_order, 0));
+        CUDA_CHECK(cudaMemcpyAsync(dst, t->dptr, t->size, cudaMemcpyDeviceToHost, dev->readback_stream));
+        if (!t->ev_read) CUDA_CHECK(cudaEventCreateWithFlags(&t->ev_read, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventRecord(t->ev_read, dev->readback_stream));
+        t->read_pending = true;
+    });
+}
+wgb_status wgb_device_wait_readbacks(wgb_device device) {
+    return guarded([&] {
+        Device* dev = from_handle<Device>(device, "device");
+        if (dev->compile_only) return;
+        std::lock_guard<std::recursive_mutex> dl(dev->mu);
+        dev->make_current();
+        if (dev->readback_stream) CUDA_CHECK(cudaStreamSynchronize(dev->readback_stream));
     });
 }
 wgb_status wgb_write_png(const char* path, const void* pixels, uint32_t width, uint32_t height, uint32_t channels) {
