@@ -465,6 +465,14 @@ def main():
     geom_ms = float(np.mean([s["geometry_ms"] for s in stats]))
     dev_ms = float(np.mean([s["total_ms"] for s in stats]))
     last = stats[-1]
+    # every rank's share (sort-first: the geometry stage is replicated, the tile work follows the scene): rank 0 reports them all
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([geom_ms, tile_ms, dev_ms, float(last["bin_pairs"]), float(last["fragments"])], device=tdev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"geometry_ms": [round(float(t[0]), 4) for t in allr], "tile_ms": [round(float(t[1]), 4) for t in allr],
+                    "device_ms": [round(float(t[2]), 4) for t in allr], "bin_pairs": [int(t[3]) for t in allr], "fragments": [int(t[4]) for t in allr]}
 
     # ---- e2e: host buffers in, colour target out, every step ----
     e2e = None
@@ -687,7 +695,7 @@ def main():
         "timing": {"method": "CUDA events on the render stream around the K steps (wgb_device_timer_begin / _end), max over ranks"
                              if event_ms else "wall clock between barrier + synchronize (the events failed)",
                    "event_ms_per_step": event_ms / args.steps if event_ms else None, "wall_ms_per_step": wall_dt / args.steps * 1e3},
-        "device_ms_per_step": dev_ms, "geometry_ms": geom_ms, "tile_ms": tile_ms,
+        "device_ms_per_step": dev_ms, "geometry_ms": geom_ms, "tile_ms": tile_ms, "per_rank": per_rank,
         "pass_stats": {k: last[k] for k in ("primitives", "fragments", "shaded", "bin_pairs", "hiz_culled", "big_primitives",
                                             "clipped_primitives", "clip_records", "kernel_launches", "replays")},
         "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "parity": parity, "clocks": clocks,

@@ -337,6 +337,35 @@ struct Device : Object {
     int ordinal = -1;
     bool compile_only = false;
     cudaStream_t stream = nullptr;
+    // The tile kernels of passes that are not waited for run on their own stream, so that the geometry stage of the next
+    // pass (render stream, its own set of work buffers) runs beside the tile kernel of this one: the first is bound by
+    // latency and memory, the second by instruction issue.  Everything else the render stream does first waits for the
+    // tile stream (joined()); what only has to FOLLOW the queued work -- the events that mark a submission done or a
+    // buffer used -- is recorded behind both (tail()).  WGB_NO_OVERLAP=1 keeps the tile kernels on the render stream.
+    cudaStream_t tile_stream = nullptr;
+    cudaEvent_t ev_tiles = nullptr, ev_render_pos = nullptr;
+    bool tiles_ahead = false;              // the tile stream holds work the render stream has not waited for
+    bool overlap_stages = true;
+    // The tile stream pays only where the next geometry stage follows without anything else on the render stream in
+    // between (a queue.write_buffer of the next frame's camera makes the render stream wait for the tile kernel, which
+    // reads the old one; the two cross-stream waits then cost more than nothing at all).  A draw takes the tile stream
+    // when the draw before it was followed by nothing but this one.
+    uint32_t ops_since_tile = 1;
+    cudaStream_t joined() {
+        ops_since_tile++;
+        if (tiles_ahead) {
+            cudaEventRecord(ev_tiles, tile_stream);
+            cudaStreamWaitEvent(stream, ev_tiles, 0);
+            tiles_ahead = false;
+        }
+        return stream;
+    }
+    cudaStream_t tail() {
+        if (!tiles_ahead) return stream;
+        cudaEventRecord(ev_render_pos, stream);
+        cudaStreamWaitEvent(tile_stream, ev_render_pos, 0);
+        return tile_stream;
+    }
     cudaStream_t copy_stream = nullptr;    // large host->device uploads (wgb_queue_write_buffer from pinned memory)
     cudaStream_t readback_stream = nullptr;    // device->host read-backs that are not waited for (wgb_texture_read_pinned_async)
     cudaEvent_t ev_readback_order = nullptr;
@@ -353,7 +382,22 @@ struct Device : Object {
     std::map<std::pair<uint32_t, uint32_t>, uint32_t> bin_cap_hint;   // (primitives, band tiles) of a draw -> slots per tile it needed
     bool no_direct_bins = false;
     bool small_work_buffers = false;       // testing knob: start the clip-record and big lists at 2 entries so that both overflow-and-replay paths run
-    DevBuf counters, prim_box, setup_cache, vcache_raster, vcache_ndc, vcache_flags, slow_list, clip_records, big_list, tile_count, tile_offset, tile_cursor, bins, coverage, strip_map, strip_count;
+    // the buffers a draw's kernels hand to each other; two sets, used in turn by the draws that are not waited for, so
+    // that a geometry stage can fill one while the tile kernel of the draw before still reads the other
+    struct WorkSet {
+        DevBuf counters, prim_box, setup_cache, vcache_raster, vcache_ndc, vcache_flags, slow_list, clip_records, big_list, tile_offset, tile_cursor, bins;
+        cudaEvent_t ev_free = nullptr;     // on the tile stream, behind the tile kernel that read the set last
+        bool busy = false;
+        void release() {
+            DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &vcache_raster, &vcache_ndc, &vcache_flags, &slow_list, &clip_records, &big_list, &tile_offset, &tile_cursor, &bins};
+            for (DevBuf* b : bufs) b->release();
+            if (ev_free) cudaEventDestroy(ev_free);
+            ev_free = nullptr;
+        }
+    };
+    WorkSet work[2];
+    uint32_t work_next = 0;
+    DevBuf coverage, strip_map, strip_count;
     WgbCounters* host_counters = nullptr;   // pinned
     uint32_t clip_capacity = 0, big_capacity = 0;
     bool coverage_capture = false;
@@ -371,7 +415,7 @@ struct Device : Object {
     // it, synchronously.  (Passes that load their attachments, strips with primitive restart and the coverage capture
     // of the parity tests are executed synchronously as before; so is everything with WGB_SYNC_SUBMIT=1.)
     bool async_submit = true;
-    struct PendingBatch { WgbCounters* host; cudaEvent_t ev[3]; uint32_t np, band_tiles; };
+    struct PendingBatch { WgbCounters* host; cudaEvent_t ev[4]; uint32_t np, band_tiles; };      // events: geometry stage begins / ends, tile kernel ends / begins
     struct Unsettled {
         uint64_t submission = 0;
         std::shared_ptr<struct PassCommand> pass;              // a render pass that was enqueued without waiting, or ...
@@ -423,12 +467,16 @@ struct Device : Object {
         if (compile_only) return;
         cudaSetDevice(ordinal);
         if (stream) cudaStreamSynchronize(stream);
+        if (tile_stream) { cudaStreamSynchronize(tile_stream); cudaStreamDestroy(tile_stream); }
+        if (ev_tiles) cudaEventDestroy(ev_tiles);
+        if (ev_render_pos) cudaEventDestroy(ev_render_pos);
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         if (readback_stream) { cudaStreamSynchronize(readback_stream); cudaStreamDestroy(readback_stream); }
         if (ev_readback_order) cudaEventDestroy(ev_readback_order);
         for (auto& f : inflight) cudaEventDestroy(f.done);
         for (auto& kv : kernel_cache) if (kv.second->module && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->module);
-        DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &vcache_raster, &vcache_ndc, &vcache_flags, &slow_list, &clip_records, &big_list, &tile_count, &tile_offset, &tile_cursor, &bins, &coverage, &strip_map, &strip_count};
+        for (auto& w : work) w.release();
+        DevBuf* bufs[] = {&coverage, &strip_map, &strip_count};
         for (DevBuf* b : bufs) b->release();
         if (host_counters) cudaFreeHost(host_counters);
         if (counter_ring) cudaFreeHost(counter_ring);
@@ -782,12 +830,13 @@ struct PassState {   // render_pass/state.rs:58-75
     uint32_t sc[4];
 };
 
-void launch(Device* dev, CUfunction f, dim3 grid, dim3 block, WgbDraw* d) {
+void launch_on(Device* dev, cudaStream_t stream, CUfunction f, dim3 grid, dim3 block, WgbDraw* d) {
     void* args[] = {d};
-    CUresult r = g_drv.LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, 0, (CUstream)dev->stream, args, nullptr);
+    CUresult r = g_drv.LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, 0, (CUstream)stream, args, nullptr);
     if (r != CUDA_SUCCESS) fail(WGB_ERROR_DEVICE, "kernel launch failed: %s", cu_error(r));
     dev->last_stats.kernel_launches++;
 }
+void launch(Device* dev, CUfunction f, dim3 grid, dim3 block, WgbDraw* d) { launch_on(dev, dev->joined(), f, grid, block, d); }
 
 void band_rows(const Device* dev, uint32_t tiles_y, uint32_t& ty0, uint32_t& ty1) {
     // contiguous bands of whole tile rows, the first (tiles_y % n) bands one row taller
@@ -829,7 +878,7 @@ bool batch_result(Device* dev, const Device::PendingBatch& pb, uint32_t np, uint
     const WgbCounters c = *pb.host;
     float g_ms = 0, t_ms = 0;
     cudaEventElapsedTime(&g_ms, pb.ev[0], pb.ev[1]);
-    cudaEventElapsedTime(&t_ms, pb.ev[1], pb.ev[2]);
+    cudaEventElapsedTime(&t_ms, pb.ev[3], pb.ev[2]);
     stats.geometry_ms += g_ms;
     stats.tile_ms += t_ms;
     stats.total_ms += g_ms + t_ms;
@@ -996,14 +1045,14 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
         dev->strip_map.ensure((size_t)ppi * ps * 4);
         dev->strip_count.ensure(4);
         d.strip_map = dev->strip_map.addr();
-        CUDA_CHECK(cudaMemsetAsync(dev->strip_map.p, 0xFF, (size_t)ppi * ps * 4, dev->stream));
+        CUDA_CHECK(cudaMemsetAsync(dev->strip_map.p, 0xFF, (size_t)ppi * ps * 4, dev->joined()));
         void* args[] = {&d, &dev->strip_count.p};
-        CUresult r = g_drv.LaunchKernel(ks->strip_map, 1, 1, 1, 32, 1, 1, 0, (CUstream)dev->stream, args, nullptr);
+        CUresult r = g_drv.LaunchKernel(ks->strip_map, 1, 1, 1, 32, 1, 1, 0, (CUstream)dev->joined(), args, nullptr);
         if (r != CUDA_SUCCESS) fail(WGB_ERROR_DEVICE, "strip map launch failed: %s", cu_error(r));
         dev->last_stats.kernel_launches++;
         uint32_t n = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&n, dev->strip_count.p, 4, cudaMemcpyDeviceToHost, dev->stream));
-        CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+        CUDA_CHECK(cudaMemcpyAsync(&n, dev->strip_count.p, 4, cudaMemcpyDeviceToHost, dev->joined()));
+        CUDA_CHECK(cudaStreamSynchronize(dev->joined()));
         ppi = n;
         if (ppi == 0) return;
     }
@@ -1013,7 +1062,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
 
     if (dev->coverage_capture && (dev->coverage_w != tg.width || dev->coverage_h != tg.height)) {
         dev->coverage.ensure((size_t)tg.width * tg.height * 4);
-        CUDA_CHECK(cudaMemsetAsync(dev->coverage.p, 0, (size_t)tg.width * tg.height * 4, dev->stream));
+        CUDA_CHECK(cudaMemsetAsync(dev->coverage.p, 0, (size_t)tg.width * tg.height * 4, dev->joined()));
         dev->coverage_w = tg.width; dev->coverage_h = tg.height;
     }
     d.coverage = dev->coverage.addr();
@@ -1028,21 +1077,26 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             const uint32_t clip_cap = dev->small_work_buffers ? dev->clip_capacity : std::max<uint32_t>(dev->clip_capacity, np / 16);
             const uint32_t big_cap = dev->small_work_buffers ? std::max<uint32_t>(dev->big_capacity, 2) : std::max<uint32_t>(dev->big_capacity, std::max<uint32_t>(65536, np / 8));
             dev->clip_capacity = clip_cap; dev->big_capacity = big_cap;
+            // a draw that is not waited for: geometry stage on the render stream without waiting for the tile stream, in
+            // the work set the draw before it does not use; its tile kernel follows on the tile stream
+            const bool async = dev->recording != nullptr;
+            const bool two_streams = async && dev->overlap_stages && dev->ops_since_tile == 0;
+            Device::WorkSet& ws = dev->work[two_streams ? (dev->work_next++ & 1u) : 0u];
             // the counters and the per-tile pair counts share one buffer: one memset clears both
-            dev->counters.ensure(sizeof(WgbCounters) + (size_t)(band_tiles + 1) * 4);
-            dev->prim_box.ensure((size_t)np * 4);
-            if (!vcache_n) dev->setup_cache.ensure((size_t)np * 48);
+            ws.counters.ensure(sizeof(WgbCounters) + (size_t)(band_tiles + 1) * 4);
+            ws.prim_box.ensure((size_t)np * 4);
+            if (!vcache_n) ws.setup_cache.ensure((size_t)np * 48);
             if (vcache_n) {
                 const size_t nv = (size_t)vcache_n * sc.instance_count;
-                dev->vcache_raster.ensure(nv * 16); dev->vcache_ndc.ensure(nv * 8); dev->vcache_flags.ensure(nv);
-                d.vcache_raster = dev->vcache_raster.addr(); d.vcache_ndc = dev->vcache_ndc.addr(); d.vcache_flags = dev->vcache_flags.addr();
+                ws.vcache_raster.ensure(nv * 16); ws.vcache_ndc.ensure(nv * 8); ws.vcache_flags.ensure(nv);
+                d.vcache_raster = ws.vcache_raster.addr(); d.vcache_ndc = ws.vcache_ndc.addr(); d.vcache_flags = ws.vcache_flags.addr();
                 d.vcache_count = (uint32_t)vcache_n;
             }
-            dev->slow_list.ensure((size_t)np * 4);
-            dev->clip_records.ensure((size_t)clip_cap * sizeof(WgbClipRecord));
-            dev->big_list.ensure((size_t)big_cap * sizeof(WgbBigEntry));
-            dev->tile_offset.ensure((size_t)(band_tiles + 1) * 4);
-            dev->tile_cursor.ensure((size_t)(band_tiles + 1) * 4);
+            ws.slow_list.ensure((size_t)np * 4);
+            ws.clip_records.ensure((size_t)clip_cap * sizeof(WgbClipRecord));
+            ws.big_list.ensure((size_t)big_cap * sizeof(WgbBigEntry));
+            ws.tile_offset.ensure((size_t)(band_tiles + 1) * 4);
+            ws.tile_cursor.ensure((size_t)(band_tiles + 1) * 4);
             // direct binning: a fixed number of slots per tile, sized from what this draw shape needed before
             // (or twice the mean on first sight); the geometry kernels then store the bin entries themselves and
             // the scan + fill kernels are skipped.  A tile that overflows flags the pass and the draw is replayed.
@@ -1056,15 +1110,14 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 if (!dev->no_direct_bins && band_tiles > 0 && (uint64_t)band_tiles * cap * 4 <= (1ull << 30)) bin_cap = (uint32_t)cap;
             }
             d.bin_cap = bin_cap;
-            dev->bins.ensure(bin_cap ? (size_t)band_tiles * bin_cap * 4 : ((size_t)np + clip_cap) * WGB_SMALL_MAX_TILES * 4);
-            d.counters = dev->counters.addr(); d.prim_box = dev->prim_box.addr(); d.slow_list = dev->slow_list.addr();
-            d.setup_cache = dev->setup_cache.addr();
-            d.clip_records = dev->clip_records.addr(); d.clip_capacity = clip_cap;
-            d.big_list = dev->big_list.addr(); d.big_capacity = big_cap;
-            d.tile_count = dev->counters.addr() + sizeof(WgbCounters); d.tile_offset = dev->tile_offset.addr(); d.tile_cursor = dev->tile_cursor.addr();
-            d.bins = dev->bins.addr();
+            ws.bins.ensure(bin_cap ? (size_t)band_tiles * bin_cap * 4 : ((size_t)np + clip_cap) * WGB_SMALL_MAX_TILES * 4);
+            d.counters = ws.counters.addr(); d.prim_box = ws.prim_box.addr(); d.slow_list = ws.slow_list.addr();
+            d.setup_cache = ws.setup_cache.addr();
+            d.clip_records = ws.clip_records.addr(); d.clip_capacity = clip_cap;
+            d.big_list = ws.big_list.addr(); d.big_capacity = big_cap;
+            d.tile_count = ws.counters.addr() + sizeof(WgbCounters); d.tile_offset = ws.tile_offset.addr(); d.tile_cursor = ws.tile_cursor.addr();
+            d.bins = ws.bins.addr();
 
-            const bool async = dev->recording != nullptr;
             d.poison = async ? dev->poison.addr() : 0;
             Device::PendingBatch pb{};
             if (async) {
@@ -1075,31 +1128,48 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 pb.host = dev->host_counters;
                 for (int k = 0; k < 3; k++) pb.ev[k] = dev->ev[k];
             }
-            CUDA_CHECK(cudaEventRecord(pb.ev[0], dev->stream));
-            CUDA_CHECK(cudaMemsetAsync(dev->counters.p, 0, sizeof(WgbCounters) + (size_t)(band_tiles + 1) * 4, dev->stream));
+            cudaStream_t gs, ts;
+            if (two_streams) {
+                gs = dev->stream;
+                ts = dev->tile_stream;
+                if (ws.busy) { CUDA_CHECK(cudaStreamWaitEvent(gs, ws.ev_free, 0)); ws.busy = false; }
+            } else gs = ts = dev->joined();
+            CUDA_CHECK(cudaEventRecord(pb.ev[0], gs));
+            CUDA_CHECK(cudaMemsetAsync(ws.counters.p, 0, sizeof(WgbCounters) + (size_t)(band_tiles + 1) * 4, gs));
             const uint32_t gblocks = (np + 255) / 256;
             if (vcache_n) {
                 // the cache holds every instance of the draw, so it is filled once, by the first batch
-                if (base == 0) launch(dev, ks->vertex, dim3((uint32_t)(((uint64_t)vcache_n * sc.instance_count + 255) / 256)), dim3(256), &d);
-                launch(dev, ks->geometry_cached, dim3(((np >= WGB_GEOMETRY_PAIRED_MIN ? (np + 1) / 2 : np) + 255) / 256), dim3(256), &d);      // two primitives per thread of a large batch
-            } else launch(dev, ks->geometry, dim3(gblocks), dim3(256), &d);
-            launch(dev, ks->clip, dim3(std::min<uint32_t>(std::max<uint32_t>((np + 127) / 128, 148), 148 * 8)), dim3(128), &d);      // (the kernel deals its list out over the warps it finds)
+                if (base == 0) launch_on(dev, gs, ks->vertex, dim3((uint32_t)(((uint64_t)vcache_n * sc.instance_count + 255) / 256)), dim3(256), &d);
+                launch_on(dev, gs, ks->geometry_cached, dim3(((np >= WGB_GEOMETRY_PAIRED_MIN ? (np + 1) / 2 : np) + 255) / 256), dim3(256), &d);      // two primitives per thread of a large batch
+            } else launch_on(dev, gs, ks->geometry, dim3(gblocks), dim3(256), &d);
+            launch_on(dev, gs, ks->clip, dim3(std::min<uint32_t>(std::max<uint32_t>((np + 127) / 128, 148), 148 * 8)), dim3(128), &d);      // (the kernel deals its list out over the warps it finds)
             if (!bin_cap) {
-                launch(dev, ks->scan, dim3(1), dim3(1024), &d);
-                launch(dev, ks->fill, dim3(gblocks), dim3(256), &d);
+                launch_on(dev, gs, ks->scan, dim3(1), dim3(1024), &d);
+                launch_on(dev, gs, ks->fill, dim3(gblocks), dim3(256), &d);
             }
-            if (ks->ordered) launch(dev, ks->big_sort, dim3(1), dim3(1024), &d);
-            CUDA_CHECK(cudaEventRecord(pb.ev[1], dev->stream));
-            launch(dev, ks->tile, dim3(d.tiles_x, d.band_ty1 - d.band_ty0), dim3(256), &d);
-            CUDA_CHECK(cudaEventRecord(pb.ev[2], dev->stream));
-            CUDA_CHECK(cudaMemcpyAsync(pb.host, dev->counters.p, sizeof(WgbCounters), cudaMemcpyDeviceToHost, dev->stream));
+            if (ks->ordered) launch_on(dev, gs, ks->big_sort, dim3(1), dim3(1024), &d);
+            CUDA_CHECK(cudaEventRecord(pb.ev[1], gs));
+            if (two_streams) {
+                CUDA_CHECK(cudaStreamWaitEvent(ts, pb.ev[1], 0));
+                CUDA_CHECK(cudaEventRecord(pb.ev[3], ts));
+            } else pb.ev[3] = pb.ev[1];
+            launch_on(dev, ts, ks->tile, dim3(d.tiles_x, d.band_ty1 - d.band_ty0), dim3(256), &d);
+            CUDA_CHECK(cudaEventRecord(pb.ev[2], ts));
+            CUDA_CHECK(cudaMemcpyAsync(pb.host, ws.counters.p, sizeof(WgbCounters), cudaMemcpyDeviceToHost, ts));
+            if (two_streams) {
+                if (!ws.ev_free) CUDA_CHECK(cudaEventCreateWithFlags(&ws.ev_free, cudaEventDisableTiming));
+                CUDA_CHECK(cudaEventRecord(ws.ev_free, ts));
+                ws.busy = true;
+                dev->tiles_ahead = true;
+            }
+            dev->ops_since_tile = 0;
             if (async) {
                 // not waited for: settle() looks at the counters when somebody waits, and re-runs the pass if this batch failed
                 dev->recording->batches.push_back(pb);
                 dev->last_stats.primitives += np;
                 break;
             }
-            CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+            CUDA_CHECK(cudaStreamSynchronize(dev->joined()));
             if (batch_result(dev, pb, np, band_tiles, dev->last_stats)) {
                 // the tile kernel saw the overflow flag and left the attachments untouched: the buffers have grown, replay
                 if (attempt >= 8) fail(WGB_ERROR_OUT_OF_MEMORY, "work buffers still too small after %d replays", attempt);
@@ -1164,7 +1234,7 @@ void settle(Device* dev) {
     if (dev->unsettled.empty() || dev->settling) return;
     dev->settling = true;
     struct Done { Device* d; ~Done() { d->settling = false; d->counter_ring_used = 0; d->event_pool_used = 0; } } done{dev};
-    CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+    CUDA_CHECK(cudaStreamSynchronize(dev->joined()));
     std::deque<Device::Unsettled> work;
     work.swap(dev->unsettled);
     auto defer = [&](const Error& e) {
@@ -1189,15 +1259,15 @@ void settle(Device* dev) {
     // small writes that were queued since the last settle back into their order, then run pass i (unless it failed
     // with an error: then the rest of its submission is dropped, as when the error is raised synchronously) and
     // everything behind it again, waiting for every draw.
-    CUDA_CHECK(cudaMemsetAsync(dev->poison.p, 0, 4, dev->stream));
+    CUDA_CHECK(cudaMemsetAsync(dev->poison.p, 0, 4, dev->joined()));
     auto rewrite = [&](const Device::Unsettled& u) {
-        CUDA_CHECK(cudaMemcpyAsync((char*)u.write_buffer->dptr + u.write_offset, u.write_data.data(), u.write_data.size(), cudaMemcpyHostToDevice, dev->stream));
+        CUDA_CHECK(cudaMemcpyAsync((char*)u.write_buffer->dptr + u.write_offset, u.write_data.data(), u.write_data.size(), cudaMemcpyHostToDevice, dev->joined()));
     };
     // (first the regions as they were at the head of the log: writes queued behind pass i have gone over them)
     for (const auto& u : work)
         if (u.write_buffer)
             if (const Device::BaseWrite* w = dev->find_base_write(u.write_buffer, u.write_offset, u.write_data.size()))
-                CUDA_CHECK(cudaMemcpyAsync((char*)w->buffer->dptr + w->offset, w->data.data(), w->data.size(), cudaMemcpyHostToDevice, dev->stream));
+                CUDA_CHECK(cudaMemcpyAsync((char*)w->buffer->dptr + w->offset, w->data.data(), w->data.size(), cudaMemcpyHostToDevice, dev->joined()));
     for (size_t k = 0; k < i; k++) if (work[k].write_buffer) rewrite(work[k]);
     size_t j = i;
     uint64_t dropped = 0;
@@ -1211,7 +1281,7 @@ void settle(Device* dev) {
             if (j == i) dev->last_stats.replays++;          // the attempt that overflowed
         } catch (const Error& e) { defer(e); dropped = u.submission; }
     }
-    CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+    CUDA_CHECK(cudaStreamSynchronize(dev->joined()));
 }
 
 void execute_pass(Device* dev, const std::shared_ptr<PassCommand>& pass_ptr, bool allow_async) {
@@ -1224,7 +1294,7 @@ void execute_pass(Device* dev, const std::shared_ptr<PassCommand>& pass_ptr, boo
         for (const SubCommand& sc : pass.sub) draws += (sc.kind == SubCommand::Draw || sc.kind == SubCommand::DrawIndexed) ? 1 : 0;
         if (dev->counter_ring_used + draws + 8 > Device::COUNTER_RING) settle(dev);
         if (!dev->counter_ring) CUDA_CHECK(cudaMallocHost((void**)&dev->counter_ring, sizeof(WgbCounters) * Device::COUNTER_RING));
-        if (!dev->poison.p) { dev->poison.ensure(4); CUDA_CHECK(cudaMemsetAsync(dev->poison.p, 0, 4, dev->stream)); }
+        if (!dev->poison.p) { dev->poison.ensure(4); CUDA_CHECK(cudaMemsetAsync(dev->poison.p, 0, 4, dev->joined())); }
         dev->unsettled.emplace_back();
         dev->unsettled.back().submission = dev->current_submission;
         dev->unsettled.back().pass = pass_ptr;
@@ -1264,7 +1334,7 @@ void execute_pass_body(Device* dev, const PassCommand& pass) {
         check_size(t);
         REQUIRE(tg.num_color < WGB_MAX_COLOR, "too many colour attachments");
         WgbAttachment& a = tg.color[tg.num_color++];
-        t->acquire_for_write(dev->stream);
+        t->acquire_for_write(dev->stream);      // (a wait only: the render stream is not joined with the tile stream for it)
         a.ptr = (uint64_t)(uintptr_t)t->dptr + (uint64_t)c.view->base_layer * t->desc.width * t->desc.height * t->bpp;
         a.format = t->desc.format;
         a.bytes_per_texel = t->bpp;
@@ -1298,7 +1368,7 @@ void execute_pass_body(Device* dev, const PassCommand& pass) {
 
     if (dev->coverage_capture && have_size) {
         dev->coverage.ensure((size_t)tg.width * tg.height * 4);
-        CUDA_CHECK(cudaMemsetAsync(dev->coverage.p, 0, (size_t)tg.width * tg.height * 4, dev->stream));
+        CUDA_CHECK(cudaMemsetAsync(dev->coverage.p, 0, (size_t)tg.width * tg.height * 4, dev->joined()));
         dev->coverage_w = tg.width; dev->coverage_h = tg.height;
     }
 
@@ -1377,10 +1447,10 @@ void execute_pass_body(Device* dev, const PassCommand& pass) {
             d.poison = dev->poison.addr();
             launch(dev, ks->clear, dim3(148 * 4), dim3(256), &d);
         } else {
-            CUDA_CHECK(cudaEventRecord(dev->ev[0], dev->stream));
+            CUDA_CHECK(cudaEventRecord(dev->ev[0], dev->joined()));
             launch(dev, ks->clear, dim3(148 * 4), dim3(256), &d);
-            CUDA_CHECK(cudaEventRecord(dev->ev[2], dev->stream));
-            CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+            CUDA_CHECK(cudaEventRecord(dev->ev[2], dev->joined()));
+            CUDA_CHECK(cudaStreamSynchronize(dev->joined()));
             float ms = 0;
             cudaEventElapsedTime(&ms, dev->ev[0], dev->ev[2]);
             dev->last_stats.total_ms += ms;
@@ -1395,23 +1465,23 @@ void execute_copy(Device* dev, const CopyCommand& c) {
     switch (c.kind) {
         case CopyCommand::BufferToBuffer:
             dev->forget_base_writes(c.dst_buffer.get());
-            if (c.size) CUDA_CHECK(cudaMemcpyAsync((char*)c.dst_buffer->dptr + c.dst_offset, (char*)c.src_buffer->dptr + c.src_offset, c.size, cudaMemcpyDeviceToDevice, dev->stream));
+            if (c.size) CUDA_CHECK(cudaMemcpyAsync((char*)c.dst_buffer->dptr + c.dst_offset, (char*)c.src_buffer->dptr + c.src_offset, c.size, cudaMemcpyDeviceToDevice, dev->joined()));
             break;
         case CopyCommand::ClearBuffer:
             dev->forget_base_writes(c.dst_buffer.get());
-            if (c.size) CUDA_CHECK(cudaMemsetAsync((char*)c.dst_buffer->dptr + c.dst_offset, 0, c.size, dev->stream));
+            if (c.size) CUDA_CHECK(cudaMemsetAsync((char*)c.dst_buffer->dptr + c.dst_offset, 0, c.size, dev->joined()));
             break;
         case CopyCommand::ClearTexture:
-            c.dst_texture->acquire_for_write(dev->stream);
-            CUDA_CHECK(cudaMemsetAsync(c.dst_texture->dptr, 0, c.dst_texture->size, dev->stream));
+            c.dst_texture->acquire_for_write(dev->joined());
+            CUDA_CHECK(cudaMemsetAsync(c.dst_texture->dptr, 0, c.dst_texture->size, dev->joined()));
             break;
         case CopyCommand::BufferToTexture: {
             Texture* t = c.dst_texture.get();
-            t->acquire_for_write(dev->stream);
+            t->acquire_for_write(dev->joined());
             const size_t row = (size_t)c.width * t->bpp, pitch = c.bytes_per_row ? c.bytes_per_row : row;
             if (c.width && c.height)
                 CUDA_CHECK(cudaMemcpy2DAsync(tex_ptr(t, c.dst_x, c.dst_y, c.dst_layer), (size_t)t->desc.width * t->bpp,
-                                             (char*)c.src_buffer->dptr + c.src_offset, pitch, row, c.height, cudaMemcpyDeviceToDevice, dev->stream));
+                                             (char*)c.src_buffer->dptr + c.src_offset, pitch, row, c.height, cudaMemcpyDeviceToDevice, dev->joined()));
             break;
         }
         case CopyCommand::TextureToBuffer: {
@@ -1420,16 +1490,16 @@ void execute_copy(Device* dev, const CopyCommand& c) {
             const size_t row = (size_t)c.width * t->bpp, pitch = c.bytes_per_row ? c.bytes_per_row : row;
             if (c.width && c.height)
                 CUDA_CHECK(cudaMemcpy2DAsync((char*)c.dst_buffer->dptr + c.dst_offset, pitch, tex_ptr(t, c.src_x, c.src_y, c.src_layer),
-                                             (size_t)t->desc.width * t->bpp, row, c.height, cudaMemcpyDeviceToDevice, dev->stream));
+                                             (size_t)t->desc.width * t->bpp, row, c.height, cudaMemcpyDeviceToDevice, dev->joined()));
             break;
         }
         case CopyCommand::TextureToTexture: {
             Texture *st = c.src_texture.get(), *dt = c.dst_texture.get();
-            dt->acquire_for_write(dev->stream);
+            dt->acquire_for_write(dev->joined());
             if (c.width && c.height)
                 CUDA_CHECK(cudaMemcpy2DAsync(tex_ptr(dt, c.dst_x, c.dst_y, c.dst_layer), (size_t)dt->desc.width * dt->bpp,
                                              tex_ptr(st, c.src_x, c.src_y, c.src_layer), (size_t)st->desc.width * st->bpp,
-                                             (size_t)c.width * st->bpp, c.height, cudaMemcpyDeviceToDevice, dev->stream));
+                                             (size_t)c.width * st->bpp, c.height, cudaMemcpyDeviceToDevice, dev->joined()));
             break;
         }
     }
@@ -1586,6 +1656,10 @@ wgb_status wgb_adapter_request_device(wgb_adapter adapter, const wgb_device_desc
             if (p.major != 10) fail(WGB_ERROR_DEVICE, "device %d is sm_%d%d; this backend is built for sm_100a (B200) only", ord, p.major, p.minor);
             load_driver_api();
             CUDA_CHECK(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
+            CUDA_CHECK(cudaStreamCreateWithFlags(&dev->tile_stream, cudaStreamNonBlocking));     // (stream priorities either way round: no difference measured)
+            CUDA_CHECK(cudaEventCreateWithFlags(&dev->ev_tiles, cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&dev->ev_render_pos, cudaEventDisableTiming));
+            dev->overlap_stages = getenv("WGB_NO_OVERLAP") == nullptr;
             CUDA_CHECK(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
             dev->no_direct_bins = getenv("WGB_NO_DIRECT_BINS") != nullptr;      // testing knob: always count / scan / fill
             dev->small_work_buffers = getenv("WGB_TEST_SMALL_WORK_BUFFERS") != nullptr;
@@ -1678,7 +1752,7 @@ wgb_status wgb_device_create_buffer(wgb_device device, const wgb_buffer_descript
         if (!dev->compile_only) {
             dev->make_current();
             CUDA_CHECK(cudaMalloc(&b->dptr, std::max<uint64_t>(desc->size, 16)));
-            CUDA_CHECK(cudaMemsetAsync(b->dptr, 0, std::max<uint64_t>(desc->size, 16), dev->stream));   // Vec<u8> is zero-initialised (buffer.rs:31-35)
+            CUDA_CHECK(cudaMemsetAsync(b->dptr, 0, std::max<uint64_t>(desc->size, 16), dev->joined()));   // Vec<u8> is zero-initialised (buffer.rs:31-35)
         }
         if (desc->mapped_at_creation) {
             b->staging.assign(desc->size, 0);
@@ -1702,8 +1776,8 @@ wgb_status wgb_buffer_map_async(wgb_buffer buffer, uint32_t mode, uint64_t offse
             std::lock_guard<std::recursive_mutex> dl(dev->mu);
             dev->make_current();
         settle(dev);
-            b->acquire_on(dev->stream);
-            CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+            b->acquire_on(dev->joined());
+            CUDA_CHECK(cudaStreamSynchronize(dev->joined()));
             // both modes start from the buffer's contents (a write guard derefs to the live Vec<u8>)
             if (b->size) CUDA_CHECK(cudaMemcpy(b->staging.data(), b->dptr, b->size, cudaMemcpyDeviceToHost));
         }
@@ -1734,10 +1808,10 @@ wgb_status wgb_buffer_unmap(wgb_buffer buffer) {
             dev->make_current();
             settle(dev);
             dev->forget_base_writes(b);
-            b->acquire_on(dev->stream);
-            CUDA_CHECK(cudaMemcpyAsync(b->dptr, b->staging.data(), b->size, cudaMemcpyHostToDevice, dev->stream));
-            CUDA_CHECK(cudaStreamSynchronize(dev->stream));
-            b->mark_used(dev->stream);
+            b->acquire_on(dev->joined());
+            CUDA_CHECK(cudaMemcpyAsync(b->dptr, b->staging.data(), b->size, cudaMemcpyHostToDevice, dev->joined()));
+            CUDA_CHECK(cudaStreamSynchronize(dev->joined()));
+            b->mark_used(dev->joined());
         }
         b->mapped = false;
         std::vector<uint8_t>().swap(b->staging);
@@ -1794,9 +1868,9 @@ static void write_buffer_impl(wgb_queue queue, wgb_buffer buffer, uint64_t offse
         if (!async) CUDA_CHECK(cudaEventSynchronize(b->ev_write));
     } else {
         // pageable source: the runtime stages the bytes before cudaMemcpyAsync returns, so `data` may be reused
-        b->acquire_on(dev->stream);
-        CUDA_CHECK(cudaMemcpyAsync((char*)b->dptr + offset, data, size, cudaMemcpyHostToDevice, dev->stream));
-        b->mark_used(dev->stream);
+        b->acquire_on(dev->joined());
+        CUDA_CHECK(cudaMemcpyAsync((char*)b->dptr + offset, data, size, cudaMemcpyHostToDevice, dev->joined()));
+        b->mark_used(dev->joined());
     }
 }
 wgb_status wgb_queue_write_buffer(wgb_queue queue, wgb_buffer buffer, uint64_t offset, const void* data, uint64_t size) {
@@ -1848,7 +1922,7 @@ wgb_status wgb_device_create_texture(wgb_device device, const wgb_texture_descri
         if (!dev->compile_only) {
             dev->make_current();
             CUDA_CHECK(cudaMalloc(&t->dptr, t->size));
-            CUDA_CHECK(cudaMemsetAsync(t->dptr, 0, t->size, dev->stream));
+            CUDA_CHECK(cudaMemsetAsync(t->dptr, 0, t->size, dev->joined()));
         }
         t->rc.fetch_add(1);
         *out = to_handle<wgb_texture>(t.get());
@@ -1881,10 +1955,10 @@ wgb_status wgb_queue_write_texture(wgb_queue queue, wgb_texture texture, uint32_
         std::lock_guard<std::recursive_mutex> dl(dev->mu);
         dev->make_current();
         settle(dev);
-        t->acquire_for_write(dev->stream);
+        t->acquire_for_write(dev->joined());
         char* dst = (char*)t->dptr + ((uint64_t)y * t->desc.width + x) * t->bpp;
-        CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)t->desc.width * t->bpp, data, pitch, row, height, cudaMemcpyHostToDevice, dev->stream));
-        CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+        CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)t->desc.width * t->bpp, data, pitch, row, height, cudaMemcpyHostToDevice, dev->joined()));
+        CUDA_CHECK(cudaStreamSynchronize(dev->joined()));
     });
 }
 wgb_status wgb_texture_read(wgb_texture texture, void* dst, uint64_t dst_size) {
@@ -1896,8 +1970,8 @@ wgb_status wgb_texture_read(wgb_texture texture, void* dst, uint64_t dst_size) {
         std::lock_guard<std::recursive_mutex> dl(dev->mu);
         dev->make_current();
         settle(dev);
-        CUDA_CHECK(cudaMemcpyAsync(dst, t->dptr, t->size, cudaMemcpyDeviceToHost, dev->stream));
-        CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+        CUDA_CHECK(cudaMemcpyAsync(dst, t->dptr, t->size, cudaMemcpyDeviceToHost, dev->joined()));
+        CUDA_CHECK(cudaStreamSynchronize(dev->joined()));
     });
 }
 // The read-back that is not waited for: the texels as every submission made so far leaves them, copied to page-locked
@@ -1920,7 +1994,7 @@ wgb_status wgb_texture_read_pinned_async(wgb_texture texture, void* dst, uint64_
             CUDA_CHECK(cudaStreamCreateWithFlags(&dev->readback_stream, cudaStreamNonBlocking));
             CUDA_CHECK(cudaEventCreateWithFlags(&dev->ev_readback_order, cudaEventDisableTiming));
         }
-        CUDA_CHECK(cudaEventRecord(dev->ev_readback_order, dev->stream));
+        CUDA_CHECK(cudaEventRecord(dev->ev_readback_order, dev->joined()));
         CUDA_CHECK(cudaStreamWaitEvent(dev->readback_stream, dev->ev_readback_order, 0));
         CUDA_CHECK(cudaMemcpyAsync(dst, t->dptr, t->size, cudaMemcpyDeviceToHost, dev->readback_stream));
         if (!t->ev_read) CUDA_CHECK(cudaEventCreateWithFlags(&t->ev_read, cudaEventDisableTiming));
@@ -1952,8 +2026,8 @@ wgb_status wgb_texture_dump_png(wgb_texture texture, const char* path) {
             std::lock_guard<std::recursive_mutex> dl(dev->mu);
             dev->make_current();
             settle(dev);
-            CUDA_CHECK(cudaMemcpyAsync(texels.data(), t->dptr, texels.size(), cudaMemcpyDeviceToHost, dev->stream));
-            CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+            CUDA_CHECK(cudaMemcpyAsync(texels.data(), t->dptr, texels.size(), cudaMemcpyDeviceToHost, dev->joined()));
+            CUDA_CHECK(cudaStreamSynchronize(dev->joined()));
         }
         switch (t->desc.format) {                                                       // lib.rs:124-154
             case WGB_TEXTURE_FORMAT_RGBA8_UNORM: case WGB_TEXTURE_FORMAT_RGBA8_UNORM_SRGB:
@@ -2406,11 +2480,11 @@ wgb_status wgb_queue_submit(wgb_queue queue, const wgb_command_buffer* command_b
             // once the pass is recorded) and are cleared below, before this scope ends: keep the buffers alive until the
             // end-of-scope bookkeeping has run
             std::vector<Ref<Buffer>> keep_alive(used.begin(), used.end());
-            for (Buffer* b : used) { b->acquire_on(dev->stream); b->last_use_submission = index; }
+            for (Buffer* b : used) { b->acquire_on(dev->stream); b->last_use_submission = index; }      // (waits only)
             struct MarkUsed {
-                std::vector<Buffer*>& v; cudaStream_t s;
-                ~MarkUsed() { for (Buffer* b : v) b->mark_used(s); }
-            } mark_used{used, dev->stream};
+                std::vector<Buffer*>& v; Device* d;
+                ~MarkUsed() { if (v.empty()) return; cudaStream_t s = d->tail(); for (Buffer* b : v) b->mark_used(s); }      // behind the tile kernels too
+            } mark_used{used, dev};
             for (const auto& cmd : cb->passes) {
                 // errors raised while a submission executes surface at poll, where the reference's
                 // engine-thread panic would be observed (device.rs:498-503)
@@ -2424,7 +2498,7 @@ wgb_status wgb_queue_submit(wgb_queue queue, const wgb_command_buffer* command_b
         }
         cudaEvent_t done;
         CUDA_CHECK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-        CUDA_CHECK(cudaEventRecord(done, dev->stream));
+        CUDA_CHECK(cudaEventRecord(done, dev->tail()));
         dev->inflight.push_back({index, done});
         if (st != WGB_OK && dev->deferred_status == WGB_OK) { dev->deferred_status = st; dev->deferred_error = msg; }
     });
@@ -2458,8 +2532,8 @@ wgb_status wgb_device_read_coverage(wgb_device device, uint32_t* dst, uint64_t p
         REQUIRE(pixel_count == (uint64_t)dev->coverage_w * dev->coverage_h, "pixel_count does not match the last pass (%ux%u)", dev->coverage_w, dev->coverage_h);
         dev->make_current();
         settle(dev);
-        CUDA_CHECK(cudaMemcpyAsync(dst, dev->coverage.p, pixel_count * 4, cudaMemcpyDeviceToHost, dev->stream));
-        CUDA_CHECK(cudaStreamSynchronize(dev->stream));
+        CUDA_CHECK(cudaMemcpyAsync(dst, dev->coverage.p, pixel_count * 4, cudaMemcpyDeviceToHost, dev->joined()));
+        CUDA_CHECK(cudaStreamSynchronize(dev->joined()));
     });
 }
 wgb_status wgb_device_set_band(wgb_device device, uint32_t band_rank, uint32_t band_count) {
@@ -2488,7 +2562,7 @@ wgb_status wgb_device_timer_begin(wgb_device device) {
         std::lock_guard<std::recursive_mutex> lk(dev->mu);
         if (dev->compile_only) fail(WGB_ERROR_DEVICE, "a compile-only device has no stream");
         dev->make_current();
-        CUDA_CHECK(cudaEventRecord(dev->timer_ev[0], dev->stream));
+        CUDA_CHECK(cudaEventRecord(dev->timer_ev[0], dev->joined()));
     });
 }
 wgb_status wgb_device_timer_end(wgb_device device, float* out_ms) {
@@ -2498,7 +2572,7 @@ wgb_status wgb_device_timer_end(wgb_device device, float* out_ms) {
         std::lock_guard<std::recursive_mutex> lk(dev->mu);
         if (dev->compile_only) fail(WGB_ERROR_DEVICE, "a compile-only device has no stream");
         dev->make_current();
-        CUDA_CHECK(cudaEventRecord(dev->timer_ev[1], dev->stream));
+        CUDA_CHECK(cudaEventRecord(dev->timer_ev[1], dev->joined()));
         CUDA_CHECK(cudaEventSynchronize(dev->timer_ev[1]));
         CUDA_CHECK(cudaEventElapsedTime(out_ms, dev->timer_ev[0], dev->timer_ev[1]));
     });
@@ -2507,7 +2581,7 @@ wgb_status wgb_device_get_stream(wgb_device device, void** out_stream) {
     return guarded([&] {
         Device* dev = from_handle<Device>(device, "device");
         REQUIRE(out_stream, "out is null");
-        *out_stream = (void*)dev->stream;
+        *out_stream = (void*)dev->joined();
     });
 }
 
