@@ -24,13 +24,21 @@ def _bunny_frames(n, size=(160, 120)):
     return [S.hello_texture(size[0], size[1], yaw=f * 2.0 * math.pi / n) for f in range(n)]
 
 
-def test_frames_in_flight_with_uniform_writes_between_them(gpu):
+@pytest.mark.parametrize("camera_bytes", [64, 4096])
+def test_frames_in_flight_with_uniform_writes_between_them(gpu, camera_bytes):
     """A batch of frames like BASELINE's C5: one camera write + one submission per frame, each frame into its own
-    target, ONE wait at the end."""
+    target, ONE wait at the end.  The tile kernel of frame k runs beside the geometry stage of frame k + 1 and reads the
+    camera again when it shades: a small binding from the snapshot its pass took, a large one (the camera at the head
+    of a 4 KB buffer) where it is -- the write for frame k + 1 then has to wait for it."""
     from oracle import pyoracle
     from wgpu_cpu_b200.render import SceneRenderer
     dev, queue = gpu
     frames = _bunny_frames(6)
+    for sc in frames:
+        cam = np.zeros(camera_bytes, dtype=np.uint8)
+        cam[:64] = sc.bindings[(0, 0)][1]
+        sc.bindings = dict(sc.bindings)
+        sc.bindings[(0, 0)] = ("buffer", cam)
     targets = [dev.create_texture(frames[0].width, frames[0].height, frames[0].color_format) for _ in frames]
     r = SceneRenderer(dev, queue, frames[0], targets=targets)
     r.render()                                   # the draw shape's bin capacity is known from here on

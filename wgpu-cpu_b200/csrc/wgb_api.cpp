@@ -325,7 +325,7 @@ struct DevBuf {
 // kernels of one compiled pipeline variant
 struct KernelSet {
     CUmodule module = nullptr;
-    CUfunction geometry = nullptr, vertex = nullptr, geometry_cached = nullptr, clip = nullptr, scan = nullptr, fill = nullptr, tile = nullptr, clear = nullptr, strip_map = nullptr,
+    CUfunction begin = nullptr, geometry = nullptr, vertex = nullptr, geometry_cached = nullptr, clip = nullptr, scan = nullptr, fill = nullptr, tile = nullptr, clear = nullptr, strip_map = nullptr,
                big_sort = nullptr;     // ordered variants only
     bool ordered = false;
 };
@@ -351,6 +351,12 @@ struct Device : Object {
     // reads the old one; the two cross-stream waits then cost more than nothing at all).  A draw takes the tile stream
     // when the draw before it was followed by nothing but this one.
     uint32_t ops_since_tile = 1;
+    // Which writes have to wait for tile kernels: a draw that is not waited for reads its small buffer bindings from a
+    // snapshot in its work set (K0), its vertex / index buffers and large bindings where they are.  The draws are
+    // numbered; a buffer remembers the last draw that reads it in place, the device the last draw the render stream has
+    // been ordered behind.  A small queue.write_buffer goes behind the tile stream only if its buffer is read in place
+    // by a draw after that one.
+    uint64_t draw_serial = 0, joined_draw_serial = 0;
     cudaStream_t joined() {
         ops_since_tile++;
         if (tiles_ahead) {
@@ -358,6 +364,7 @@ struct Device : Object {
             cudaStreamWaitEvent(stream, ev_tiles, 0);
             tiles_ahead = false;
         }
+        joined_draw_serial = draw_serial;
         return stream;
     }
     cudaStream_t tail() {
@@ -385,11 +392,11 @@ struct Device : Object {
     // the buffers a draw's kernels hand to each other; two sets, used in turn by the draws that are not waited for, so
     // that a geometry stage can fill one while the tile kernel of the draw before still reads the other
     struct WorkSet {
-        DevBuf counters, prim_box, setup_cache, vcache_raster, vcache_ndc, vcache_flags, slow_list, clip_records, big_list, tile_offset, tile_cursor, bins;
+        DevBuf counters, prim_box, setup_cache, vcache_raster, vcache_ndc, vcache_flags, slow_list, clip_records, big_list, tile_offset, tile_cursor, bins, snapshots;
         cudaEvent_t ev_free = nullptr;     // on the tile stream, behind the tile kernel that read the set last
         bool busy = false;
         void release() {
-            DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &vcache_raster, &vcache_ndc, &vcache_flags, &slow_list, &clip_records, &big_list, &tile_offset, &tile_cursor, &bins};
+            DevBuf* bufs[] = {&counters, &prim_box, &setup_cache, &vcache_raster, &vcache_ndc, &vcache_flags, &slow_list, &clip_records, &big_list, &tile_offset, &tile_cursor, &bins, &snapshots};
             for (DevBuf* b : bufs) b->release();
             if (ev_free) cudaEventDestroy(ev_free);
             ev_free = nullptr;
@@ -505,6 +512,7 @@ struct Buffer : Object {
     cudaEvent_t ev_write = nullptr, ev_use = nullptr;
     bool write_pending = false, use_pending = false;
     uint64_t last_use_submission = 0;       // the latest submission that reads or writes the buffer (guarded by the device mutex)
+    uint64_t last_live_draw = 0;            // Device::draw_serial of the last draw that reads the buffer in place
     bool external_writers = false;          // wgb_buffer_device_pointer has handed the storage out: its contents are the caller's business
     ~Buffer() override {
         {
@@ -742,6 +750,7 @@ struct RenderPipeline : Object {
                 };
                 ks->ordered = src.find("#define WGB_RESOLVE 7\n") != std::string::npos;
                 if (ks->ordered) fn("wgb_big_sort_kernel", &ks->big_sort);
+                fn("wgb_begin_kernel", &ks->begin);
                 fn("wgb_geometry_kernel", &ks->geometry);
                 fn("wgb_vertex_kernel", &ks->vertex);
                 fn("wgb_geometry_cached_kernel", &ks->geometry_cached);
@@ -968,6 +977,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
         d.vb[b].ptr = (uint64_t)(uintptr_t)vb->dptr + st.vertex_buffers[b].offset;
         d.vb[b].size = std::min<uint64_t>(st.vertex_buffers[b].size, vb->size - st.vertex_buffers[b].offset);
     }
+    Buffer* res_buffer[WGB_MAX_GROUPS][WGB_MAX_BINDINGS] = {};
     for (uint32_t g = 0; g < WGB_MAX_GROUPS; g++) {                                     // binding.rs:22-52
         BindGroup* bg = st.bind_groups[g].get();
         if (!bg) continue;
@@ -991,6 +1001,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 REQUIRE(off <= e.buffer->size, "bind group buffer offset out of range");
                 r.ptr = (uint64_t)(uintptr_t)e.buffer->dptr + off;
                 r.a = (uint32_t)std::min<uint64_t>(e.size, e.buffer->size - off);
+                res_buffer[g][e.binding] = e.buffer.get();
             } else if (e.kind == WGB_BINDING_TEXTURE_VIEW) {
                 Texture* t = e.view->texture.get();
                 if (t->desc.format != WGB_TEXTURE_FORMAT_RGBA8_UNORM && t->desc.format != WGB_TEXTURE_FORMAT_RGBA8_UNORM_SRGB)
@@ -1067,6 +1078,8 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
     }
     d.coverage = dev->coverage.addr();
 
+    uint64_t live_res[WGB_MAX_GROUPS][WGB_MAX_BINDINGS];          // where the bindings are (a draw that is not waited for reads the small ones from a snapshot)
+    for (uint32_t g = 0; g < WGB_MAX_GROUPS; g++) for (uint32_t b = 0; b < WGB_MAX_BINDINGS; b++) live_res[g][b] = d.res[g][b].ptr;
     for (uint64_t base = 0; base < total_prims; base += max_batch) {
         const uint32_t np = (uint32_t)std::min<uint64_t>(max_batch, total_prims - base);
         d.prim_base = (uint32_t)base;   // batches beyond 2^32 primitives are not addressable
@@ -1081,6 +1094,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             // the work set the draw before it does not use; its tile kernel follows on the tile stream
             const bool async = dev->recording != nullptr;
             const bool two_streams = async && dev->overlap_stages && dev->ops_since_tile == 0;
+            for (uint32_t g = 0; g < WGB_MAX_GROUPS; g++) for (uint32_t b = 0; b < WGB_MAX_BINDINGS; b++) d.res[g][b].ptr = live_res[g][b];
             Device::WorkSet& ws = dev->work[two_streams ? (dev->work_next++ & 1u) : 0u];
             // the counters and the per-tile pair counts share one buffer: one memset clears both
             ws.counters.ensure(sizeof(WgbCounters) + (size_t)(band_tiles + 1) * 4);
@@ -1135,7 +1149,27 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 if (ws.busy) { CUDA_CHECK(cudaStreamWaitEvent(gs, ws.ev_free, 0)); ws.busy = false; }
             } else gs = ts = dev->joined();
             CUDA_CHECK(cudaEventRecord(pb.ev[0], gs));
-            CUDA_CHECK(cudaMemsetAsync(ws.counters.p, 0, sizeof(WgbCounters) + (size_t)(band_tiles + 1) * 4, gs));
+            // K0: counters and per-tile pair counts to zero (they share one buffer), snapshots of the small bindings
+            d.begin_words = (uint32_t)((sizeof(WgbCounters) + (size_t)(band_tiles + 1) * 4) / 4);
+            memset(d.snap_src, 0, sizeof(d.snap_src));
+            if (async) {
+                dev->draw_serial++;
+                constexpr uint32_t SNAP_MAX = 1024, SNAP_SLOT = 1024;
+                ws.snapshots.ensure((size_t)WGB_MAX_GROUPS * WGB_MAX_BINDINGS * SNAP_SLOT);
+                for (uint32_t g = 0; g < WGB_MAX_GROUPS; g++)
+                    for (uint32_t b = 0; b < WGB_MAX_BINDINGS; b++) {
+                        Buffer* rb = res_buffer[g][b];
+                        if (!rb) continue;
+                        WgbResource& r = d.res[g][b];
+                        if (r.a > 0 && r.a <= SNAP_MAX) {
+                            d.snap_src[g][b] = live_res[g][b];
+                            r.ptr = ws.snapshots.addr() + (uint64_t)(g * WGB_MAX_BINDINGS + b) * SNAP_SLOT;
+                        } else rb->last_live_draw = dev->draw_serial;
+                    }
+                for (size_t b = 0; b < pipe->vbs.size(); b++) st.vertex_buffers[b].buffer->last_live_draw = dev->draw_serial;
+                if (indexed) st.index_buffer.buffer->last_live_draw = dev->draw_serial;
+            }
+            launch_on(dev, gs, ks->begin, dim3(std::min<uint32_t>((d.begin_words + 255) / 256, 148 * 4)), dim3(256), &d);
             const uint32_t gblocks = (np + 255) / 256;
             if (vcache_n) {
                 // the cache holds every instance of the draw, so it is filled once, by the first batch
@@ -1868,9 +1902,11 @@ static void write_buffer_impl(wgb_queue queue, wgb_buffer buffer, uint64_t offse
         if (!async) CUDA_CHECK(cudaEventSynchronize(b->ev_write));
     } else {
         // pageable source: the runtime stages the bytes before cudaMemcpyAsync returns, so `data` may be reused
-        b->acquire_on(dev->joined());
-        CUDA_CHECK(cudaMemcpyAsync((char*)b->dptr + offset, data, size, cudaMemcpyHostToDevice, dev->joined()));
-        b->mark_used(dev->joined());
+        // (behind the tile kernels only where one of them may read this buffer in place -- Device::draw_serial)
+        cudaStream_t ws = b->last_live_draw > dev->joined_draw_serial || size > (64u << 10) ? dev->joined() : dev->stream;
+        b->acquire_on(ws);
+        CUDA_CHECK(cudaMemcpyAsync((char*)b->dptr + offset, data, size, cudaMemcpyHostToDevice, ws));
+        b->mark_used(ws);
     }
 }
 wgb_status wgb_queue_write_buffer(wgb_queue queue, wgb_buffer buffer, uint64_t offset, const void* data, uint64_t size) {

@@ -178,6 +178,12 @@ struct WgbDraw {
     wgb_u64 bins;                        // u32 entries
     wgb_u64 coverage;                    // optional u32 per pixel (stats)
     wgb_u64 poison;                      // asynchronous submissions: u32 the tile kernels raise / obey (0 = synchronous execution)
+    // K0 (wgb_begin_kernel): zeroes `begin_words` words at `counters` (the counters and the per-tile pair counts) and
+    // copies the small buffer bindings of a draw that is not waited for to the work set -- snap_src[g][b] (0 = none) to
+    // res[g][b].ptr, res[g][b].a bytes -- so that the pass reads them as they were when it was queued, whatever
+    // queue.write_buffer puts there while its tile kernel runs
+    wgb_u32 begin_words, pad4;
+    wgb_u64 snap_src[WGB_MAX_GROUPS][WGB_MAX_BINDINGS];
     wgb_u32 tmap_color, tmap_depth;      // 1: map_color / map_depth describe colour attachment 0 / the depth attachment
     WgbTensorMap map_color, map_depth;
 };
