@@ -428,6 +428,7 @@ def main():
     sampler.start()
     for _ in range(warm):
         step()
+    run_steps(2)          # and two steps the way the timed ones run (in flight together: the second set of work buffers, the tile stream)
     for k in range(frame_no[0], frame_no[0] + args.steps * passes_per_step):      # recording is outside the timed span, as for the reference's pass timer
         recorded[k] = r.encode(k)
 

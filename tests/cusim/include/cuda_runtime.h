@@ -44,6 +44,8 @@ cudaError_t cudaMemcpyAsync(void*, const void*, size_t, cudaMemcpyKind, cudaStre
 cudaError_t cudaMemcpy2DAsync(void*, size_t, const void*, size_t, size_t, size_t, cudaMemcpyKind, cudaStream_t);
 cudaError_t cudaMemsetAsync(void*, int, size_t, cudaStream_t);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t*, unsigned);
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t*, unsigned, int);
+cudaError_t cudaDeviceGetStreamPriorityRange(int*, int*);
 cudaError_t cudaStreamDestroy(cudaStream_t);
 cudaError_t cudaStreamSynchronize(cudaStream_t);
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned);

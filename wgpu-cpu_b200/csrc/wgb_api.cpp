@@ -1093,24 +1093,10 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             // a draw that is not waited for: geometry stage on the render stream without waiting for the tile stream, in
             // the work set the draw before it does not use; its tile kernel follows on the tile stream
             const bool async = dev->recording != nullptr;
-            const bool two_streams = async && dev->overlap_stages && dev->ops_since_tile == 0;
+            static const bool always_two = getenv("WGB_ALWAYS_TWO_STREAMS") != nullptr;      // A/B knob
+            const bool two_streams = async && dev->overlap_stages && (dev->ops_since_tile == 0 || always_two);
             for (uint32_t g = 0; g < WGB_MAX_GROUPS; g++) for (uint32_t b = 0; b < WGB_MAX_BINDINGS; b++) d.res[g][b].ptr = live_res[g][b];
             Device::WorkSet& ws = dev->work[two_streams ? (dev->work_next++ & 1u) : 0u];
-            // the counters and the per-tile pair counts share one buffer: one memset clears both
-            ws.counters.ensure(sizeof(WgbCounters) + (size_t)(band_tiles + 1) * 4);
-            ws.prim_box.ensure((size_t)np * 4);
-            if (!vcache_n) ws.setup_cache.ensure((size_t)np * 48);
-            if (vcache_n) {
-                const size_t nv = (size_t)vcache_n * sc.instance_count;
-                ws.vcache_raster.ensure(nv * 16); ws.vcache_ndc.ensure(nv * 8); ws.vcache_flags.ensure(nv);
-                d.vcache_raster = ws.vcache_raster.addr(); d.vcache_ndc = ws.vcache_ndc.addr(); d.vcache_flags = ws.vcache_flags.addr();
-                d.vcache_count = (uint32_t)vcache_n;
-            }
-            ws.slow_list.ensure((size_t)np * 4);
-            ws.clip_records.ensure((size_t)clip_cap * sizeof(WgbClipRecord));
-            ws.big_list.ensure((size_t)big_cap * sizeof(WgbBigEntry));
-            ws.tile_offset.ensure((size_t)(band_tiles + 1) * 4);
-            ws.tile_cursor.ensure((size_t)(band_tiles + 1) * 4);
             // direct binning: a fixed number of slots per tile, sized from what this draw shape needed before
             // (or twice the mean on first sight); the geometry kernels then store the bin entries themselves and
             // the scan + fill kernels are skipped.  A tile that overflows flags the pass and the draw is replayed.
@@ -1124,7 +1110,29 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 if (!dev->no_direct_bins && band_tiles > 0 && (uint64_t)band_tiles * cap * 4 <= (1ull << 30)) bin_cap = (uint32_t)cap;
             }
             d.bin_cap = bin_cap;
-            ws.bins.ensure(bin_cap ? (size_t)band_tiles * bin_cap * 4 : ((size_t)np + clip_cap) * WGB_SMALL_MAX_TILES * 4);
+            // A draw that is not waited for sizes BOTH work sets: the one it does not use is the next draw's, and a first
+            // cudaMalloc of 10^8 bytes in the middle of a queue of passes stalls all of them.
+            for (Device::WorkSet& w : dev->work) {
+                if (&w != &ws && !(async && dev->overlap_stages)) continue;
+                w.counters.ensure(sizeof(WgbCounters) + (size_t)(band_tiles + 1) * 4);       // the counters and the per-tile pair counts share one buffer: K0 clears both
+                w.prim_box.ensure((size_t)np * 4);
+                if (!vcache_n) w.setup_cache.ensure((size_t)np * 48);
+                if (vcache_n) {
+                    const size_t nv = (size_t)vcache_n * sc.instance_count;
+                    w.vcache_raster.ensure(nv * 16); w.vcache_ndc.ensure(nv * 8); w.vcache_flags.ensure(nv);
+                }
+                w.slow_list.ensure((size_t)np * 4);
+                w.clip_records.ensure((size_t)clip_cap * sizeof(WgbClipRecord));
+                w.big_list.ensure((size_t)big_cap * sizeof(WgbBigEntry));
+                w.tile_offset.ensure((size_t)(band_tiles + 1) * 4);
+                w.tile_cursor.ensure((size_t)(band_tiles + 1) * 4);
+                w.bins.ensure(bin_cap ? (size_t)band_tiles * bin_cap * 4 : ((size_t)np + clip_cap) * WGB_SMALL_MAX_TILES * 4);
+                if (async) w.snapshots.ensure((size_t)WGB_MAX_GROUPS * WGB_MAX_BINDINGS * 1024);
+            }
+            if (vcache_n) {
+                d.vcache_raster = ws.vcache_raster.addr(); d.vcache_ndc = ws.vcache_ndc.addr(); d.vcache_flags = ws.vcache_flags.addr();
+                d.vcache_count = (uint32_t)vcache_n;
+            }
             d.counters = ws.counters.addr(); d.prim_box = ws.prim_box.addr(); d.slow_list = ws.slow_list.addr();
             d.setup_cache = ws.setup_cache.addr();
             d.clip_records = ws.clip_records.addr(); d.clip_capacity = clip_cap;
@@ -1155,13 +1163,13 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             if (async) {
                 dev->draw_serial++;
                 constexpr uint32_t SNAP_MAX = 1024, SNAP_SLOT = 1024;
-                ws.snapshots.ensure((size_t)WGB_MAX_GROUPS * WGB_MAX_BINDINGS * SNAP_SLOT);
                 for (uint32_t g = 0; g < WGB_MAX_GROUPS; g++)
                     for (uint32_t b = 0; b < WGB_MAX_BINDINGS; b++) {
                         Buffer* rb = res_buffer[g][b];
                         if (!rb) continue;
                         WgbResource& r = d.res[g][b];
-                        if (r.a > 0 && r.a <= SNAP_MAX) {
+                        static const bool no_snapshots = getenv("WGB_NO_SNAPSHOTS") != nullptr;      // A/B knob
+                        if (r.a > 0 && r.a <= SNAP_MAX && !no_snapshots) {
                             d.snap_src[g][b] = live_res[g][b];
                             r.ptr = ws.snapshots.addr() + (uint64_t)(g * WGB_MAX_BINDINGS + b) * SNAP_SLOT;
                         } else rb->last_live_draw = dev->draw_serial;
@@ -1169,7 +1177,9 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
                 for (size_t b = 0; b < pipe->vbs.size(); b++) st.vertex_buffers[b].buffer->last_live_draw = dev->draw_serial;
                 if (indexed) st.index_buffer.buffer->last_live_draw = dev->draw_serial;
             }
-            launch_on(dev, gs, ks->begin, dim3(std::min<uint32_t>((d.begin_words + 255) / 256, 148 * 4)), dim3(256), &d);
+            static const bool memset_begin = getenv("WGB_MEMSET_BEGIN") != nullptr;                   // A/B knob (needs WGB_NO_SNAPSHOTS)
+            if (memset_begin) CUDA_CHECK(cudaMemsetAsync(ws.counters.p, 0, (size_t)d.begin_words * 4, gs));
+            else launch_on(dev, gs, ks->begin, dim3(std::min<uint32_t>((d.begin_words + 255) / 256, 148 * 4)), dim3(256), &d);
             const uint32_t gblocks = (np + 255) / 256;
             if (vcache_n) {
                 // the cache holds every instance of the draw, so it is filled once, by the first batch
@@ -1689,8 +1699,18 @@ wgb_status wgb_adapter_request_device(wgb_adapter adapter, const wgb_device_desc
             CUDA_CHECK(cudaGetDeviceProperties(&p, ord));
             if (p.major != 10) fail(WGB_ERROR_DEVICE, "device %d is sm_%d%d; this backend is built for sm_100a (B200) only", ord, p.major, p.minor);
             load_driver_api();
-            CUDA_CHECK(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
-            CUDA_CHECK(cudaStreamCreateWithFlags(&dev->tile_stream, cudaStreamNonBlocking));     // (stream priorities either way round: no difference measured)
+            {
+                int prio_least = 0, prio_greatest = 0;
+                CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+                const char* pm = getenv("WGB_STREAM_PRIORITY");      // A/B knob: "flags" (no priorities), "equal", default: render stream first
+                if (pm && !strcmp(pm, "flags")) {
+                    CUDA_CHECK(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
+                    CUDA_CHECK(cudaStreamCreateWithFlags(&dev->tile_stream, cudaStreamNonBlocking));
+                } else {
+                    CUDA_CHECK(cudaStreamCreateWithPriority(&dev->stream, cudaStreamNonBlocking, (pm && !strcmp(pm, "equal")) ? prio_least : prio_greatest));
+                    CUDA_CHECK(cudaStreamCreateWithPriority(&dev->tile_stream, cudaStreamNonBlocking, prio_least));
+                }
+            }
             CUDA_CHECK(cudaEventCreateWithFlags(&dev->ev_tiles, cudaEventDisableTiming));
             CUDA_CHECK(cudaEventCreateWithFlags(&dev->ev_render_pos, cudaEventDisableTiming));
             dev->overlap_stages = getenv("WGB_NO_OVERLAP") == nullptr;
