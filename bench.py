@@ -40,8 +40,9 @@ CONFIGS = {
     "c4": ("full-screen 64-iteration fragment shader 7680x4320 (C4)", lambda S: S.procedural(7680, 4320)),
     "c5": ("batch of 64 frames of the textured bunny at 3840x2160, camera yaw = frame*tau/64 (C5); one step = 64 passes",
            lambda S: S.hello_texture(3840, 2160)),
+    "c5s": ("batch of 4 frames of the textured bunny at 320x256 (reduced C5, smoke only); one step = 4 passes", lambda S: S.hello_texture(320, 256)),
 }
-C5_FRAMES = 64
+BATCH_FRAMES = {"c5": 64, "c5s": 4}      # configs whose step is a batch of independent frames
 
 
 def measured_peak_hbm():
@@ -317,12 +318,21 @@ def main():
     # N > 1: two presenter targets, used alternately, so that a rank that is a frame ahead never stores into the frame
     # rank 0 is still reading (one barrier per frame is then enough)
     targets = None
-    n_present = (C5_FRAMES if args.config == "c5" else 2) if world > 1 else 1
+    batch = BATCH_FRAMES.get(args.config)
+    n_present = (batch if batch else 2) if world > 1 else 1
+
+    def presenter_of(frame):
+        """The rank a frame is assembled on.  A batch of independent frames is presented round-robin -- frame f on rank
+        f mod N -- so that the bands of one frame converge on one GPU and those of the next on another (all of them
+        into rank 0: its NVLink ingest, 7/8 of every frame, bounds the tile kernels of the whole batch)."""
+        return (frame % n_present) % world if batch and args.present == "peer" else 0
+
     if world > 1 and args.present == "peer":
         targets = []
-        for _ in range(n_present):
-            own = dev.create_texture(W, H, scene.color_format) if rank == 0 else None
-            targets.append(multigpu.share_presenter_target(dev, own, rank, world, W, H, scene.color_format, dst=0))
+        for i in range(n_present):
+            dst = presenter_of(i)
+            own = dev.create_texture(W, H, scene.color_format) if rank == dst else None
+            targets.append(multigpu.share_presenter_target(dev, own, rank, world, W, H, scene.color_format, dst=dst))
     elif world > 1:
         targets = [dev.create_texture(W, H, scene.color_format) for _ in range(n_present)]
     r = SceneRenderer(dev, queue, scene, use_emitted=use_emitted, targets=targets)
@@ -359,9 +369,9 @@ def main():
 
     # C5: a step is a batch of 64 frames, each with its own camera (a 64-byte uniform update per frame)
     cameras = None
-    if args.config == "c5":
+    if batch:
         import math
-        cameras = [S.hello_texture(W, H, yaw=f * 2.0 * math.pi / C5_FRAMES).bindings[(0, 0)][1] for f in range(C5_FRAMES)]
+        cameras = [S.hello_texture(W, H, yaw=f * 2.0 * math.pi / batch).bindings[(0, 0)][1] for f in range(batch)]
     passes_per_step = len(cameras) if cameras else 1
 
     # The timed span mirrors the reference's own (render_pass/mod.rs:346-392: State::new -> load -> draws -> store, i.e.
@@ -616,9 +626,13 @@ def main():
                 queue.write_buffer(r.resources[(0, 0)], 0, cam)
                 r.render(r.encode(k))
                 gather(k)
-                if rank == 0:
-                    frames.append(hashlib.sha256(np.ascontiguousarray(r.targets[k % n_present].read()).tobytes()).hexdigest())
+                frames.append(hashlib.sha256(np.ascontiguousarray(r.targets[k % n_present].read()).tobytes()).hexdigest()
+                              if rank == presenter_of(k) else None)
                 barrier()
+            if world > 1:           # every rank hashed the frames it presents
+                every = [None] * world
+                dist.all_gather_object(every, frames)
+                frames = [next(d[i] for d in every if d[i] is not None) for i in range(len(frames))]
             digest = hashlib.sha256("".join(frames).encode()).hexdigest() if rank == 0 else None
             want = golden.get("batch")
         if rank == 0:
@@ -686,7 +700,7 @@ def main():
         "config": {"workload": workload, "width": W, "height": H, "triangles": prims,
                    "l2": "inputs (280 MB vertex+index) and attachments (66 MB) exceed the 126 MB L2 at C3; no explicit flush",
                    "timed_span": "K steps of submit + poll(Wait) with step k+1 submitted before step k is waited for (execution, as the reference's own pass timer); command buffers recorded before the timed region",
-                   "parallelism": (f"sort-first x{world}, bands presented to rank 0 by " +
+                   "parallelism": (f"sort-first x{world}, bands presented to " + ("rank f mod N (frame f of the batch) by " if batch and args.present == "peer" else "rank 0 by ") +
                                    ("NVLink peer stores from the tile kernel" if args.present == "peer" else "NCCL send/recv"))
                    if world > 1 else "single GPU",
                    "shaders": "WGSL translated to CUDA C++ and compiled with NVRTC for sm_100a"},

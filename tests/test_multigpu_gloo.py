@@ -82,7 +82,7 @@ def test_host_barrier_world_size_2(tmp_path):
     assert (log >= np.arange(50)).all()
 
 
-def _bench_dry_run(tmp_path, world, extra):
+def _bench_dry_run(tmp_path, world, extra, config="c1"):
     """bench.py itself on the software model of tests/cusim (WGB_CUSIM=1: gloo instead of NCCL, "device" memory is host
     memory, the presenter's targets shared through a memfd): frame numbering, the presenter exchange with alternating
     targets, the sharded upload + all-gather of the e2e leg and the oracle digest of the assembled frame."""
@@ -92,7 +92,7 @@ def _bench_dry_run(tmp_path, world, extra):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, WGB_CUSIM="1", CUSIM_THREADS="2", CUSIM_CACHE=str(tmp_path / "cache"))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), "bench.py", "--gpus", str(world), "--config", "c1", "--steps", "2", "--warmup", "1",
+           "--master-port", str(_free_port()), "bench.py", "--gpus", str(world), "--config", config, "--steps", "2", "--warmup", "1",
            "--no-cpu-baseline"] + extra
     p = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
@@ -116,3 +116,13 @@ def test_bench_dry_run_two_ranks_peer_presenter(tmp_path):
 def test_bench_dry_run_two_ranks_nccl_presenter(tmp_path):
     d = _bench_dry_run(tmp_path, 2, ["--present", "nccl", "--no-e2e"])
     assert d["parity"]["matches_oracle"] is True and "send/recv" in d["config"]["parallelism"]
+
+
+def test_bench_dry_run_a_batch_of_frames_presented_round_robin(tmp_path):
+    """A reduced C5 (4 frames per batch): with three ranks frame f is assembled on rank f mod 3 from the bands of all of
+    them, every rank hashes the frames it presents, and the digest over the batch equals the one a single rank renders."""
+    one = _bench_dry_run(tmp_path, 1, [], config="c5s")
+    three = _bench_dry_run(tmp_path, 3, [], config="c5s")
+    assert "rank f mod N" in three["config"]["parallelism"]
+    assert three["parity"]["frame_sha256"] == one["parity"]["frame_sha256"]
+    assert three["per_rank"] is not None and len(three["per_rank"]["tile_ms"]) == 3
