@@ -422,10 +422,17 @@ def main():
             return
         for _ in range(n):
             first, idx = frame_no[0], 0
-            for cam in cameras:
-                k = frame_no[0]
-                frame_no[0] += 1
-                queue.write_buffer(r.resources[(0, 0)], 0, cam)
+            frame_no[0] += len(cameras)
+            # The frames of a batch are independent (own camera, own target), so a rank is free to render them in any
+            # order: rank r starts at frame r.  At any moment the N ranks are then on N different frames, whose bands
+            # converge on N different presenters (frame f assembles on rank f mod N) -- started together on frame 0
+            # they all store into one GPU at once, and its NVLink ingest (7/8 of a frame per pass) is what the tile
+            # kernels of the whole batch wait for.
+            shift = rank % len(cameras) if world > 1 and args.present == "peer" else 0
+            for j in range(len(cameras)):
+                f = (j + shift) % len(cameras)
+                k = first + f
+                queue.write_buffer(r.resources[(0, 0)], 0, cameras[f])
                 idx = r.submit(recorded.pop(k, None) or r.encode(k))
             dev.poll(True, idx)
             if world > 1 and args.present == "nccl":
@@ -612,13 +619,23 @@ def main():
             golden = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_frames_sha256.json"))).get(args.config, {})
         except Exception:      # noqa: BLE001
             pass
+        frames = None
         if cameras is None:
             k = frame_no[0]
             step()
             barrier()
             digest = hashlib.sha256(np.ascontiguousarray(r.targets[k % n_present].read()).tobytes()).hexdigest() if rank == 0 else None
             want = golden.get("color")
-        else:       # C5: every frame of one more batch
+        elif world > 1 and args.present == "peer":
+            # C5: one more batch rendered the way the timed ones are (all frames in flight, every rank in its own frame
+            # order, one wait), then every frame of it is hashed on the rank it assembled on
+            first = frame_no[0]
+            run_steps(1)
+            barrier()
+            frames = [hashlib.sha256(np.ascontiguousarray(r.targets[(first + f) % n_present].read()).tobytes()).hexdigest()
+                      if rank == presenter_of(first + f) else None for f in range(len(cameras))]
+            barrier()
+        else:       # C5 on one GPU (one target) or gathered by NCCL: every frame of one more batch, one at a time
             frames = []
             for cam in cameras:
                 k = frame_no[0]
@@ -629,6 +646,7 @@ def main():
                 frames.append(hashlib.sha256(np.ascontiguousarray(r.targets[k % n_present].read()).tobytes()).hexdigest()
                               if rank == presenter_of(k) else None)
                 barrier()
+        if frames is not None:
             if world > 1:           # every rank hashed the frames it presents
                 every = [None] * world
                 dist.all_gather_object(every, frames)
@@ -638,7 +656,7 @@ def main():
         if rank == 0:
             parity = {"frame_sha256": digest, "oracle_sha256": want, "matches_oracle": (digest == want) if want else None,
                       "what": ("SHA-256 of the colour bytes of the frame assembled on rank 0" if cameras is None else
-                               f"SHA-256 over the {len(cameras)} frame digests of one more batch") +
+                               f"SHA-256 over the {len(cameras)} frame digests of one more batch" + (", rendered like the timed ones (all frames in flight, one wait)" if world > 1 and args.present == "peer" else "")) +
                               ", rendered after the timed region; oracle digest from tests/golden/bench_frames_sha256.json"}
 
     if rank != 0:
@@ -700,7 +718,7 @@ def main():
         "config": {"workload": workload, "width": W, "height": H, "triangles": prims,
                    "l2": "inputs (280 MB vertex+index) and attachments (66 MB) exceed the 126 MB L2 at C3; no explicit flush",
                    "timed_span": "K steps of submit + poll(Wait) with step k+1 submitted before step k is waited for (execution, as the reference's own pass timer); command buffers recorded before the timed region",
-                   "parallelism": (f"sort-first x{world}, bands presented to " + ("rank f mod N (frame f of the batch) by " if batch and args.present == "peer" else "rank 0 by ") +
+                   "parallelism": (f"sort-first x{world}, bands presented to " + ("rank f mod N (frame f of the batch; rank r renders the batch starting at frame r, so the ranks are on N different frames and presenters at any moment) by " if batch and args.present == "peer" else "rank 0 by ") +
                                    ("NVLink peer stores from the tile kernel" if args.present == "peer" else "NCCL send/recv"))
                    if world > 1 else "single GPU",
                    "shaders": "WGSL translated to CUDA C++ and compiled with NVRTC for sm_100a"},

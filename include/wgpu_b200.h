@@ -59,6 +59,7 @@ typedef struct wgb_render_pipeline_t* wgb_render_pipeline;
 typedef struct wgb_command_encoder_t* wgb_command_encoder;
 typedef struct wgb_render_pass_t* wgb_render_pass;
 typedef struct wgb_command_buffer_t* wgb_command_buffer;
+typedef struct wgb_surface_t* wgb_surface;
 
 /* ---- enumerations (names follow wgpu-types) ---- */
 enum { WGB_TOPOLOGY_POINT_LIST = 0, WGB_TOPOLOGY_LINE_LIST = 1, WGB_TOPOLOGY_LINE_STRIP = 2,
@@ -91,6 +92,13 @@ enum { WGB_BUFFER_USAGE_MAP_READ = 1, WGB_BUFFER_USAGE_MAP_WRITE = 2, WGB_BUFFER
        WGB_BUFFER_USAGE_COPY_DST = 8, WGB_BUFFER_USAGE_INDEX = 16, WGB_BUFFER_USAGE_VERTEX = 32,
        WGB_BUFFER_USAGE_UNIFORM = 64, WGB_BUFFER_USAGE_STORAGE = 128 };
 enum { WGB_POLL_OK = 0, WGB_POLL_QUEUE_EMPTY = 1, WGB_POLL_TIMEOUT = 2 };
+/* wgpu::TextureUsages bits */
+enum { WGB_TEXTURE_USAGE_COPY_SRC = 1, WGB_TEXTURE_USAGE_COPY_DST = 2, WGB_TEXTURE_USAGE_TEXTURE_BINDING = 4,
+       WGB_TEXTURE_USAGE_STORAGE_BINDING = 8, WGB_TEXTURE_USAGE_RENDER_ATTACHMENT = 16 };
+enum { WGB_PRESENT_MODE_AUTO_VSYNC = 0, WGB_PRESENT_MODE_AUTO_NO_VSYNC = 1, WGB_PRESENT_MODE_FIFO = 2,
+       WGB_PRESENT_MODE_FIFO_RELAXED = 3, WGB_PRESENT_MODE_IMMEDIATE = 4, WGB_PRESENT_MODE_MAILBOX = 5 };
+enum { WGB_COMPOSITE_ALPHA_MODE_AUTO = 0, WGB_COMPOSITE_ALPHA_MODE_OPAQUE = 1 };
+enum { WGB_SURFACE_STATUS_GOOD = 0 };
 #define WGB_WHOLE_SIZE UINT64_MAX
 #define WGB_SUBMISSION_ANY UINT64_MAX
 
@@ -215,6 +223,48 @@ WGB_API wgb_status wgb_device_import_texture_ipc(wgb_device device, const uint8_
                                                  const wgb_texture_descriptor* desc, wgb_texture* out);
 /* device address of the texel storage (linear, row-major), for collectives over NVLink */
 WGB_API wgb_status wgb_texture_device_pointer(wgb_texture texture, uint64_t* out_ptr, uint64_t* out_size);
+/* ---- surface / present (surface.rs) ----
+ * The reference presents through softbuffer: a window's CPU pixel buffer, one 32-bit word per pixel, that `present` fills
+ * with the surface texture's bytes as they are and hands to the window system (surface.rs:168-193).  On a headless GPU box
+ * the window is a *host pixel sink*: page-locked host memory of width*height*4 bytes that `present` fills with one
+ * device-to-host copy of the surface texture, and a callback that stands where softbuffer's `Buffer::present` does (a
+ * caller forwards the pixels to whatever displays them -- an encoder, a socket, softbuffer itself in the Rust host).
+ * Same contract as the reference otherwise: one format (Bgra8Unorm, as softbuffer's 0RGB words), present mode Immediate,
+ * alpha Opaque, usage RENDER_ATTACHMENT; one texture per configuration, handed out by every get_current_texture. */
+typedef void (*wgb_present_callback)(void* user_data, const void* pixels, uint32_t width, uint32_t height, uint32_t bytes_per_row);
+typedef struct { wgb_present_callback on_present; void* user_data; } wgb_surface_target;
+/* InstanceInterface::create_surface (instance.rs:51-70), Surface::new (surface.rs:29-49).  `target` may be null or hold a
+ * null callback: the presented pixels are then only kept in the window buffer (wgb_surface_get_window_buffer). */
+WGB_API wgb_status wgb_instance_create_surface(wgb_instance instance, const wgb_surface_target* target, wgb_surface* out);
+/* AdapterInterface::is_surface_supported (adapter.rs:44-54): true for every surface of this library */
+WGB_API wgb_status wgb_adapter_is_surface_supported(wgb_adapter adapter, wgb_surface surface, int32_t* out_supported);
+typedef struct {
+    uint32_t format_count, formats[4];                 /* Bgra8Unorm */
+    uint32_t present_mode_count, present_modes[4];     /* Immediate */
+    uint32_t alpha_mode_count, alpha_modes[4];         /* Opaque */
+    uint32_t usages;                                   /* RENDER_ATTACHMENT */
+} wgb_surface_capabilities;
+/* SurfaceInterface::get_capabilities (surface.rs:52-72) */
+WGB_API wgb_status wgb_surface_get_capabilities(wgb_surface surface, wgb_adapter adapter, wgb_surface_capabilities* out);
+typedef struct {
+    uint32_t usage, format, width, height, present_mode, alpha_mode;
+    uint32_t view_format_count; const uint32_t* view_formats;
+} wgb_surface_configuration;
+/* SurfaceInterface::configure (surface.rs:74-114): the format and every view format must be Bgra8Unorm
+ * (check_surface_config, surface.rs:234-257: the reference unwraps the error) and the extent non-zero (`NonZero::new(..)
+ * .expect`), else WGB_ERROR_VALIDATION; allocates the surface texture (zeroed) and sizes the window buffer. */
+WGB_API wgb_status wgb_surface_configure(wgb_surface surface, wgb_device device, const wgb_surface_configuration* config);
+/* SurfaceInterface::get_current_texture (surface.rs:116-146): a new handle (release it) to the configuration's one
+ * texture, status Good; WGB_ERROR_VALIDATION before the first configure ("Surface not configured yet"). */
+WGB_API wgb_status wgb_surface_get_current_texture(wgb_surface surface, wgb_texture* out, uint32_t* out_status);
+/* SurfaceOutputDetailInterface::present (surface.rs:168-193): waits for the submissions that write the texture (the
+ * reference waits for the texture's write guard), copies its bytes into the window buffer and calls `on_present`. */
+WGB_API wgb_status wgb_surface_present(wgb_surface surface);
+/* SurfaceOutputDetailInterface::texture_discard (surface.rs:195-197): nothing, as in the reference */
+WGB_API wgb_status wgb_surface_texture_discard(wgb_surface surface);
+/* the window's pixels as the last present left them (valid until the next configure / release), and how many presents
+ * this surface has seen */
+WGB_API wgb_status wgb_surface_get_window_buffer(wgb_surface surface, const void** out_pixels, uint64_t* out_size, uint64_t* out_presents);
 /* DeviceInterface::create_sampler (device.rs:177-180), Sampler (sampler.rs:4-27) */
 typedef struct {
     uint32_t address_mode_u, address_mode_v, address_mode_w;

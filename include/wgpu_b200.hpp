@@ -297,8 +297,50 @@ struct Device : Handle<wgb_device> {
     }
 };
 
+// SurfaceInterface + SurfaceOutputDetailInterface (surface.rs:51-198); the window is a host pixel sink (wgpu_b200.h)
+struct Surface : Handle<wgb_surface> {
+    using Handle::Handle;
+    wgb_surface_capabilities get_capabilities(wgb_adapter adapter) const {               // surface.rs:52-72
+        wgb_surface_capabilities c{};
+        check(wgb_surface_get_capabilities(get(), adapter, &c));
+        return c;
+    }
+    void configure(const Device& device, uint32_t width, uint32_t height, uint32_t format = WGB_TEXTURE_FORMAT_BGRA8_UNORM,
+                   uint32_t usage = WGB_TEXTURE_USAGE_RENDER_ATTACHMENT) {               // surface.rs:74-114
+        wgb_surface_configuration c{usage, format, width, height, WGB_PRESENT_MODE_IMMEDIATE, WGB_COMPOSITE_ALPHA_MODE_OPAQUE, 0, nullptr};
+        check(wgb_surface_configure(get(), device.get(), &c));
+        width_ = width; height_ = height; format_ = format;
+    }
+    Texture get_current_texture() const {                                                // surface.rs:116-146
+        wgb_texture t = nullptr;
+        uint32_t status = 0;
+        check(wgb_surface_get_current_texture(get(), &t, &status));
+        Texture tex(t);
+        tex.desc.width = width_; tex.desc.height = height_; tex.desc.depth_or_array_layers = 1;
+        tex.desc.mip_level_count = 1; tex.desc.sample_count = 1; tex.desc.format = format_;
+        return tex;
+    }
+    void present() const { check(wgb_surface_present(get())); }                          // surface.rs:168-193
+    void texture_discard() const { check(wgb_surface_texture_discard(get())); }          // surface.rs:195-197
+    // the window's pixels as the last present left them (width * height * 4 bytes, BGRA), and the presents so far
+    std::pair<const uint8_t*, uint64_t> window_buffer() const {
+        const void* p = nullptr;
+        uint64_t n = 0, k = 0;
+        check(wgb_surface_get_window_buffer(get(), &p, &n, &k));
+        return {static_cast<const uint8_t*>(p), k};
+    }
+
+  private:
+    uint32_t width_ = 0, height_ = 0, format_ = WGB_TEXTURE_FORMAT_BGRA8_UNORM;
+};
+
 struct Adapter : Handle<wgb_adapter> {
     using Handle::Handle;
+    bool is_surface_supported(const Surface& surface) const {                            // adapter.rs:44-54
+        int32_t out = 0;
+        check(wgb_adapter_is_surface_supported(get(), surface.get(), &out));
+        return out != 0;
+    }
     wgb_adapter_info get_info() const {                                                  // adapter.rs:60-75
         wgb_adapter_info i{};
         check(wgb_adapter_get_info(get(), &i));
@@ -320,6 +362,14 @@ struct Instance : Handle<wgb_instance> {
         wgb_adapter a = nullptr;
         check(wgb_instance_request_adapter(get(), &a));
         return Adapter(a);
+    }
+    // InstanceInterface::create_surface (instance.rs:51-70): `on_present(user_data, pixels, w, h, bytes_per_row)` stands
+    // where softbuffer's Buffer::present does
+    Surface create_surface(wgb_present_callback on_present = nullptr, void* user_data = nullptr) const {
+        wgb_surface_target t{on_present, user_data};
+        wgb_surface s = nullptr;
+        check(wgb_instance_create_surface(get(), &t, &s));
+        return Surface(s);
     }
 };
 // wgpu_cpu::instance(Config) (lib.rs:22-27)

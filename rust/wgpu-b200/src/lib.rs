@@ -136,17 +136,25 @@ impl InstanceInterface for Instance {
         unreachable!("wgpu_b200::instance(Config) is the constructor");
     }
 
-    unsafe fn create_surface(&self, _target: wgpu::SurfaceTargetUnsafe) -> Result<DispatchSurface, wgpu::CreateSurfaceError> {
-        // headless: the presenting rank reads the frame back
-        Err(wgpu::CreateSurfaceError::custom("wgpu-b200 renders off-screen; read the target back or dump it".to_owned()))
+    unsafe fn create_surface(&self, target: wgpu::SurfaceTargetUnsafe) -> Result<DispatchSurface, wgpu::CreateSurfaceError> {
+        // instance.rs:51-70: with the `softbuffer` feature the window's pixel buffer is the sink the library presents
+        // into (surface::Surface below); without it there are no surfaces, as in the reference
+        #[cfg(feature = "softbuffer")]
+        {
+            surface::Surface::new(self.handle.clone(), target)
+                .map(DispatchSurface::custom)
+                .map_err(|error| wgpu::CreateSurfaceError::custom(error))
+        }
+        #[cfg(not(feature = "softbuffer"))]
+        {
+            let _ = target;
+            Err(wgpu::CreateSurfaceError::custom("wgpu-b200 compiled without softbuffer feature, so no surfaces are supported".to_owned()))
+        }
     }
 
-    fn request_adapter(&self, options: &wgpu::RequestAdapterOptions<'_, '_>) -> Pin<Box<dyn RequestAdapterFuture>> {
-        let result = if options.compatible_surface.is_some() {
-            Err(wgpu::RequestAdapterError::Custom("wgpu-b200 has no surfaces".to_owned()))
-        } else {
-            Ok(self.adapter())
-        };
+    fn request_adapter(&self, _options: &wgpu::RequestAdapterOptions<'_, '_>) -> Pin<Box<dyn RequestAdapterFuture>> {
+        // every surface of this crate is supported by its one adapter (adapter.rs:44-54)
+        let result = Ok(self.adapter());
         Box::pin(async move { result })
     }
 
@@ -193,8 +201,14 @@ impl AdapterInterface for Adapter {
         Box::pin(async move { result })
     }
 
-    fn is_surface_supported(&self, _surface: &DispatchSurface) -> bool {
-        false
+    fn is_surface_supported(&self, surface: &DispatchSurface) -> bool {
+        #![allow(unused)]
+        let mut supported = false;
+        #[cfg(feature = "softbuffer")]
+        {
+            supported = surface.as_custom::<surface::Surface>().is_some();
+        }
+        supported
     }
 
     fn features(&self) -> wgpu::Features {
@@ -1259,4 +1273,169 @@ pub fn band_rows(device: &wgpu::Device, height: u32) -> Range<u32> {
     let (mut a, mut b) = (0u32, 0u32);
     check(unsafe { sys::wgb_device_get_band_rows(d.handle.raw(), height, &mut a, &mut b) });
     a..b
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// surface / present  (surface.rs:24-198)
+// ---------------------------------------------------------------------------------------------------------------
+
+/// The library's surface (`wgb_surface_*`) presents into a host pixel sink; here the sink is the softbuffer window the
+/// reference presents into.  `present` = wait for the frame, one device-to-host copy into the library's page-locked
+/// window buffer, then the `on_present` callback below copies those bytes into softbuffer's buffer and presents it.
+#[cfg(feature = "softbuffer")]
+pub mod surface {
+    use std::ffi::c_void;
+    use std::num::NonZero;
+    use std::ptr;
+    use std::sync::Arc;
+
+    use parking_lot::Mutex;
+    use wgpu::custom::*;
+    use wgpu_b200_sys as sys;
+
+    use super::{check, Device, Handle, Texture};
+
+    struct Window {
+        _context: softbuffer::Context<Display>,
+        surface: softbuffer::Surface<Display, WindowHandle>,
+    }
+
+    #[derive(Debug)]
+    pub struct Surface {
+        handle: Handle<sys::wgb_surface_t>,
+        _instance: Handle<sys::wgb_instance_t>,
+        #[allow(dead_code)]
+        window: Arc<Mutex<Window>>,      // `user_data` of the present callback points into this allocation
+        extent: Mutex<Option<(wgpu::Extent3d, wgpu::TextureFormat)>>,
+    }
+
+    impl std::fmt::Debug for Window {
+        fn fmt(&self, f: &mut std::fmt::Formatter<'_>) -> std::fmt::Result {
+            f.write_str("Window")
+        }
+    }
+
+    /// `SurfaceOutputDetailInterface::present` of the reference (surface.rs:185-192): bytes as they are, then present.
+    unsafe extern "C" fn on_present(user_data: *mut c_void, pixels: *const c_void, width: u32, height: u32, _bytes_per_row: u32) {
+        let window = &*(user_data as *const Mutex<Window>);
+        let mut window = window.lock();
+        let mut target = window.surface.buffer_mut().unwrap();
+        let source = std::slice::from_raw_parts(pixels as *const u8, width as usize * height as usize * 4);
+        let bytes: &mut [u8] = bytemuck::cast_slice_mut(&mut *target);
+        bytes.copy_from_slice(source);
+        target.present().unwrap();
+    }
+
+    impl Surface {
+        pub(super) fn new(instance: Handle<sys::wgb_instance_t>, target: wgpu::SurfaceTargetUnsafe) -> Result<Self, String> {
+            match target {
+                wgpu::SurfaceTargetUnsafe::RawHandle { raw_display_handle, raw_window_handle } => {
+                    let context = softbuffer::Context::new(Display::from(raw_display_handle)).map_err(|e| e.to_string())?;
+                    let surface = softbuffer::Surface::new(&context, WindowHandle::from(raw_window_handle)).map_err(|e| e.to_string())?;
+                    let window = Arc::new(Mutex::new(Window { _context: context, surface }));
+                    let sink = sys::wgb_surface_target { on_present: Some(on_present), user_data: Arc::as_ptr(&window) as *mut c_void };
+                    let handle = create_surface(&instance, &sink);
+                    Ok(Surface { handle, _instance: instance, window, extent: Mutex::new(None) })
+                }
+                _ => Err("Surface not supported".to_owned()),
+            }
+        }
+    }
+
+    fn create_surface(instance: &Handle<sys::wgb_instance_t>, sink: &sys::wgb_surface_target) -> Handle<sys::wgb_surface_t> {
+        let mut out: sys::wgb_surface = ptr::null_mut();
+        check(unsafe { sys::wgb_instance_create_surface(instance.raw(), sink, &mut out) });
+        unsafe { Handle::adopt(out) }
+    }
+
+    impl SurfaceInterface for Surface {
+        fn get_capabilities(&self, adapter: &DispatchAdapter) -> wgpu::SurfaceCapabilities {
+            let adapter = adapter.as_custom::<super::Adapter>().unwrap();
+            let mut caps: sys::wgb_surface_capabilities = unsafe { std::mem::zeroed() };
+            check(unsafe { sys::wgb_surface_get_capabilities(self.handle.raw(), adapter.handle.raw(), &mut caps) });
+            // the library answers what the reference answers (surface.rs:52-72)
+            assert_eq!((caps.formats[0], caps.present_modes[0], caps.alpha_modes[0]),
+                       (sys::WGB_TEXTURE_FORMAT_BGRA8_UNORM, sys::WGB_PRESENT_MODE_IMMEDIATE, sys::WGB_COMPOSITE_ALPHA_MODE_OPAQUE));
+            wgpu::SurfaceCapabilities {
+                formats: vec![wgpu::TextureFormat::Bgra8Unorm],
+                present_modes: vec![wgpu::PresentMode::Immediate],
+                alpha_modes: vec![wgpu::CompositeAlphaMode::Opaque],
+                usages: wgpu::TextureUsages::from_bits_truncate(caps.usages),
+            }
+        }
+
+        fn configure(&self, device: &DispatchDevice, config: &wgpu::SurfaceConfiguration) {
+            let device = device.as_custom::<Device>().unwrap();
+            let view_formats: Vec<u32> = config.view_formats.iter().map(|f| super::convert::texture_format(*f).unwrap_or(u32::MAX)).collect();
+            let c = sys::wgb_surface_configuration {
+                usage: config.usage.bits(),
+                format: super::convert::texture_format(config.format).unwrap_or(u32::MAX),     // not Bgra8Unorm: the library refuses
+                width: config.width,
+                height: config.height,
+                present_mode: sys::WGB_PRESENT_MODE_IMMEDIATE,
+                alpha_mode: sys::WGB_COMPOSITE_ALPHA_MODE_OPAQUE,
+                view_format_count: view_formats.len() as u32,
+                view_formats: view_formats.as_ptr(),
+            };
+            check(unsafe { sys::wgb_surface_configure(self.handle.raw(), device.handle.raw(), &c) });     // panics like the reference's unwrap
+            self.window.lock().surface
+                .resize(NonZero::new(config.width).expect("Surface width must not be zero"),
+                        NonZero::new(config.height).expect("Surface height must not be zero"))
+                .unwrap();
+            *self.extent.lock() = Some((wgpu::Extent3d { width: config.width, height: config.height, depth_or_array_layers: 1 }, config.format));
+        }
+
+        fn get_current_texture(&self) -> (Option<DispatchTexture>, wgpu::SurfaceStatus, DispatchSurfaceOutputDetail) {
+            let mut texture: sys::wgb_texture = ptr::null_mut();
+            let mut status = 0u32;
+            check(unsafe { sys::wgb_surface_get_current_texture(self.handle.raw(), &mut texture, &mut status) });
+            let (size, format) = self.extent.lock().expect("Surface not configured yet");
+            let texture = Texture { handle: unsafe { Handle::adopt(texture) }, size, format };
+            (Some(DispatchTexture::custom(texture)), wgpu::SurfaceStatus::Good,
+             DispatchSurfaceOutputDetail::custom(SurfaceOutputDetail { handle: self.handle.clone() }))
+        }
+    }
+
+    #[derive(Debug)]
+    pub struct SurfaceOutputDetail {
+        handle: Handle<sys::wgb_surface_t>,
+    }
+
+    impl SurfaceOutputDetailInterface for SurfaceOutputDetail {
+        fn present(&self) {
+            check(unsafe { sys::wgb_surface_present(self.handle.raw()) });
+        }
+
+        fn texture_discard(&self) {
+            check(unsafe { sys::wgb_surface_texture_discard(self.handle.raw()) });
+        }
+    }
+
+    // raw-window-handle plumbing, as the reference has it (surface.rs:200-232)
+    struct Display(wgpu::rwh::DisplayHandle<'static>);
+    impl From<wgpu::rwh::RawDisplayHandle> for Display {
+        fn from(value: wgpu::rwh::RawDisplayHandle) -> Self {
+            Self(unsafe { wgpu::rwh::DisplayHandle::borrow_raw(value) })
+        }
+    }
+    impl wgpu::rwh::HasDisplayHandle for Display {
+        fn display_handle(&self) -> Result<wgpu::rwh::DisplayHandle<'_>, wgpu::rwh::HandleError> {
+            Ok(self.0)
+        }
+    }
+    unsafe impl Send for Display {}
+    unsafe impl Sync for Display {}
+
+    struct WindowHandle(wgpu::rwh::WindowHandle<'static>);
+    impl From<wgpu::rwh::RawWindowHandle> for WindowHandle {
+        fn from(value: wgpu::rwh::RawWindowHandle) -> Self {
+            Self(unsafe { wgpu::rwh::WindowHandle::borrow_raw(value) })
+        }
+    }
+    impl wgpu::rwh::HasWindowHandle for WindowHandle {
+        fn window_handle(&self) -> Result<wgpu::rwh::WindowHandle<'_>, wgpu::rwh::HandleError> {
+            Ok(self.0)
+        }
+    }
+    unsafe impl Send for WindowHandle {}
 }

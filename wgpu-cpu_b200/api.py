@@ -158,6 +158,30 @@ class _RenderPassDescriptor(C.Structure):
                 ("depth_stencil_attachment", C.POINTER(_DepthStencilAttachment))]
 
 
+_PRESENT_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32)
+
+
+class _SurfaceTarget(C.Structure):
+    _fields_ = [("on_present", _PRESENT_CALLBACK), ("user_data", C.c_void_p)]
+
+
+class _SurfaceCapabilities(C.Structure):
+    _fields_ = [("format_count", C.c_uint32), ("formats", C.c_uint32 * 4),
+                ("present_mode_count", C.c_uint32), ("present_modes", C.c_uint32 * 4),
+                ("alpha_mode_count", C.c_uint32), ("alpha_modes", C.c_uint32 * 4), ("usages", C.c_uint32)]
+
+
+class _SurfaceConfiguration(C.Structure):
+    _fields_ = [("usage", C.c_uint32), ("format", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("present_mode", C.c_uint32), ("alpha_mode", C.c_uint32),
+                ("view_format_count", C.c_uint32), ("view_formats", C.POINTER(C.c_uint32))]
+
+
+TEXTURE_USAGE = {"copy-src": 1, "copy-dst": 2, "texture-binding": 4, "storage-binding": 8, "render-attachment": 16}
+PRESENT_MODE = {"auto-vsync": 0, "auto-no-vsync": 1, "fifo": 2, "fifo-relaxed": 3, "immediate": 4, "mailbox": 5}
+COMPOSITE_ALPHA_MODE = {"auto": 0, "opaque": 1}
+
+
 class PassStats(C.Structure):
     _fields_ = [("primitives", C.c_uint64), ("fragments", C.c_uint64), ("shaded", C.c_uint64), ("bin_pairs", C.c_uint64),
                 ("big_primitives", C.c_uint64), ("clipped_primitives", C.c_uint64), ("clip_records", C.c_uint64),
@@ -221,12 +245,33 @@ class Instance(_Handle):
         _check(_lib.wgb_instance_request_adapter(self._h, C.byref(h)))
         return Adapter(h)
 
+    def create_surface(self, on_present=None) -> "Surface":
+        """InstanceInterface::create_surface (instance.rs:51-70).  The window is a host pixel sink: `on_present(pixels)` is
+        called by Surface.present with the frame as an (H, W, 4) uint8 view of the window buffer (BGRA bytes)."""
+        surface = Surface(None)
+        target = None
+        if on_present is not None:
+            def _cb(_user, pixels, width, height, bytes_per_row):
+                view = np.ctypeslib.as_array(C.cast(pixels, C.POINTER(C.c_uint8)), shape=(height, bytes_per_row))
+                on_present(view[:, :width * 4].reshape(height, width, 4))
+            surface._callback = _PRESENT_CALLBACK(_cb)        # kept alive as long as the surface
+            target = C.byref(_SurfaceTarget(surface._callback, None))
+        h = C.c_void_p()
+        _check(_lib.wgb_instance_create_surface(self._h, target, C.byref(h)))
+        surface._h = h
+        return surface
+
 
 class Adapter(_Handle):
     def get_info(self) -> dict:
         info = _AdapterInfo()
         _check(_lib.wgb_adapter_get_info(self._h, C.byref(info)))
         return {"name": info.name.decode(), "device_type": info.device_type, "cuda_device_count": info.cuda_device_count}
+
+    def is_surface_supported(self, surface: "Surface") -> bool:
+        out = C.c_int32()
+        _check(_lib.wgb_adapter_is_surface_supported(self._h, surface._h, C.byref(out)))
+        return bool(out.value)
 
     def request_device(self, cuda_device: int = CUDA_DEVICE_CURRENT, band_rank: int = 0, band_count: int = 1, features: int = 0):
         """`features`: FEATURE[...] bits -- WebGPU behaviour the reference accepts and ignores; 0 = parity mode."""
@@ -237,6 +282,50 @@ class Adapter(_Handle):
         queue = Queue(q)
         queue.device = dev
         return dev, queue
+
+
+class Surface(_Handle):
+    """SurfaceInterface + SurfaceOutputDetailInterface (surface.rs:51-198)."""
+    _callback = None
+
+    def get_capabilities(self, adapter: "Adapter") -> dict:
+        caps = _SurfaceCapabilities()
+        _check(_lib.wgb_surface_get_capabilities(self._h, adapter._h, C.byref(caps)))
+        inv = lambda table, values, n: [next(k for k, v in table.items() if v == values[i]) for i in range(n)]   # noqa: E731
+        return {"formats": inv(TEXTURE_FORMAT, caps.formats, caps.format_count),
+                "present_modes": inv(PRESENT_MODE, caps.present_modes, caps.present_mode_count),
+                "alpha_modes": inv(COMPOSITE_ALPHA_MODE, caps.alpha_modes, caps.alpha_mode_count),
+                "usages": caps.usages}
+
+    def configure(self, device: "Device", width: int, height: int, format: str = "bgra8unorm", usage: int = 16,
+                  present_mode: str = "immediate", alpha_mode: str = "opaque", view_formats: Sequence[str] = ()):
+        vf = (C.c_uint32 * max(len(view_formats), 1))(*[TEXTURE_FORMAT[f] for f in view_formats])
+        cfg = _SurfaceConfiguration(usage, TEXTURE_FORMAT[format], width, height, PRESENT_MODE[present_mode],
+                                    COMPOSITE_ALPHA_MODE[alpha_mode], len(view_formats), C.cast(vf, C.POINTER(C.c_uint32)))
+        _check(_lib.wgb_surface_configure(self._h, device._h, C.byref(cfg)))
+        self._extent = (width, height, format)
+
+    def get_current_texture(self) -> "Texture":
+        h, status = C.c_void_p(), C.c_uint32()
+        _check(_lib.wgb_surface_get_current_texture(self._h, C.byref(h), C.byref(status)))
+        t = Texture(h)
+        t.width, t.height, t.format = self._extent
+        t.layers = 1
+        t.status = status.value
+        return t
+
+    def present(self):
+        _check(_lib.wgb_surface_present(self._h))
+
+    def texture_discard(self):
+        _check(_lib.wgb_surface_texture_discard(self._h))
+
+    def window_buffer(self):
+        """(pixels as an (H, W, 4) uint8 view of the window buffer -- valid until the next configure --, presents so far)"""
+        p, n, k = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        _check(_lib.wgb_surface_get_window_buffer(self._h, C.byref(p), C.byref(n), C.byref(k)))
+        w, h, _ = self._extent
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(h, w, 4)), k.value
 
 
 class Buffer(_Handle):

@@ -583,6 +583,26 @@ struct Texture : Object {
     }
 };
 struct TextureView : Object { Ref<Texture> texture; uint32_t base_layer = 0; };
+// surface.rs:24-27,148-166: the window (here: a page-locked host pixel buffer + a present callback) and the current
+// configuration's one texture
+struct Surface : Object {
+    std::mutex mu;
+    wgb_surface_target target{};
+    bool configured = false;
+    wgb_surface_configuration config{};
+    Ref<Device> device;
+    Ref<Texture> texture;
+    void* window = nullptr;          // cudaMallocHost: width * height * 4 bytes
+    uint64_t window_size = 0;
+    uint64_t presents = 0;
+    bool window_pinned = false;
+    void drop_window() {
+        if (window && window_pinned) { cudaSetDevice(device->ordinal); cudaFreeHost(window); }
+        else if (window) free(window);
+        window = nullptr; window_size = 0; window_pinned = false;
+    }
+    ~Surface() override { drop_window(); }
+};
 struct Sampler : Object { wgb_sampler_descriptor desc{}; };
 
 struct ShaderModule : Object {
@@ -1184,7 +1204,7 @@ void execute_draw(Device* dev, PassState& st, PassTargets& tg, const SubCommand&
             if (vcache_n) {
                 // the cache holds every instance of the draw, so it is filled once, by the first batch
                 if (base == 0) launch_on(dev, gs, ks->vertex, dim3((uint32_t)(((uint64_t)vcache_n * sc.instance_count + 255) / 256)), dim3(256), &d);
-                launch_on(dev, gs, ks->geometry_cached, dim3(((np >= WGB_GEOMETRY_PAIRED_MIN ? (np + 1) / 2 : np) + 255) / 256), dim3(256), &d);      // two primitives per thread of a large batch
+                launch_on(dev, gs, ks->geometry_cached, dim3((np + 255) / 256), dim3(256), &d);
             } else launch_on(dev, gs, ks->geometry, dim3(gblocks), dim3(256), &d);
             launch_on(dev, gs, ks->clip, dim3(std::min<uint32_t>(std::max<uint32_t>((np + 127) / 128, 148), 148 * 8)), dim3(128), &d);      // (the kernel deals its list out over the warps it finds)
             if (!bin_cap) {
@@ -2638,6 +2658,123 @@ wgb_status wgb_device_get_stream(wgb_device device, void** out_stream) {
         Device* dev = from_handle<Device>(device, "device");
         REQUIRE(out_stream, "out is null");
         *out_stream = (void*)dev->joined();
+    });
+}
+
+// ---- surface / present (surface.rs) ----
+wgb_status wgb_instance_create_surface(wgb_instance instance, const wgb_surface_target* target, wgb_surface* out) {
+    return guarded([&] {
+        from_handle<Instance>(instance, "instance");
+        REQUIRE(out, "out is null");
+        Surface* s = new Surface();
+        if (target) s->target = *target;
+        *out = to_handle<wgb_surface>(s);
+    });
+}
+wgb_status wgb_adapter_is_surface_supported(wgb_adapter adapter, wgb_surface surface, int32_t* out_supported) {
+    return guarded([&] {
+        from_handle<Adapter>(adapter, "adapter");
+        REQUIRE(out_supported, "out is null");
+        // adapter.rs:44-54: `surface.as_custom::<Surface>().is_some()`
+        *out_supported = surface && dynamic_cast<Surface*>(reinterpret_cast<Object*>(surface)) ? 1 : 0;
+    });
+}
+wgb_status wgb_surface_get_capabilities(wgb_surface surface, wgb_adapter adapter, wgb_surface_capabilities* out) {
+    return guarded([&] {
+        from_handle<Surface>(surface, "surface");
+        from_handle<Adapter>(adapter, "adapter");
+        REQUIRE(out, "out is null");
+        memset(out, 0, sizeof(*out));
+        out->format_count = 1; out->formats[0] = WGB_TEXTURE_FORMAT_BGRA8_UNORM;               // surface.rs:61, 242
+        out->present_mode_count = 1; out->present_modes[0] = WGB_PRESENT_MODE_IMMEDIATE;        // surface.rs:64
+        out->alpha_mode_count = 1; out->alpha_modes[0] = WGB_COMPOSITE_ALPHA_MODE_OPAQUE;       // surface.rs:66
+        out->usages = WGB_TEXTURE_USAGE_RENDER_ATTACHMENT;                                      // surface.rs:68
+    });
+}
+wgb_status wgb_surface_configure(wgb_surface surface, wgb_device device, const wgb_surface_configuration* config) {
+    return guarded([&] {
+        Surface* s = from_handle<Surface>(surface, "surface");
+        Device* dev = from_handle<Device>(device, "device");
+        REQUIRE(config, "config is null");
+        // check_surface_config (surface.rs:234-257)
+        REQUIRE(config->format == WGB_TEXTURE_FORMAT_BGRA8_UNORM, "Unsupported surface texture format: %u", config->format);
+        REQUIRE(config->view_format_count == 0 || config->view_formats, "view_formats is null");
+        for (uint32_t i = 0; i < config->view_format_count; i++)
+            REQUIRE(config->view_formats[i] == WGB_TEXTURE_FORMAT_BGRA8_UNORM, "Unsupported surface texture format: %u", config->view_formats[i]);
+        REQUIRE(config->width != 0, "Surface width must not be zero");         // surface.rs:105
+        REQUIRE(config->height != 0, "Surface height must not be zero");       // surface.rs:106
+        wgb_texture_descriptor td{};
+        td.width = config->width; td.height = config->height; td.depth_or_array_layers = 1;
+        td.mip_level_count = 1; td.sample_count = 1; td.format = config->format; td.usage = config->usage;
+        wgb_texture th = nullptr;
+        const wgb_status st = wgb_device_create_texture(device, &td, &th);      // Texture::new (surface.rs:94-101): zeroed
+        if (st != WGB_OK) throw Error(st, g_last_error);
+        Ref<Texture> tex;
+        tex.p = from_handle<Texture>(th, "texture");      // takes over the handle's reference
+        std::lock_guard<std::mutex> lk(s->mu);
+        s->configured = false;
+        s->drop_window();
+        s->device = Ref<Device>(dev);
+        s->texture = tex;
+        s->config = *config;
+        s->config.view_formats = nullptr; s->config.view_format_count = 0;
+        s->window_size = tex->size;
+        if (dev->compile_only) {
+            s->window = calloc(1, s->window_size);
+            REQUIRE(s->window, "out of host memory");
+        } else {
+            std::lock_guard<std::recursive_mutex> dl(dev->mu);
+            dev->make_current();
+            CUDA_CHECK(cudaMallocHost(&s->window, s->window_size));     // inner.surface.resize (surface.rs:103-109)
+            s->window_pinned = true;
+            memset(s->window, 0, s->window_size);
+        }
+        s->configured = true;
+    });
+}
+wgb_status wgb_surface_get_current_texture(wgb_surface surface, wgb_texture* out, uint32_t* out_status) {
+    return guarded([&] {
+        Surface* s = from_handle<Surface>(surface, "surface");
+        REQUIRE(out, "out is null");
+        std::lock_guard<std::mutex> lk(s->mu);
+        REQUIRE(s->configured, "Surface not configured yet");            // surface.rs:127-130
+        s->texture->rc.fetch_add(1);                                     // `configured.buffer.clone()`
+        *out = to_handle<wgb_texture>(s->texture.get());
+        if (out_status) *out_status = WGB_SURFACE_STATUS_GOOD;
+    });
+}
+wgb_status wgb_surface_present(wgb_surface surface) {
+    return guarded([&] {
+        Surface* s = from_handle<Surface>(surface, "surface");
+        std::lock_guard<std::mutex> lk(s->mu);
+        REQUIRE(s->configured, "Surface not configured yet");            // surface.rs:174-177
+        Texture* t = s->texture.get();
+        Device* dev = s->device.get();
+        if (dev->compile_only) fail(WGB_ERROR_DEVICE, "a compile-only device has no texture storage");
+        {
+            // `wait.wait()` + `buffer.read()` (surface.rs:179-183): everything submitted so far has written the texture
+            std::lock_guard<std::recursive_mutex> dl(dev->mu);
+            dev->make_current();
+            settle(dev);
+            CUDA_CHECK(cudaMemcpyAsync(s->window, t->dptr, t->size, cudaMemcpyDeviceToHost, dev->joined()));   // target.copy_from_slice(&*source)
+            CUDA_CHECK(cudaStreamSynchronize(dev->joined()));
+        }
+        s->presents++;
+        if (s->target.on_present)                                        // `buffer_mut().present()` (surface.rs:192)
+            s->target.on_present(s->target.user_data, s->window, t->desc.width, t->desc.height, t->desc.width * t->bpp);
+    });
+}
+wgb_status wgb_surface_texture_discard(wgb_surface surface) {
+    return guarded([&] { from_handle<Surface>(surface, "surface"); });   // surface.rs:195-197: nop
+}
+wgb_status wgb_surface_get_window_buffer(wgb_surface surface, const void** out_pixels, uint64_t* out_size, uint64_t* out_presents) {
+    return guarded([&] {
+        Surface* s = from_handle<Surface>(surface, "surface");
+        std::lock_guard<std::mutex> lk(s->mu);
+        REQUIRE(s->configured, "Surface not configured yet");
+        if (out_pixels) *out_pixels = s->window;
+        if (out_size) *out_size = s->window_size;
+        if (out_presents) *out_presents = s->presents;
     });
 }
 

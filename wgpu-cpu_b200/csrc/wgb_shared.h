@@ -33,8 +33,6 @@ typedef uint64_t wgb_u64;
 // "big" list that every tile scans instead of into per-tile bins; this bounds the bin
 // storage at WGB_SMALL_MAX_TILES entries per primitive
 #define WGB_SMALL_MAX_TILES 4
-// the cached geometry kernel takes two primitives per thread from this batch size on (host: the grid; device: the split)
-#define WGB_GEOMETRY_PAIRED_MIN (1u << 20)
 // upper bound on sub-triangles the six-plane clipper can emit for one triangle
 // (wgpu-cpu/src/render_pass/clipper.rs:737-739 "2**6")
 #define WGB_MAX_CLIP_TRIS 64
