@@ -93,5 +93,5 @@ def test_backend_crate_matches_the_sys_crate():
     for trait in ("InstanceInterface", "AdapterInterface", "DeviceInterface", "QueueInterface", "BufferInterface", "BufferMappedRangeInterface",
                   "TextureInterface", "TextureViewInterface", "SamplerInterface", "ShaderModuleInterface", "BindGroupLayoutInterface",
                   "PipelineLayoutInterface", "BindGroupInterface", "RenderPipelineInterface", "CommandEncoderInterface",
-                  "CommandBufferInterface", "RenderPassInterface"):
+                  "CommandBufferInterface", "RenderPassInterface", "SurfaceInterface", "SurfaceOutputDetailInterface"):
         assert re.search(r"impl %s for \w+" % trait, src), trait
