@@ -111,9 +111,9 @@ def main():
     w("Commands (one `gpurun` call on a fresh B200, `tools/gpu.sh`):\n\n```\n"
       "python bench.py --steps 50 --warmup 5 > gpurun_out/bench_final.json\n"
       "python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.json\n"
-      "ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_final.csv \\\n"
+      "ncu --metrics gpu__time_duration.sum --clock-control none -c 75 --csv --log-file gpurun_out/launches_final.csv \\\n"
       "    python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e\n"
-      "(cd wgpu-cpu_b200/csrc && ncu --set full --import-source on --clock-control none -k regex:wgb_ -s 12 -c 4 \\\n"
+      "(cd wgpu-cpu_b200/csrc && ncu --set full --import-source on --clock-control none -k regex:wgb_ -s 15 -c 5 \\\n"
       "    -o gpurun_out/prof_final python ../../bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e)\n"
       "python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\\n"
       "    bench.py --gpus N --steps 50 --warmup 5        # N = 2, 4, 8 (gpurun --gpus 8)\n"
