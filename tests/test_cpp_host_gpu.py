@@ -37,6 +37,31 @@ def test_cpp_host_renders_hello_mesh(tmp_path):
     assert np.array_equal(_decode_png(out + ".png"), color)
 
 
+def test_cpp_host_presents_hello_mesh_on_a_surface(tmp_path):
+    """The windowed flow of hello_mesh.rs (:236-250, 380-410: create_surface, get_capabilities, formats[0], configure,
+    get_current_texture -> pass -> submit -> present) against the headless surface: the window receives the oracle's
+    Bgra8Unorm frame."""
+    from oracle import pyoracle
+    scene = S.hello_mesh(256, 192)
+    scene.color_format = "bgra8unorm"
+    ref = pyoracle.render(scene, want_coverage=False)
+    (tmp_path / "v.bin").write_bytes(scene.vertex_buffers[0].tobytes())
+    (tmp_path / "i.bin").write_bytes(scene.index_data.astype(np.uint32).tobytes())
+    (tmp_path / "u.bin").write_bytes(np.ascontiguousarray(scene.bindings[(0, 0)][1]).tobytes())
+    out = str(tmp_path / "frame")
+    exe = os.path.join(ROOT, "examples", "hello_mesh")
+    if os.environ.get("WGB_CUSIM") == "1":
+        from tests.cusim import build as cusim_build
+        exe = cusim_build.build_example()
+    p = subprocess.run([exe, os.path.join(ROOT, "wgpu-cpu_b200", "shaders", "mesh_vertex_color.wgsl"),
+                        str(tmp_path / "v.bin"), str(tmp_path / "i.bin"), str(tmp_path / "u.bin"), "256", "192", out, "3"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "presented 3 frames of 256x192" in p.stdout
+    window = np.fromfile(out + ".window", dtype=np.uint8).reshape(192, 256, 4)
+    assert np.array_equal(window, ref.color)
+
+
 def test_cpp_host_renders_hello_texture(tmp_path):
     """examples/hello_texture (the reference's hello_texture.rs flow: texture from image bytes, Repeat / Nearest sampler, a
     second bind group) renders the textured bunny bit-exactly."""
