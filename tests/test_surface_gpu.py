@@ -70,3 +70,30 @@ def test_reconfigure_resizes_the_window(ctx):
         SceneRenderer(dev, queue, scene, target=surface.get_current_texture()).render()
         surface.present()
         assert np.array_equal(surface.window_buffer()[0], pyoracle.render(scene).color)
+
+
+def test_a_multisample_state_is_carried_and_not_applied(ctx):
+    """SURVEY 8 f.4, second half: the reference keeps `MultisampleState` in the pipeline (pipeline.rs:67,98) and has the
+    WebGPU sample positions in a table (raster.rs:45-63), but its rasteriser emits `sample_index: None` for every fragment
+    (raster.rs:213,259,351) -- one sample at the pixel -- so a count of 4 renders the single-sample frame.  So does this."""
+    _, _, dev, queue = ctx
+    scene = scenes.hello_mesh(96, 64)
+    ref = pyoracle.render(scene)
+    scene.multisample_count = 4
+    r = SceneRenderer(dev, queue, scene)
+    r.render()
+    f = r.read()
+    assert np.array_equal(f.color, ref.color) and np.array_equal(f.depth.view(np.uint32), ref.depth.view(np.uint32))
+
+
+def test_the_present_callback_may_ask_for_the_next_texture(ctx):
+    """(A window loop that requests its next frame from inside the present notification must not deadlock.)"""
+    inst, _, dev, queue = ctx
+    nxt = []
+    surface = inst.create_surface(lambda pixels: nxt.append(surface.get_current_texture()))
+    scene = _bgra(scenes.colored_triangle("default", 64, 48))
+    surface.configure(dev, 64, 48)
+    SceneRenderer(dev, queue, scene, target=surface.get_current_texture()).submit()
+    surface.present()
+    assert len(nxt) == 1 and (nxt[0].width, nxt[0].height) == (64, 48)
+    assert np.array_equal(nxt[0].read(), pyoracle.render(scene).color)

@@ -586,7 +586,7 @@ struct TextureView : Object { Ref<Texture> texture; uint32_t base_layer = 0; };
 // surface.rs:24-27,148-166: the window (here: a page-locked host pixel buffer + a present callback) and the current
 // configuration's one texture
 struct Surface : Object {
-    std::mutex mu;
+    std::recursive_mutex mu;         // (recursive: the present callback may ask the surface for its next texture)
     wgb_surface_target target{};
     bool configured = false;
     wgb_surface_configuration config{};
@@ -2711,7 +2711,7 @@ wgb_status wgb_surface_configure(wgb_surface surface, wgb_device device, const w
         if (st != WGB_OK) throw Error(st, g_last_error);
         Ref<Texture> tex;
         tex.p = from_handle<Texture>(th, "texture");      // takes over the handle's reference
-        std::lock_guard<std::mutex> lk(s->mu);
+        std::lock_guard<std::recursive_mutex> lk(s->mu);
         s->configured = false;
         s->drop_window();
         s->device = Ref<Device>(dev);
@@ -2736,7 +2736,7 @@ wgb_status wgb_surface_get_current_texture(wgb_surface surface, wgb_texture* out
     return guarded([&] {
         Surface* s = from_handle<Surface>(surface, "surface");
         REQUIRE(out, "out is null");
-        std::lock_guard<std::mutex> lk(s->mu);
+        std::lock_guard<std::recursive_mutex> lk(s->mu);
         REQUIRE(s->configured, "Surface not configured yet");            // surface.rs:127-130
         s->texture->rc.fetch_add(1);                                     // `configured.buffer.clone()`
         *out = to_handle<wgb_texture>(s->texture.get());
@@ -2746,7 +2746,7 @@ wgb_status wgb_surface_get_current_texture(wgb_surface surface, wgb_texture* out
 wgb_status wgb_surface_present(wgb_surface surface) {
     return guarded([&] {
         Surface* s = from_handle<Surface>(surface, "surface");
-        std::lock_guard<std::mutex> lk(s->mu);
+        std::lock_guard<std::recursive_mutex> lk(s->mu);
         REQUIRE(s->configured, "Surface not configured yet");            // surface.rs:174-177
         Texture* t = s->texture.get();
         Device* dev = s->device.get();
@@ -2770,7 +2770,7 @@ wgb_status wgb_surface_texture_discard(wgb_surface surface) {
 wgb_status wgb_surface_get_window_buffer(wgb_surface surface, const void** out_pixels, uint64_t* out_size, uint64_t* out_presents) {
     return guarded([&] {
         Surface* s = from_handle<Surface>(surface, "surface");
-        std::lock_guard<std::mutex> lk(s->mu);
+        std::lock_guard<std::recursive_mutex> lk(s->mu);
         REQUIRE(s->configured, "Surface not configured yet");
         if (out_pixels) *out_pixels = s->window;
         if (out_size) *out_size = s->window_size;

@@ -83,7 +83,8 @@ class SceneRenderer:
             depth_stencil=depth_state,
             targets=[s.color_format if s.color_write_mask == 15 and not s.blend
                      else {"format": s.color_format, "write_mask": s.color_write_mask, "blend": s.blend}] +
-                    [fmt for fmt, _ in (s.extra_targets or [])])
+                    [fmt for fmt, _ in (s.extra_targets or [])],
+            multisample_count=getattr(s, "multisample_count", 1))      # carried and never applied, like the reference's (pipeline.rs:98)
         self.extra_targets = [device.create_texture(s.width, s.height, fmt) for fmt, _ in (s.extra_targets or [])]
         self.extra_views = [t.create_view() for t in self.extra_targets]
         if targets:
