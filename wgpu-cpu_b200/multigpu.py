@@ -13,8 +13,10 @@ def band_rows(height: int, rank: int, count: int, tile_h: int = TILE_H):
     """First and one-past-last pixel row of band `rank` (must equal wgb_device_get_band_rows)."""
     tiles = (height + tile_h - 1) // tile_h
     q, rem = divmod(tiles, max(count, 1))
-    t0 = rank * q + min(rank, rem)
-    t1 = t0 + q + (1 if rank < rem else 0)
+    lo = (max(count, 1) - rem) // 2          # the rows left over go to the middle bands (the outer ones hold the clipped primitives)
+    extra_before = lambda k: min(max(k - lo, 0), rem)      # noqa: E731 -- taller bands among bands 0 .. k-1
+    t0 = rank * q + extra_before(rank)
+    t1 = (rank + 1) * q + extra_before(rank + 1)
     return min(t0 * tile_h, height), min(t1 * tile_h, height)
 
 
