@@ -251,3 +251,40 @@ def test_multiple_colour_targets_compile_offline(offline):
                                        depth_stencil={"depth_compare": compare, "depth_write_enabled": True})
         src = p.get_source()
         assert "#define WGB_NUM_COLOR 3" in src and f"#define WGB_RESOLVE {resolve}" in src and "#define WGB_FS_COLOR_MASK 7" in src
+
+
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """The boundary is a C ABI: include/wgpu_b200.h compiles as C99 (-pedantic), and a host written in C links against
+    the library and walks instance -> adapter -> surface without a GPU (no compute call)."""
+    import subprocess
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "wgpu_b200.h"
+int main(void) {
+    wgb_instance inst = NULL; wgb_adapter adapter = NULL; wgb_surface surface = NULL;
+    wgb_surface_capabilities caps; wgb_adapter_info info; int32_t ok = 0; wgb_texture t = NULL; uint32_t st = 0;
+    if (wgb_create_instance(NULL, &inst) != WGB_OK) return 1;
+    if (wgb_instance_request_adapter(inst, &adapter) != WGB_OK) return 2;
+    if (wgb_adapter_get_info(adapter, &info) != WGB_OK) return 3;
+    if (wgb_instance_create_surface(inst, NULL, &surface) != WGB_OK) return 4;
+    if (wgb_adapter_is_surface_supported(adapter, surface, &ok) != WGB_OK || !ok) return 5;
+    if (wgb_surface_get_capabilities(surface, adapter, &caps) != WGB_OK) return 6;
+    if (caps.format_count != 1 || caps.formats[0] != WGB_TEXTURE_FORMAT_BGRA8_UNORM || caps.present_modes[0] != WGB_PRESENT_MODE_IMMEDIATE) return 7;
+    if (wgb_surface_get_current_texture(surface, &t, &st) != WGB_ERROR_VALIDATION) return 8;       /* not configured yet */
+    if (!strstr(wgb_last_error(), "Surface not configured yet")) return 9;
+    printf("%s\n", wgb_version());
+    wgb_release((wgb_object)surface); wgb_release((wgb_object)adapter); wgb_release((wgb_object)inst);
+    return 0;
+}
+''')
+    exe = tmp_path / "host"
+    lib_dir = os.path.dirname(api.LIB_PATH)
+    lib = os.path.basename(api.LIB_PATH)[3:-3]
+    p = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{os.path.join(ROOT, 'include')}", str(src), "-o", str(exe),
+                        f"-L{lib_dir}", f"-l{lib}", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    assert "sm_100a" in r.stdout
