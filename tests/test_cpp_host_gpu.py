@@ -113,3 +113,23 @@ def test_cpp_host_renders_hello_shader(tmp_path):
     assert np.array_equal(_decode_png(out + ".png"), color)
     grey = np.clip(np.trunc(depth * np.float32(255.0)), 0, 255).astype(np.uint8)
     assert np.array_equal(_decode_png(out + ".depth.png")[:, :, 0], grey)
+
+
+def test_cpp_host_presents_hello_shader_on_a_surface(tmp_path):
+    """hello_shader's windowed flow (hello_shader.rs:168-185, 330-350) against the headless surface: a draw without vertex
+    or index buffers into the surface's Bgra8Unorm texture reaches the window as the oracle renders it."""
+    from oracle import pyoracle
+    scene = S.colored_triangle("draw_backwards_no_cull", 200, 120)
+    scene.color_format = "bgra8unorm"
+    ref = pyoracle.render(scene, want_coverage=False)
+    out = str(tmp_path / "frame")
+    exe = os.path.join(ROOT, "examples", "hello_shader")
+    if os.environ.get("WGB_CUSIM") == "1":
+        from tests.cusim import build as cusim_build
+        exe = cusim_build.build_example("hello_shader")
+    p = subprocess.run([exe, os.path.join(ROOT, "wgpu-cpu_b200", "shaders", "index_triangle.wgsl"), "3", "200", "120", out, "2"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "presented 2 frames" in p.stdout
+    window = np.fromfile(out + ".window", dtype=np.uint8).reshape(120, 200, 4)
+    assert np.array_equal(window, ref.color)
