@@ -3,7 +3,11 @@
 // Queue::write_texture, hello_texture.rs:184-206), a Repeat / Nearest sampler (hello_texture.rs:209-217) and a second
 // bind group {texture view, sampler} for the fragment stage's textureSample.
 //
-//   hello_texture <shader.wgsl> <vertices.bin> <indices.bin> <uniform.bin> <texture.rgba> <tex-width> <tex-height> <width> <height> <out-prefix>
+//   hello_texture <shader.wgsl> <vertices.bin> <indices.bin> <uniform.bin> <texture.rgba> <tex-width> <tex-height> <width> <height> <out-prefix> [frames]
+//
+// With `frames`: the windowed flow of hello_texture.rs (:328-345, the redraw handler) against the library's headless surface
+// -- create_surface, formats[0], configure, and per frame get_current_texture -> pass -> submit -> present; the last frame
+// the window received goes to <out-prefix>.window (raw BGRA texels).
 //
 // vertices: {pos vec4f, uv vec2f} (24 bytes, hello_texture.rs:651-659); indices: u32; uniform: the 64-byte camera matrix;
 // texture: tex-width x tex-height RGBA8 texels.  Writes <out-prefix>.png, .rgba and .depth like hello_mesh.
@@ -25,8 +29,15 @@ static void write_file(const std::string& path, const void* data, size_t size) {
     f.write(static_cast<const char*>(data), (std::streamsize)size);
 }
 
+struct Window { std::vector<uint8_t> pixels; uint32_t presents = 0; };
+static void on_present(void* user_data, const void* pixels, uint32_t, uint32_t height, uint32_t bytes_per_row) {
+    Window* w = static_cast<Window*>(user_data);
+    w->presents++;
+    w->pixels.assign(static_cast<const uint8_t*>(pixels), static_cast<const uint8_t*>(pixels) + (size_t)bytes_per_row * height);
+}
+
 int main(int argc, char** argv) {
-    if (argc != 11) {
+    if (argc != 11 && argc != 12) {
         std::fprintf(stderr, "usage: %s shader.wgsl vertices.bin indices.bin uniform.bin texture.rgba tex-width tex-height width height out-prefix\n", argv[0]);
         return 2;
     }
@@ -36,6 +47,7 @@ int main(int argc, char** argv) {
         const uint32_t tex_w = (uint32_t)std::atoi(argv[6]), tex_h = (uint32_t)std::atoi(argv[7]);
         const uint32_t width = (uint32_t)std::atoi(argv[8]), height = (uint32_t)std::atoi(argv[9]);
         const std::string out = argv[10];
+        const int frames = argc == 12 ? std::atoi(argv[11]) : 0;
         if (texels.size() != (size_t)tex_w * tex_h * 4) { std::fprintf(stderr, "texture file does not hold %u x %u RGBA8 texels\n", tex_w, tex_h); return 2; }
 
         wgb::Instance instance = wgb::instance();
@@ -70,11 +82,40 @@ int main(int argc, char** argv) {
         pd.vertex_buffers = {layout};
         pd.front_face = WGB_FRONT_FACE_CW; pd.cull_mode = WGB_CULL_MODE_BACK;
         pd.has_depth_stencil = true;
-        pd.targets = {wgb::color_target(WGB_TEXTURE_FORMAT_RGBA8_UNORM_SRGB)};
+        Window window;
+        wgb::Surface surface;
+        uint32_t target_format = WGB_TEXTURE_FORMAT_RGBA8_UNORM_SRGB;
+        if (frames > 0) {
+            surface = instance.create_surface(on_present, &window);
+            target_format = surface.get_capabilities(adapter.get()).formats[0];      // hello_texture.rs:332-333
+            surface.configure(device, width, height, target_format);
+        }
+        pd.targets = {wgb::color_target(target_format)};
         wgb::RenderPipeline pipeline = device.create_render_pipeline(pd);
 
-        wgb::Texture target = device.create_texture(width, height, WGB_TEXTURE_FORMAT_RGBA8_UNORM_SRGB);
         wgb::Texture depth = device.create_texture(width, height, WGB_TEXTURE_FORMAT_DEPTH32_FLOAT);
+        for (int frame = 0; frame < frames; frame++) {
+            wgb::Texture frame_texture = surface.get_current_texture();
+            wgb::CommandEncoder encoder = device.create_command_encoder();
+            {
+                wgb::DepthAttachment da{depth.create_view(), true, 1.0f};
+                wgb::RenderPass pass = encoder.begin_render_pass({wgb::ColorAttachment{frame_texture.create_view(), true, {0.0, 0.0, 0.0, 1.0}}}, &da);
+                pass.set_pipeline(pipeline);
+                pass.set_bind_group(0, camera_group);
+                pass.set_bind_group(1, texture_group);
+                pass.set_index_buffer(index_buffer, WGB_INDEX_FORMAT_UINT32);
+                pass.set_vertex_buffer(0, vertex_buffer);
+                pass.draw_indexed(0, (uint32_t)(indices.size() / 4));
+            }
+            queue.submit({encoder.finish()});
+            surface.present();
+        }
+        if (frames > 0) {
+            std::cout << "presented " << window.presents << " frames\n";
+            write_file(out + ".window", window.pixels.data(), window.pixels.size());
+            return 0;
+        }
+        wgb::Texture target = device.create_texture(width, height, WGB_TEXTURE_FORMAT_RGBA8_UNORM_SRGB);
 
         wgb::CommandEncoder encoder = device.create_command_encoder();
         {

@@ -133,3 +133,29 @@ def test_cpp_host_presents_hello_shader_on_a_surface(tmp_path):
     assert "presented 2 frames" in p.stdout
     window = np.fromfile(out + ".window", dtype=np.uint8).reshape(120, 200, 4)
     assert np.array_equal(window, ref.color)
+
+
+def test_cpp_host_presents_hello_texture_on_a_surface(tmp_path):
+    """hello_texture's windowed flow against the headless surface: the textured bunny (sampled texture, Repeat / Nearest
+    sampler, two bind groups) through the surface's Bgra8Unorm texture, byte-exact in the window."""
+    from oracle import pyoracle
+    scene = S.hello_texture(240, 160)
+    scene.color_format = "bgra8unorm"
+    ref = pyoracle.render(scene, want_coverage=False)
+    image = np.ascontiguousarray(scene.bindings[(1, 0)][1])
+    (tmp_path / "v.bin").write_bytes(scene.vertex_buffers[0].tobytes())
+    (tmp_path / "i.bin").write_bytes(scene.index_data.astype(np.uint32).tobytes())
+    (tmp_path / "u.bin").write_bytes(np.ascontiguousarray(scene.bindings[(0, 0)][1]).tobytes())
+    (tmp_path / "t.rgba").write_bytes(image.tobytes())
+    out = str(tmp_path / "frame")
+    exe = os.path.join(ROOT, "examples", "hello_texture")
+    if os.environ.get("WGB_CUSIM") == "1":
+        from tests.cusim import build as cusim_build
+        exe = cusim_build.build_example("hello_texture")
+    p = subprocess.run([exe, os.path.join(ROOT, "wgpu-cpu_b200", "shaders", "mesh_textured.wgsl"), str(tmp_path / "v.bin"), str(tmp_path / "i.bin"),
+                        str(tmp_path / "u.bin"), str(tmp_path / "t.rgba"), str(image.shape[1]), str(image.shape[0]), "240", "160", out, "2"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "presented 2 frames" in p.stdout
+    window = np.fromfile(out + ".window", dtype=np.uint8).reshape(160, 240, 4)
+    assert np.array_equal(window, ref.color)
